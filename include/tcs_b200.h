@@ -1,0 +1,159 @@
+/*
+ * tcs_b200.h — C-ABI of the B200-native cost-volume hot path of TC-Stereo.
+ *
+ * One shared library (libtcs_b200.so, hand-written sm_100a CUDA) exports the entry points below.
+ * Every entry point
+ *   - takes raw DEVICE pointers, plain ints/floats and the CUDA stream to launch on (as void*:
+ *     a cudaStream_t), never a torch type;
+ *   - allocates nothing and frees nothing: the caller owns every buffer, scratch included;
+ *   - never synchronises the host with the device;
+ *   - returns 0 on success, a negative TCS_E_* code for a rejected argument, or a positive
+ *     cudaError_t value when a launch failed.  tcs_last_error() gives the text (thread-local).
+ *
+ * "ref:" comments cite the reference interface each function replaces, relative to the upstream
+ * repository root (jiaxiZeng/Temporally-Consistent-Stereo-Matching).
+ *
+ * Layouts (all row-major, innermost last):
+ *   fmap        [B, C, H, W]        fp32   the reference's NCHW feature maps
+ *   operands    [B, H, W, C]        16-bit the L2-normalised features, channels last (K-major GEMM operands)
+ *   level l     [B, H, W1, W2 >> l] fp32   correlation pyramid level l  (ref: corr_pyramid[l] viewed 4-D)
+ *   lookup out  [B, L*(2r+1), H, W1] fp32  (ref: CorrBlock1D.__call__ result)
+ */
+#ifndef TCS_B200_H
+#define TCS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCS_ABI_VERSION 1
+
+/* argument errors (negative); CUDA launch errors are returned as positive cudaError_t values */
+#define TCS_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported combination */
+#define TCS_E_SHAPE    (-2)   /* shape outside what the kernel supports (see each function)  */
+#define TCS_E_ALIGN    (-3)   /* pointer not aligned as required                              */
+#define TCS_E_DRIVER   (-4)   /* cuTensorMapEncodeTiled unavailable or failed                 */
+
+/* precision of the tensor-core correlation build */
+#define TCS_PREC_BF16    0    /* one bf16 pass, fp32 accumulate (north_star's fast mode)      */
+#define TCS_PREC_BF16X3  1    /* hi/lo split: hi*hi + hi*lo + lo*hi, fp32-level accuracy      */
+#define TCS_PREC_FP16    2    /* one fp16 pass on 2^8-scaled unit vectors                     */
+#define TCS_PREC_FP16X3  3    /* fp16 hi/lo split                                             */
+
+#define TCS_MAX_LEVELS   4
+#define TCS_MAX_RADIUS   8
+
+int         tcs_abi_version(void);
+const char* tcs_last_error(void);
+
+/* ---- (1) correlation build ------------------------------------------------------------------ */
+
+/* L2-normalise over channels and re-lay out NCHW fp32 -> channels-last 16-bit GEMM operands.
+ * ref: core/corr.py:58-59 (F.normalize(fmap, dim=1), eps 1e-12).
+ *   fmap  [B,C,H,W] fp32 (in)
+ *   hi    [B,H,W,C] bf16/fp16 (out)            the rounded normalised feature (x 2^8 for fp16)
+ *   lo    [B,H,W,C] bf16/fp16 (out, nullable)  the rounding residual, for the *X3 modes
+ *   n32   [B,H,W,C] fp32 (out, nullable)       the fp32 normalised feature (alternate path operand)
+ * prec selects bf16 vs fp16 rounding.  Requires C % 64 == 0, C <= 512. */
+int tcs_corr_prepass(const float* fmap, void* hi, void* lo, float* n32,
+                     int B, int C, int H, int W, int prec, void* stream);
+
+/* All-pairs 1-D correlation of one frame, all pyramid levels in one pass (tcgen05 + TMEM + TMA).
+ * ref: core/corr.py:54-62 (CorrBlock1D.corr: einsum 'aijk,aijh->ajkh') and core/corr.py:15-23
+ * (the avg_pool2d([1,2]) pyramid).  Level l+1 = 0.5*(even + odd column) of level l, floor on odd
+ * widths, exactly as avg_pool2d does.
+ *   a_hi,a_lo  [B,H,W1,C] operands of the left image  (lo nullable unless prec is *X3)
+ *   b_hi,b_lo  [B,H,W2,C] operands of the right image
+ *   lvl[l]     [B,H,W1,W2>>l] fp32 (out), l < num_levels <= 4; every level pointer 16-byte aligned
+ * Requires C % 64 == 0, W1 >= 1, W2 >= 8. */
+int tcs_corr_build(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                   float* lvl0, float* lvl1, float* lvl2, float* lvl3,
+                   int B, int H, int W1, int W2, int C, int num_levels, int prec, void* stream);
+
+/* Exact-fp32 CUDA-core build (no tensor cores): the strict-parity mode and the in-library check of
+ * the tensor-core path.  Same outputs as tcs_corr_build; operands are the fp32 normalised
+ * channels-last features written by tcs_corr_prepass (n32). */
+int tcs_corr_build_fp32(const float* a_n32, const float* b_n32,
+                        float* lvl0, float* lvl1, float* lvl2, float* lvl3,
+                        int B, int H, int W1, int W2, int C, int num_levels, void* stream);
+
+/* ---- (2) fused pyramid lookup ----------------------------------------------------------------- */
+
+/* ref: core/corr.py:33-52 (CorrBlock1D.__call__) + core/utils/utils.py:82-97 (bilinear_sampler ->
+ * F.grid_sample, align_corners=True, zeros padding), including grid_sample's normalise /
+ * un-normalise fp32 round trip.
+ *   lvl[l]  as written by tcs_corr_build; each level must be readable up to the next 16-byte
+ *           boundary past its end (the Python wrapper pads)
+ *   coords  fp32, x coordinate of pixel (b,h,w1) at  coords[b*coords_bstride + h*W1 + w1]
+ *           (coords_bstride lets the caller pass channel 0 of a [B,2,H,W1] tensor)
+ *   out     [B, num_levels*(2r+1), H, W1] fp32 */
+int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                    const float* coords, long long coords_bstride, float* out,
+                    int B, int H, int W1, int W2, int num_levels, int radius, void* stream);
+
+/* ---- (3) alternate (on-the-fly) lookup ---------------------------------------------------------- */
+
+/* Average-pool the fp32 normalised right features along W (channels last): out[b,h,j,:] =
+ * 0.5*(in[b,h,2j,:] + in[b,h,2j+1,:]).  Pooling the features == pooling the volume (linearity). */
+int tcs_fmap_pool_w(const float* in, float* out, int B, int H, int W, int C, void* stream);
+
+/* Same result as tcs_corr_lookup without a materialised volume: dot products only at the taps,
+ * warp-level reductions.  (New capability; the reference has no such path — its contract is
+ * "equals CorrBlock1D.__call__", ref: core/corr.py:33-52.)
+ *   a_n32     [B,H,W1,C]      fp32 normalised left features
+ *   b_n32[l]  [B,H,W2>>l,C]   fp32 normalised right features pooled l times */
+int tcs_corr_lookup_alt(const float* a_n32,
+                        const float* b0_n32, const float* b1_n32, const float* b2_n32, const float* b3_n32,
+                        const float* coords, long long coords_bstride, float* out,
+                        int B, int H, int W1, int W2, int C, int num_levels, int radius, void* stream);
+
+/* ---- first-frame initialisation ------------------------------------------------------------------ */
+
+/* ref: core/corr.py:67-79 (CorrBlock1D.argmax_disp) on the masked volume of core/corr.py:25-31.
+ *   lvl0 [B,H,W1,W2] -> sparse_disp, main_cost, mask : each [B,1,H,W1] fp32.  thres: 0.3 in the reference. */
+int tcs_corr_argmax(const float* lvl0, float* sparse_disp, float* main_cost, float* mask,
+                    int B, int H, int W1, int W2, float thres, void* stream);
+
+/* ref: core/corr.py:25-31,64-65 (get_cost_volume): out[b,w2,h,w1] = lvl0[b,h,w1,w2] * (w2 <= w1). */
+int tcs_corr_cost_volume(const float* lvl0, float* out, int B, int H, int W1, int W2, void* stream);
+
+/* ---- (4) temporal step -------------------------------------------------------------------------- */
+
+/* Scratch sizes (bytes) the caller must provide to tcs_warp_forward. */
+long long tcs_warp_scratch_bytes(int B, int C, int H, int W);
+
+/* Forward-warp the previous frame's disparity and features into the current view.
+ * ref: core/utils/geo_utils.py:158-198 (warp) with helpers :7-57,:135-145, core/utils/utils.py:100-103,
+ * core/utils/splatting/softsplat.py:232-274 (softsplat 'soft-clipeps') and :284-335 (softsplat_out).
+ *   disp      [B,1,H,W]  previous disparity (>= 0)
+ *   fmap      [B,C,H,W]  previous left features
+ *   rel_T     [B,4,4]    previous->current camera transform;  K, K_inv [B,3,3];  baseline [B]
+ *   cur_fmap  [B,C,H,W]  current left features (nullable: then cost is not computed)
+ *   out_disp  [B,1,H,W], out_fmap [B,C,H,W], out_mask [B,1,H,W], out_cost [B,1,H,W] (nullable)
+ *   out_cost = sum_c normalize(cur_fmap)*normalize(out_fmap) * out_mask   (ref: core/tc_stereo.py:139-140)
+ *   per_sample_mean != 0 uses each sample's own mean disparity for the soft-splat metric instead of
+ *   the reference's batch-global mean (geo_utils.py:193) — for batching independent sequences.
+ *   scratch   tcs_warp_scratch_bytes() bytes, 16-byte aligned. */
+int tcs_warp_forward(const float* disp, const float* fmap, const float* rel_T, const float* K,
+                     const float* K_inv, const float* baseline, const float* cur_fmap,
+                     float* out_disp, float* out_fmap, float* out_mask, float* out_cost,
+                     void* scratch, int B, int C, int H, int W, int per_sample_mean, void* stream);
+
+/* ref: core/utils/geo_utils.py:201-236 (get_backward_grid).  disp [B,1,H,W] -> grid [B,2,H,W] (x,y). */
+int tcs_backward_grid(const float* disp, const float* rel_T, const float* K, const float* K_inv,
+                      const float* baseline, float* grid, int B, int H, int W, void* stream);
+
+/* ref: core/utils/utils.py:82-97 (bilinear_sampler: grid_sample bilinear, zeros, align_corners=True,
+ * pixel coordinates).  img [B,C,Hi,Wi]; grid_xy [B,2,Ho,Wo] planar (x plane then y plane);
+ * out [B,C,Ho,Wo]. */
+int tcs_bilinear_sample(const float* img, const float* grid_xy, float* out,
+                        int B, int C, int Hi, int Wi, int Ho, int Wo, void* stream);
+
+/* ref: core/tc_stereo.py:163: grid <- 0.5 * F.interpolate(grid, scale_factor=0.5, 'bilinear',
+ * align_corners=True).  in [B,2,H,W] -> out [B,2,H/2,W/2]. */
+int tcs_grid_halve(const float* in, float* out, int B, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCS_B200_H */

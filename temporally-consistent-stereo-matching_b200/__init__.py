@@ -1,0 +1,23 @@
+"""B200-native cost-volume hot path of TC-Stereo behind the reference's own interfaces.
+
+The directory name carries hyphens (it is the project's name), so import it through the `tcs_b200` shim at
+the repository root, or with importlib.import_module("temporally-consistent-stereo-matching_b200").
+
+    from tcs_b200 import CorrBlock1D, warp, get_backward_grid, bilinear_sampler, install
+
+Everything computes in libtcs_b200.so (hand-written sm_100a CUDA, C-ABI in include/tcs_b200.h).  Importing
+this package loads that library and fails if it has not been built: there is no CPU or PyTorch fallback.
+"""
+from . import _lib
+
+_lib.load()
+
+from .corr import CorrBlock1D, build_pyramid, normalized_operands  # noqa: E402
+from .geo import (bilinear_sampler, cal_relative_transformation, get_backward_grid, halve_grid,  # noqa: E402
+                  sample_planar, warp, warp_hidden_states, warp_with_cost)
+from .dropin import install, uninstall  # noqa: E402
+from .sequence import HotPathRunner, shard_sequences  # noqa: E402
+
+__all__ = ["CorrBlock1D", "build_pyramid", "normalized_operands", "warp", "warp_with_cost", "get_backward_grid",
+           "bilinear_sampler", "sample_planar", "halve_grid", "warp_hidden_states", "cal_relative_transformation",
+           "install", "uninstall", "HotPathRunner", "shard_sequences"]

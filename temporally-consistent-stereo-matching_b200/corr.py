@@ -1,0 +1,228 @@
+"""CorrBlock1D — the reference's correlation-block interface on top of libtcs_b200.so.
+
+Mirrors core/corr.py of the reference (constructor :8-31, __call__ :33-52, corr :54-62, get_cost_volume
+:64-65, argmax_disp :67-79): same names, argument meaning and return shapes, so that
+`core.tc_stereo.CorrBlock1D = CorrBlock1D` is a drop-in.  All arithmetic happens in the CUDA library; this
+file validates arguments, owns the device buffers (torch's caching allocator) and passes raw pointers.
+Inference only (no autograd), CUDA tensors only, no fallback.
+"""
+import os
+
+import torch
+
+from . import _lib
+
+_DEFAULT_PRECISION = os.environ.get("TCS_B200_PRECISION", "bf16x3")
+_DEFAULT_MODE = os.environ.get("TCS_B200_CORR_MODE", "pyramid")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_fmap(name, t):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor (libtcs_b200 has no CPU path)" % name)
+    if t.dim() != 4:
+        raise ValueError("%s must be [B, C, H, W], got %s" % (name, tuple(t.shape)))
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _pad16(n_floats):
+    return (n_floats + 3) & ~3
+
+
+def normalized_operands(fmap, precision="bf16x3", want_hi=True, want_lo=None, want_n32=False):
+    """L2-normalise [B,C,H,W] fp32 features over C and re-lay them out channels-last (ref: corr.py:58-59).
+
+    Returns (hi, lo, n32): 16-bit [B,H,W,C] operands of the tensor-core build (lo only for the x3 modes)
+    and/or the fp32 normalised features."""
+    fmap = _check_fmap("fmap", fmap)
+    B, C, H, W = fmap.shape
+    fp16 = precision in ("fp16", "fp16x3")
+    if want_lo is None:
+        want_lo = precision in ("bf16x3", "fp16x3")
+    dt = torch.float16 if fp16 else torch.bfloat16
+    hi = torch.empty((B, H, W, C), dtype=dt, device=fmap.device) if want_hi else None
+    lo = torch.empty((B, H, W, C), dtype=dt, device=fmap.device) if (want_hi and want_lo) else None
+    n32 = torch.empty((B, H, W, C), dtype=torch.float32, device=fmap.device) if want_n32 else None
+    prec = _lib.PRECISIONS["fp16" if fp16 else "bf16"]
+    with torch.cuda.device(fmap.device):
+        _lib.call("tcs_corr_prepass", fmap.data_ptr(), hi.data_ptr() if hi is not None else None,
+                  lo.data_ptr() if lo is not None else None, n32.data_ptr() if n32 is not None else None,
+                  B, C, H, W, prec, _stream())
+    return hi, lo, n32
+
+
+def alloc_pyramid(B, H, W1, W2, num_levels, device):
+    """One flat fp32 buffer holding every level [B,H,W1,W2>>l], each 16-byte aligned and padded so the
+    lookup may read up to the next 16-byte boundary past a level's end."""
+    sizes = [B * H * W1 * (W2 >> l) for l in range(num_levels)]
+    offs, total = [], 0
+    for s in sizes:
+        offs.append(total)
+        total += _pad16(s) + 4
+    flat = torch.empty(total, dtype=torch.float32, device=device)
+    levels = [flat[o:o + s].view(B, H, W1, W2 >> l) for l, (o, s) in enumerate(zip(offs, sizes))]
+    return flat, levels
+
+
+def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3"):
+    """All pyramid levels of the 1-D all-pairs cosine correlation (ref: corr.py:54-62 + :15-23).
+
+    precision: 'bf16' | 'bf16x3' | 'fp16' | 'fp16x3' (tcgen05 tensor cores) or 'fp32' (CUDA cores)."""
+    fmap1 = _check_fmap("fmap1", fmap1)
+    fmap2 = _check_fmap("fmap2", fmap2)
+    B, C, H, W1 = fmap1.shape
+    B2, C2, H2, W2 = fmap2.shape
+    if (B, C, H) != (B2, C2, H2):
+        raise ValueError("fmap1 %s and fmap2 %s disagree on B, C or H" % (tuple(fmap1.shape), tuple(fmap2.shape)))
+    if not 1 <= num_levels <= _lib.MAX_LEVELS:
+        raise ValueError("num_levels must be in [1, %d]" % _lib.MAX_LEVELS)
+    flat, levels = alloc_pyramid(B, H, W1, W2, num_levels, fmap1.device)
+    ptrs = [levels[l].data_ptr() if l < num_levels else None for l in range(4)]
+    with torch.cuda.device(fmap1.device):
+        if precision == "fp32":
+            _, _, a32 = normalized_operands(fmap1, want_hi=False, want_n32=True)
+            _, _, b32 = normalized_operands(fmap2, want_hi=False, want_n32=True)
+            _lib.call("tcs_corr_build_fp32", a32.data_ptr(), b32.data_ptr(), *ptrs, B, H, W1, W2, C, num_levels, _stream())
+        else:
+            if precision not in _lib.PRECISIONS:
+                raise ValueError("unknown precision %r" % (precision,))
+            a_hi, a_lo, _ = normalized_operands(fmap1, precision)
+            b_hi, b_lo, _ = normalized_operands(fmap2, precision)
+            _lib.call("tcs_corr_build", a_hi.data_ptr(), a_lo.data_ptr() if a_lo is not None else None,
+                      b_hi.data_ptr(), b_lo.data_ptr() if b_lo is not None else None, *ptrs,
+                      B, H, W1, W2, C, num_levels, _lib.PRECISIONS[precision], _stream())
+    return flat, levels
+
+
+def _coords_plane(coords, B, H, W1):
+    """Channel 0 of [B,>=1,H,W1] coords as (tensor, pointer, batch stride) without copying when possible."""
+    if not coords.is_cuda:
+        raise TypeError("coords must be a CUDA tensor")
+    if coords.dim() != 4 or coords.shape[0] != B or coords.shape[2] != H or coords.shape[3] != W1:
+        raise ValueError("coords must be [B, >=1, H, W], got %s for B=%d H=%d W=%d" % (tuple(coords.shape), B, H, W1))
+    c = coords[:, :1]
+    if c.dtype != torch.float32:
+        c = c.float()
+    if not (c.stride(3) == 1 and c.stride(2) == W1):
+        c = c.contiguous()
+    return c, c.data_ptr(), (c.stride(0) if B > 1 else H * W1)
+
+
+class CorrBlock1D:
+    """ref: core/corr.py:7-79.  `mode='alternate'` never materialises the volume (subsystem 3)."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, thres=0.2, precision=None, mode=None):
+        self.num_levels = num_levels
+        self.thres = thres          # stored and unused, as in the reference (argmax uses 0.3, corr.py:73)
+        self.radius = radius
+        self.precision = precision or _DEFAULT_PRECISION
+        self.mode = mode or _DEFAULT_MODE
+        if self.mode not in ("pyramid", "alternate"):
+            raise ValueError("mode must be 'pyramid' or 'alternate'")
+        if not 0 <= radius <= _lib.MAX_RADIUS:
+            raise ValueError("radius must be in [0, %d]" % _lib.MAX_RADIUS)
+        fmap1 = _check_fmap("fmap1", fmap1)
+        fmap2 = _check_fmap("fmap2", fmap2)
+        self.B, self.C, self.H, self.W1 = fmap1.shape
+        self.W2 = fmap2.shape[3]
+        self.device = fmap1.device
+        self._cost_volume = None
+        if self.mode == "pyramid":
+            self._flat, self._levels = build_pyramid(fmap1, fmap2, num_levels, self.precision)
+            self._fmaps = None
+        else:
+            self._flat, self._levels = None, None
+            _, _, self._a32 = normalized_operands(fmap1, want_hi=False, want_n32=True)
+            _, _, b32 = normalized_operands(fmap2, want_hi=False, want_n32=True)
+            self._b32 = [b32]
+            with torch.cuda.device(self.device):
+                for l in range(1, num_levels):
+                    prev = self._b32[-1]
+                    nxt = torch.empty((self.B, self.H, prev.shape[2] // 2, self.C), dtype=torch.float32, device=self.device)
+                    _lib.call("tcs_fmap_pool_w", prev.data_ptr(), nxt.data_ptr(), self.B, self.H, prev.shape[2], self.C, _stream())
+                    self._b32.append(nxt)
+            self._fmaps = (fmap1, fmap2)   # argmax_disp / get_cost_volume need level 0 on demand
+
+    @classmethod
+    def from_levels(cls, levels, radius=4):
+        """A block over an existing pyramid (levels[l] [B,H,W1,W2>>l] fp32 CUDA): lookup / argmax / cost volume
+        of volumes built elsewhere, e.g. the reference's own pyramid in the parity tests."""
+        self = cls.__new__(cls)
+        lv0 = levels[0]
+        self.B, self.H, self.W1, self.W2 = lv0.shape
+        self.C = None
+        self.num_levels, self.radius, self.thres = len(levels), radius, 0.2
+        self.precision, self.mode, self.device = "external", "pyramid", lv0.device
+        self._flat, self._levels = alloc_pyramid(self.B, self.H, self.W1, self.W2, self.num_levels, self.device)
+        for dst, src in zip(self._levels, levels):
+            if tuple(dst.shape) != tuple(src.shape):
+                raise ValueError("level shape %s, expected %s" % (tuple(src.shape), tuple(dst.shape)))
+            dst.copy_(src)
+        self._fmaps, self._cost_volume = None, None
+        return self
+
+    # -- reference attributes -----------------------------------------------------------------------
+    @property
+    def corr_pyramid(self):
+        """Levels shaped like the reference's list entries, [B*H*W1, 1, 1, W2>>l] (corr.py:18-23)."""
+        if self._levels is None:
+            raise RuntimeError("mode='alternate' does not materialise corr_pyramid")
+        return [lv.view(self.B * self.H * self.W1, 1, 1, lv.shape[3]) for lv in self._levels]
+
+    @property
+    def cost_volume(self):
+        return self.get_cost_volume()
+
+    def _level0(self):
+        if self._levels is not None:
+            return self._levels[0]
+        _, levels = build_pyramid(self._fmaps[0], self._fmaps[1], 1, self.precision)
+        return levels[0]
+
+    # -- reference methods ----------------------------------------------------------------------------
+    def __call__(self, coords):
+        """ref: corr.py:33-52.  coords [B,>=1,H,W] -> [B, num_levels*(2r+1), H, W] fp32."""
+        c, cptr, cstride = _coords_plane(coords, self.B, self.H, self.W1)
+        out = torch.empty((self.B, self.num_levels * (2 * self.radius + 1), self.H, self.W1),
+                          dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            if self.mode == "pyramid":
+                ptrs = [self._levels[l].data_ptr() if l < self.num_levels else None for l in range(4)]
+                _lib.call("tcs_corr_lookup", *ptrs, cptr, cstride, out.data_ptr(),
+                          self.B, self.H, self.W1, self.W2, self.num_levels, self.radius, _stream())
+            else:
+                ptrs = [self._b32[l].data_ptr() if l < self.num_levels else None for l in range(4)]
+                _lib.call("tcs_corr_lookup_alt", self._a32.data_ptr(), *ptrs, cptr, cstride, out.data_ptr(),
+                          self.B, self.H, self.W1, self.W2, self.C, self.num_levels, self.radius, _stream())
+        return out
+
+    def get_cost_volume(self):
+        """ref: corr.py:25-31,64-65.  [B, W2, H, W1], zero where w2 > w1.  Built on first use."""
+        if self._cost_volume is None:
+            lvl0 = self._level0()
+            out = torch.empty((self.B, self.W2, self.H, self.W1), dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.call("tcs_corr_cost_volume", lvl0.data_ptr(), out.data_ptr(), self.B, self.H, self.W1, self.W2, _stream())
+            self._cost_volume = out
+        return self._cost_volume
+
+    def argmax_disp(self, thres=0.3):
+        """ref: corr.py:67-79.  -> (sparse_disp, main_cost, mask), each [B,1,H,W1] fp32."""
+        lvl0 = self._level0()
+        outs = [torch.empty((self.B, 1, self.H, self.W1), dtype=torch.float32, device=self.device) for _ in range(3)]
+        with torch.cuda.device(self.device):
+            _lib.call("tcs_corr_argmax", lvl0.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                      self.B, self.H, self.W1, self.W2, float(thres), _stream())
+        return tuple(outs)
+
+    @staticmethod
+    def corr(fmap1, fmap2, precision=None):
+        """ref: corr.py:54-62.  -> [B, H, W1, 1, W2] fp32."""
+        _, levels = build_pyramid(fmap1, fmap2, 1, precision or _DEFAULT_PRECISION)
+        lv = levels[0]
+        return lv.view(lv.shape[0], lv.shape[1], lv.shape[2], 1, lv.shape[3])

@@ -1,0 +1,401 @@
+// Per-GRU-iteration consumers of the correlation pyramid:
+//   tcs_corr_lookup       fused all-level linear-interpolated lookup        (ref: core/corr.py:33-52)
+//   tcs_corr_lookup_alt   same result with no materialised volume           (new; contract = corr.py:33-52)
+//   tcs_corr_argmax       first-frame winner-take-all + uniqueness test     (ref: core/corr.py:67-79)
+//   tcs_corr_cost_volume  masked [b,w2,h,w1] copy for the training loss     (ref: core/corr.py:25-31,64-65)
+//
+// Sampling arithmetic follows bilinear_sampler -> F.grid_sample (core/utils/utils.py:82-97) to the
+// rounding: x = k + coords/2^l ; xg = 2x/(W-1) - 1 ; ix = ((xg+1)/2)*(W-1) ; x0 = floor(ix) ;
+// out = v[x0]*(x0+1-ix) + v[x0+1]*(ix-x0), out-of-range taps contributing 0 (zeros padding).
+#include "tcs_common.cuh"
+
+namespace tcs {
+
+struct LevelPtrs {
+    const float* p[TCS_MAX_LEVELS];
+};
+
+// grid_sample's normalise / un-normalise round trip, step by step in fp32 (no contraction).
+__device__ __forceinline__ float sample_pos(float xk, float wm1) {
+    const float xg = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, xk), wm1), 1.0f);       // utils.py:86
+    return __fmul_rn(__fmul_rn(__fadd_rn(xg, 1.0f), 0.5f), wm1);                 // ATen unnormalize, align_corners
+}
+
+// ---- fused lookup, radius 4: 4 lanes per (pixel, level) -------------------------------------------
+// Each quad fetches the 64-byte, 16-byte-aligned superset of its pixel's 12-float window with one
+// ld.global.v4 per lane, parks it in shared memory and interpolates 9 taps from there.
+constexpr int kLookThreads = 256;
+
+__global__ void __launch_bounds__(kLookThreads)
+corr_lookup_r4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
+                      float* __restrict__ out, int HW, int W2, int num_levels, long long npix) {
+    __shared__ float4 win[kLookThreads];  // [64 quads][4]
+    const int tid = threadIdx.x;
+    const int quad = tid >> 2, j = tid & 3;
+    const int l = blockIdx.y;
+    const long long p = (long long)blockIdx.x * (kLookThreads / 4) + quad;
+    const bool active = p < npix;
+    const int Wl = W2 >> l;
+    const float wm1 = (float)(Wl - 1);
+    const float* __restrict__ base = lv.p[l];
+    const long long total4 = ((npix * Wl + 3) >> 2) << 2;  // readable length (caller pads to 16 B)
+
+    float cl = 0.0f;
+    long long b = 0, hw = 0;
+    if (active) {
+        b = p / HW;
+        hw = p - b * HW;
+        cl = __ldg(coords + b * coords_bstride + hw) * (1.0f / (float)(1 << l));   // coords / 2**l (exact)
+    }
+    // window = in-row indices [fc-5, fc+6] (taps can land one off the centre estimate after rounding)
+    const float fcf = fminf(fmaxf(floorf(cl), -16.0f), (float)(Wl + 16));
+    const int wfirst = (int)fcf - 5;
+    const long long row_start = p * Wl;
+    const long long a_abs = ((row_start + wfirst) >> 2) << 2;   // floor to a multiple of 4 floats (16 B)
+    const int win_first = (int)(a_abs - row_start);             // in-row index of win[0]
+    {
+        const long long idx = a_abs + 4 * j;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && idx >= 0 && idx + 3 < total4) v = __ldg(reinterpret_cast<const float4*>(base + idx));
+        win[tid] = v;
+    }
+    __syncwarp();
+    if (active) {
+        const float* w = reinterpret_cast<const float*>(win) + quad * 16;
+        float* o = out + ((b * num_levels + l) * 9) * (long long)HW + hw;
+#pragma unroll
+        for (int t = j; t < 9; t += 4) {
+            const float xk = __fadd_rn((float)(t - 4), cl);     // corr.py:43  dx + coords/2^i
+            const float ix = sample_pos(xk, wm1);
+            float r = 0.0f;
+            if (ix > -1.0f && ix < (float)Wl) {                 // otherwise both taps are out of range
+                const float x0f = floorf(ix);
+                const int x0 = (int)x0f;
+                const float w_hi = __fsub_rn(ix, x0f);
+                const float w_lo = __fsub_rn(__fadd_rn(x0f, 1.0f), ix);
+                const int i0 = x0 - win_first;
+                float v0 = 0.0f, v1 = 0.0f;
+                if (x0 >= 0 && (unsigned)i0 < 16u) v0 = w[i0];
+                if (x0 + 1 < Wl && (unsigned)(i0 + 1) < 16u) v1 = w[i0 + 1];
+                r = fmaf(v1, w_hi, __fmul_rn(v0, w_lo));
+            }
+            o[(long long)t * HW] = r;
+        }
+    }
+}
+
+// ---- generic lookup (any radius <= 8): one thread per (pixel, level), scalar loads ---------------------
+__global__ void __launch_bounds__(256)
+corr_lookup_generic_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
+                           float* __restrict__ out, int HW, int W2, int num_levels, int radius, long long npix) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const int l = blockIdx.y;
+    const int Wl = W2 >> l;
+    const float wm1 = (float)(Wl - 1);
+    const long long b = p / HW, hw = p - b * HW;
+    const float cl = __ldg(coords + b * coords_bstride + hw) * (1.0f / (float)(1 << l));
+    const float* __restrict__ row = lv.p[l] + p * Wl;
+    const int taps = 2 * radius + 1;
+    float* o = out + ((b * num_levels + l) * taps) * (long long)HW + hw;
+    for (int t = 0; t < taps; ++t) {
+        const float xk = __fadd_rn((float)(t - radius), cl);
+        const float ix = sample_pos(xk, wm1);
+        float r = 0.0f;
+        if (ix > -1.0f && ix < (float)Wl) {
+            const float x0f = floorf(ix);
+            const int x0 = (int)x0f;
+            const float w_hi = __fsub_rn(ix, x0f);
+            const float w_lo = __fsub_rn(__fadd_rn(x0f, 1.0f), ix);
+            const float v0 = (x0 >= 0) ? __ldg(row + x0) : 0.0f;
+            const float v1 = (x0 + 1 < Wl) ? __ldg(row + x0 + 1) : 0.0f;
+            r = fmaf(v1, w_hi, __fmul_rn(v0, w_lo));
+        }
+        o[(long long)t * HW] = r;
+    }
+}
+
+// ---- alternate path: dot products only at the taps -------------------------------------------------------
+// One warp per pixel.  Lanes split the C channels (float4 x C/128 per lane), the left feature vector
+// stays in registers, each candidate column of the (pooled) right features is a coalesced C*4-byte
+// read (L1/L2 resident: neighbouring pixels share almost all columns), and the per-column partial
+// sums are combined with a halving butterfly (16 values in 16 shuffles instead of 80).
+template <int kC4>  // float4 per lane = C / 128
+__global__ void __launch_bounds__(256)
+corr_lookup_alt_kernel(const float* __restrict__ a, const LevelPtrs bl, const float* __restrict__ coords,
+                       long long coords_bstride, float* __restrict__ out, int HW, int W1, int W2,
+                       int num_levels, int radius, long long npix) {
+    const int lane = threadIdx.x & 31;
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= npix) return;  // warp-uniform
+    constexpr int C = kC4 * 128;
+    const long long b = p / HW, hw = p - b * HW;
+    const long long bh = p / W1;  // row index b*H + h
+    const float c0 = __ldg(coords + b * coords_bstride + hw);
+    float4 av[kC4];
+#pragma unroll
+    for (int i = 0; i < kC4; ++i) av[i] = __ldg(reinterpret_cast<const float4*>(a + p * C) + lane + 32 * i);
+    const int taps = 2 * radius + 1;
+    const int ncols = taps + 3;  // columns [fc-r-1, fc+r+2]
+
+    for (int l = 0; l < num_levels; ++l) {
+        const int Wl = W2 >> l;
+        const float wm1 = (float)(Wl - 1);
+        const float cl = c0 * (1.0f / (float)(1 << l));
+        const float fcf = fminf(fmaxf(floorf(cl), -32.0f), (float)(Wl + 32));
+        const int col0 = (int)fcf - radius - 1;
+        const float* __restrict__ brow = bl.p[l] + bh * (long long)Wl * C;
+        // dots[g][i]: partial sums of columns col0 + 16*g + i  (ncols <= 20 -> up to two groups of 16)
+        for (int g = 0; g * 16 < ncols; ++g) {
+            float part[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int col = col0 + g * 16 + i;
+                float s = 0.0f;
+                if (g * 16 + i < ncols && col >= 0 && col < Wl) {
+                    const float4* bp = reinterpret_cast<const float4*>(brow + (long long)col * C);
+#pragma unroll
+                    for (int q = 0; q < kC4; ++q) {
+                        const float4 bv = __ldg(bp + lane + 32 * q);
+                        s = fmaf(av[q].x, bv.x, s); s = fmaf(av[q].y, bv.y, s);
+                        s = fmaf(av[q].z, bv.z, s); s = fmaf(av[q].w, bv.w, s);
+                    }
+                }
+                part[i] = s;
+            }
+            // halving butterfly: after it, lane L holds the full sum of column index (L >> 1) & 15 ... see below
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {   // xor 16: lanes < 16 keep columns 0..7, lanes >= 16 keep 8..15
+                const bool up = (lane & 16) != 0;
+                const float send = up ? part[i] : part[i + 8];
+                const float keep = up ? part[i + 8] : part[i];
+                part[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {   // xor 8
+                const bool up = (lane & 8) != 0;
+                const float send = up ? part[i] : part[i + 4];
+                const float keep = up ? part[i + 4] : part[i];
+                part[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {   // xor 4
+                const bool up = (lane & 4) != 0;
+                const float send = up ? part[i] : part[i + 2];
+                const float keep = up ? part[i + 2] : part[i];
+                part[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            {                               // xor 2
+                const bool up = (lane & 2) != 0;
+                const float send = up ? part[0] : part[1];
+                const float keep = up ? part[1] : part[0];
+                part[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
+            // lane L now owns column i(L) = 8*b4 + 4*b3 + 2*b2 + b1 (bits of L); column i lives in lane 2*rev... :
+            // owner lane of column i: bit4=i>>3&1, bit3=i>>2&1, bit2=i>>1&1, bit1=i&1  ->  lane = 2*i (bit0 free)
+            const float mine = part[0];
+            // every lane t < taps computes tap t of this level (two groups are merged through shuffles below)
+            for (int t0 = 0; t0 < taps; t0 += 32) {
+                const int t = t0 + lane;
+                float r = 0.0f;
+                int i0 = -1000;
+                float w_lo = 0.0f, w_hi = 0.0f;
+                bool inb = false;
+                int x0 = 0;
+                if (t < taps) {
+                    const float xk = __fadd_rn((float)(t - radius), cl);
+                    const float ix = sample_pos(xk, wm1);
+                    if (ix > -1.0f && ix < (float)Wl) {
+                        const float x0f = floorf(ix);
+                        x0 = (int)x0f;
+                        w_hi = __fsub_rn(ix, x0f);
+                        w_lo = __fsub_rn(__fadd_rn(x0f, 1.0f), ix);
+                        i0 = x0 - col0 - g * 16;
+                        inb = true;
+                    }
+                }
+                // fetch column sums i0 and i0+1 of this group (if they are in this group)
+                const int s0 = ((unsigned)i0 < 16u) ? 2 * i0 : 0;
+                const int s1 = ((unsigned)(i0 + 1) < 16u) ? 2 * (i0 + 1) : 0;
+                const float v0 = __shfl_sync(0xffffffffu, mine, s0);
+                const float v1 = __shfl_sync(0xffffffffu, mine, s1);
+                if (inb) {
+                    // contributions from this group only; the two groups partition the columns, so adding
+                    // the per-group contributions reproduces v0*w_lo + v1*w_hi exactly when g covers both.
+                    const float c_lo = ((unsigned)i0 < 16u && x0 >= 0) ? v0 : 0.0f;
+                    const float c_hi = ((unsigned)(i0 + 1) < 16u && x0 + 1 < Wl) ? v1 : 0.0f;
+                    r = fmaf(c_hi, w_hi, __fmul_rn(c_lo, w_lo));
+                }
+                if (t < taps) {
+                    float* o = out + ((b * num_levels + l) * taps + t) * (long long)HW + hw;
+                    if (g == 0) *o = r; else *o += r;
+                }
+            }
+        }
+    }
+}
+
+// ---- argmax_disp ---------------------------------------------------------------------------------------
+// One warp per (b,h,w1) row of level 0.  Pass 1: max over the masked row (w2 > w1 -> 0), first index on
+// ties (torch.max semantics).  Pass 2: max with w2 in {idx-1, idx, idx+1} zeroed.  Values stay in
+// registers between the passes (W2 <= 1024).
+constexpr int kArgMaxPerLane = 32;
+
+__global__ void __launch_bounds__(256)
+corr_argmax_kernel(const float* __restrict__ lvl0, float* __restrict__ sparse_disp, float* __restrict__ main_cost,
+                   float* __restrict__ mask_out, int W1, int W2, float thres, long long nrows) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const int w1 = (int)(row % W1);
+    const float* __restrict__ r = lvl0 + row * W2;
+    float vals[kArgMaxPerLane];
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < kArgMaxPerLane; ++k) {
+        const int w2 = lane + 32 * k;
+        float v = -INFINITY;
+        if (w2 < W2) {
+            v = __ldg(r + w2);
+            // corr.py:27-31: cost_volume * mask with mask = 0 where w1 < w2 (so -0.0 for negative entries)
+            if (w1 < w2) v = __fmul_rn(v, 0.0f);
+            if (v > best) { best = v; best_i = w2; }   // ascending w2 per lane: first index wins ties
+        }
+        vals[k] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    float sub = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kArgMaxPerLane; ++k) {
+        const int w2 = lane + 32 * k;
+        if (w2 < W2) {
+            float v = vals[k];
+            if (w2 >= best_i - 1 && w2 <= best_i + 1) v = 0.0f;   // corr.py:71
+            sub = fmaxf(sub, v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sub = fmaxf(sub, __shfl_xor_sync(0xffffffffu, sub, o));
+    if (lane == 0) {
+        const float m = (__fsub_rn(best, sub) > thres) ? 1.0f : 0.0f;
+        sparse_disp[row] = __fmul_rn((float)(w1 - best_i), m);   // int * float mask: keeps the reference's -0.0
+        main_cost[row] = __fmul_rn(best, m);
+        mask_out[row] = m;
+    }
+}
+
+// ---- get_cost_volume: [b,h,w1,w2] -> [b,w2,h,w1], zeroed where w1 < w2 -----------------------------------
+__global__ void __launch_bounds__(256)
+corr_cost_volume_kernel(const float* __restrict__ lvl0, float* __restrict__ out, int H, int W1, int W2) {
+    __shared__ float tile[32][33];
+    const int bh = blockIdx.z;
+    const int b = bh / H, h = bh - b * H;
+    const int w1_0 = blockIdx.y * 32, w2_0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
+    for (int i = ty; i < 32; i += 8) {
+        const int w1 = w1_0 + i, w2 = w2_0 + tx;
+        float v = 0.0f;
+        if (w1 < W1 && w2 < W2) {
+            v = __ldg(lvl0 + ((long long)bh * W1 + w1) * W2 + w2);
+            if (w1 < w2) v = __fmul_rn(v, 0.0f);
+        }
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int w2 = w2_0 + i, w1 = w1_0 + tx;
+        if (w1 < W1 && w2 < W2) out[(((long long)b * W2 + w2) * H + h) * W1 + w1] = tile[tx][i];
+    }
+}
+
+}  // namespace tcs
+
+// ================================================ C ABI ==================================================
+
+static int check_lookup_args(const char* fn, const float* const* lv, const float* coords, const float* out,
+                             int B, int H, int W1, int W2, int num_levels, int radius) {
+    using namespace tcs;
+    TCS_REQUIRE(coords != nullptr && out != nullptr, TCS_E_BADARG, "%s: null coords/out", fn);
+    TCS_REQUIRE(num_levels >= 1 && num_levels <= TCS_MAX_LEVELS, TCS_E_SHAPE, "%s: num_levels=%d not in [1,4]", fn, num_levels);
+    TCS_REQUIRE(radius >= 0 && radius <= TCS_MAX_RADIUS, TCS_E_SHAPE, "%s: radius=%d not in [0,8]", fn, radius);
+    TCS_REQUIRE(B > 0 && H > 0 && W1 > 0 && (W2 >> (num_levels - 1)) >= 2, TCS_E_SHAPE, "%s: bad sizes (coarsest level needs width >= 2)", fn);
+    for (int l = 0; l < num_levels; ++l)
+        TCS_REQUIRE(lv[l] != nullptr && aligned16(lv[l]), TCS_E_ALIGN, "%s: level %d pointer null or not 16-byte aligned", fn, l);
+    return 0;
+}
+
+extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                               const float* coords, long long coords_bstride, float* out,
+                               int B, int H, int W1, int W2, int num_levels, int radius, void* stream) {
+    using namespace tcs;
+    const float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
+    int rc = check_lookup_args("tcs_corr_lookup", lv, coords, out, B, H, W1, W2, num_levels, radius);
+    if (rc != 0) return rc;
+    LevelPtrs lp;
+    for (int l = 0; l < 4; ++l) lp.p[l] = lv[l];
+    const long long npix = (long long)B * H * W1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (radius == 4) {
+        dim3 grid((unsigned)ceil_div_ll(npix, kLookThreads / 4), num_levels);
+        corr_lookup_r4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels, npix);
+    } else {
+        dim3 grid((unsigned)ceil_div_ll(npix, 256), num_levels);
+        corr_lookup_generic_kernel<<<grid, 256, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels, radius, npix);
+    }
+    TCS_CHECK_LAUNCH("tcs_corr_lookup");
+    return 0;
+}
+
+extern "C" int tcs_corr_lookup_alt(const float* a_n32, const float* b0, const float* b1, const float* b2, const float* b3,
+                                   const float* coords, long long coords_bstride, float* out,
+                                   int B, int H, int W1, int W2, int C, int num_levels, int radius, void* stream) {
+    using namespace tcs;
+    const float* lv[4] = {b0, b1, b2, b3};
+    int rc = check_lookup_args("tcs_corr_lookup_alt", lv, coords, out, B, H, W1, W2, num_levels, radius);
+    if (rc != 0) return rc;
+    TCS_REQUIRE(a_n32 != nullptr && aligned16(a_n32), TCS_E_ALIGN, "tcs_corr_lookup_alt: a_n32 null or unaligned");
+    TCS_REQUIRE(C == 128 || C == 256 || C == 384 || C == 512, TCS_E_SHAPE, "tcs_corr_lookup_alt: C=%d must be 128, 256, 384 or 512", C);
+    LevelPtrs lp;
+    for (int l = 0; l < 4; ++l) lp.p[l] = lv[l];
+    const long long npix = (long long)B * H * W1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)ceil_div_ll(npix, 8);
+    switch (C / 128) {
+        case 1: corr_lookup_alt_kernel<1><<<grid, 256, 0, s>>>(a_n32, lp, coords, coords_bstride, out, H * W1, W1, W2, num_levels, radius, npix); break;
+        case 2: corr_lookup_alt_kernel<2><<<grid, 256, 0, s>>>(a_n32, lp, coords, coords_bstride, out, H * W1, W1, W2, num_levels, radius, npix); break;
+        case 3: corr_lookup_alt_kernel<3><<<grid, 256, 0, s>>>(a_n32, lp, coords, coords_bstride, out, H * W1, W1, W2, num_levels, radius, npix); break;
+        default: corr_lookup_alt_kernel<4><<<grid, 256, 0, s>>>(a_n32, lp, coords, coords_bstride, out, H * W1, W1, W2, num_levels, radius, npix); break;
+    }
+    TCS_CHECK_LAUNCH("tcs_corr_lookup_alt");
+    return 0;
+}
+
+extern "C" int tcs_corr_argmax(const float* lvl0, float* sparse_disp, float* main_cost, float* mask,
+                               int B, int H, int W1, int W2, float thres, void* stream) {
+    using namespace tcs;
+    TCS_REQUIRE(lvl0 != nullptr && sparse_disp != nullptr && main_cost != nullptr && mask != nullptr, TCS_E_BADARG, "tcs_corr_argmax: null pointer");
+    TCS_REQUIRE(B > 0 && H > 0 && W1 > 0 && W2 > 0, TCS_E_BADARG, "tcs_corr_argmax: non-positive size");
+    TCS_REQUIRE(W2 <= 32 * kArgMaxPerLane, TCS_E_SHAPE, "tcs_corr_argmax: W2=%d exceeds %d", W2, 32 * kArgMaxPerLane);
+    const long long nrows = (long long)B * H * W1;
+    corr_argmax_kernel<<<(unsigned)ceil_div_ll(nrows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        lvl0, sparse_disp, main_cost, mask, W1, W2, thres, nrows);
+    TCS_CHECK_LAUNCH("tcs_corr_argmax");
+    return 0;
+}
+
+extern "C" int tcs_corr_cost_volume(const float* lvl0, float* out, int B, int H, int W1, int W2, void* stream) {
+    using namespace tcs;
+    TCS_REQUIRE(lvl0 != nullptr && out != nullptr, TCS_E_BADARG, "tcs_corr_cost_volume: null pointer");
+    TCS_REQUIRE(B > 0 && H > 0 && W1 > 0 && W2 > 0 && (long long)B * H <= 65535, TCS_E_SHAPE, "tcs_corr_cost_volume: bad sizes (B*H <= 65535)");
+    dim3 grid(ceil_div(W2, 32), ceil_div(W1, 32), B * H);
+    corr_cost_volume_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(lvl0, out, H, W1, W2);
+    TCS_CHECK_LAUNCH("tcs_corr_cost_volume");
+    return 0;
+}

@@ -1,0 +1,80 @@
+// Shared host/device helpers for libtcs_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "tcs_b200.h"
+
+namespace tcs {
+
+// ---- host-side error plumbing ----------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define TCS_REQUIRE(cond, code, ...)                    \
+    do {                                                \
+        if (!(cond)) {                                  \
+            ::tcs::set_error(__VA_ARGS__);              \
+            return (code);                              \
+        }                                               \
+    } while (0)
+
+// Check the launch (not the execution): no host sync happens inside the library.
+#define TCS_CHECK_LAUNCH(what)                                                      \
+    do {                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                       \
+        if (e__ != cudaSuccess) {                                                   \
+            ::tcs::set_error("%s: %s", (what), cudaGetErrorString(e__));            \
+            return static_cast<int>(e__);                                           \
+        }                                                                           \
+    } while (0)
+
+#define TCS_CHECK_CUDA(expr)                                                        \
+    do {                                                                            \
+        cudaError_t e__ = (expr);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            ::tcs::set_error("%s: %s", #expr, cudaGetErrorString(e__));             \
+            return static_cast<int>(e__);                                           \
+        }                                                                           \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+int num_sms();  // cached SM count of the current device
+
+// ---- device helpers ----------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Streaming (read-once / write-once) global accesses: keep them out of L1.
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream_f1(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace tcs

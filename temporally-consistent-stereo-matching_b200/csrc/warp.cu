@@ -1,0 +1,503 @@
+// Temporal step: carry the previous frame's disparity, features and hidden states into the current view.
+//   tcs_warp_forward     geometry -> soft-splat (vector red.global.add) -> normalise + mask + matching cost
+//                        ref: core/utils/geo_utils.py:158-198 (warp), core/utils/splatting/softsplat.py:232-274,
+//                        :284-335 (softsplat / softsplat_out), core/tc_stereo.py:139-140 (cost)
+//   tcs_backward_grid    ref: core/utils/geo_utils.py:201-236 (get_backward_grid)
+//   tcs_bilinear_sample  ref: core/utils/utils.py:82-97 (bilinear_sampler -> F.grid_sample)
+//   tcs_grid_halve       ref: core/tc_stereo.py:163 (0.5 * F.interpolate(grid, 0.5, bilinear, align_corners))
+//
+// The splat is where the bytes are.  The reference launches one thread per (pixel, channel) scalar, so the
+// flow, the four targets and the four weights are recomputed 258 times per pixel and every atomic is a
+// lone 4-byte red.  Here one warp owns a source pixel: targets and weights are computed once, the 256
+// feature channels are read from a shared-memory transposed tile (coalesced NCHW loads), and each lane
+// issues one 16-byte red.global.add.v4.f32 per 4 channels and target into a channels-last accumulator
+// [B,H,W,C+4].  The channel order inside the accumulator is a private permutation
+// (position 128*j + 4*lane + i  <->  channel lane + 32*(4*j + i)) chosen so that both the splat's
+// shared-memory reads and the normalise kernel's shared-memory writes are bank-conflict free.
+//
+// Geometry is evaluated with explicit round-to-nearest intrinsics (no compiler-chosen contraction) in a
+// fixed order so that the validity masks and the integer splat targets are reproducible bit for bit by the
+// CPU oracle.
+#include "tcs_common.cuh"
+
+#include <cmath>
+
+namespace tcs {
+
+constexpr int kTileW = 32;
+constexpr int kWarpThreads = 256;
+
+struct Cam {
+    float K[9], Ki[9], T[12], bf;
+};
+
+__device__ __forceinline__ Cam load_cam(const float* __restrict__ rel_T, const float* __restrict__ K,
+                                        const float* __restrict__ K_inv, const float* __restrict__ baseline, int b) {
+    Cam c;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        c.K[i] = __ldg(K + b * 9 + i);
+        c.Ki[i] = __ldg(K_inv + b * 9 + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) c.T[i] = __ldg(rel_T + b * 16 + i);
+    c.bf = __fmul_rn(__ldg(baseline + b), c.K[0]);   // baseline * fx   (geo_utils.py:16)
+    return c;
+}
+
+// The FMA chain a GEMM micro-kernel runs over k = 0, 1, 2 (bit-identical to torch.matmul on the CPU for
+// these 3x3 / 4x4 products; the oracle restates it the same way).
+__device__ __forceinline__ float dot3(const float* m, float x, float y, float z) {
+    return __fmaf_rn(m[2], z, __fmaf_rn(m[1], y, __fmul_rn(m[0], x)));
+}
+
+// depth * K^-1 [x,y,1]^T, then the rigid transform (geo_utils.py:32-42, :135-145).
+__device__ __forceinline__ void project(const Cam& c, float depth, float x, float y, float (&P)[3]) {
+    float q[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) q[i] = __fmul_rn(depth, dot3(c.Ki + 3 * i, x, y, 1.0f));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) P[i] = __fadd_rn(dot3(c.T + 4 * i, q[0], q[1], q[2]), c.T[4 * i + 3]);
+}
+
+__device__ __forceinline__ float finite_or_m1(float v) { return (isnan(v) || isinf(v)) ? -1.0f : v; }
+
+// (K P)_{0,1} / z with NaN/Inf -> -1 (geo_utils.py:45-57).
+__device__ __forceinline__ void reproject(const Cam& c, const float (&P)[3], float& u, float& v) {
+    u = finite_or_m1(__fdiv_rn(dot3(c.K, P[0], P[1], P[2]), P[2]));
+    v = finite_or_m1(__fdiv_rn(dot3(c.K + 3, P[0], P[1], P[2]), P[2]));
+}
+
+// ---- forward warp, kernel A: geometry + per-sample disparity sums ----------------------------------------
+__global__ void __launch_bounds__(256)
+warp_geometry_kernel(const float* __restrict__ disp, const float* __restrict__ rel_T, const float* __restrict__ K,
+                     const float* __restrict__ K_inv, const float* __restrict__ baseline,
+                     float* __restrict__ disp1, float* __restrict__ tx, float* __restrict__ ty,
+                     float* __restrict__ valid, double* __restrict__ sums, int H, int W) {
+    const int b = blockIdx.y;
+    const int HW = H * W;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double local = 0.0;
+    if (i < HW) {
+        const Cam c = load_cam(rel_T, K, K_inv, baseline, b);
+        const int y = i / W, x = i - y * W;
+        const float d = __ldg(disp + (size_t)b * HW + i);
+        const float depth = __fdiv_rn(c.bf, fmaxf(d, 0.001f));                 // disp2depth
+        float P[3];
+        project(c, depth, (float)x, (float)y, P);
+        const float d1 = finite_or_m1(__fdiv_rn(c.bf, P[2]));                  // depth2disp
+        const bool ok = (d1 > 0.0f) && (d1 < (float)W);                        // geo_utils.py:185
+        float u, v;
+        reproject(c, P, u, v);
+        // flow = coords' - coords0; the splat then uses x + flow (softsplat.py:297-298)
+        const float fx_ = __fadd_rn((float)x, __fsub_rn(u, (float)x));
+        const float fy_ = __fadd_rn((float)y, __fsub_rn(v, (float)y));
+        const size_t o = (size_t)b * HW + i;
+        disp1[o] = d1;
+        tx[o] = fx_;
+        ty[o] = fy_;
+        valid[o] = ok ? 1.0f : 0.0f;
+        local = (double)d1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __shared__ double wsum[8];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += wsum[w];
+        atomicAdd(sums + b, s);
+    }
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// [C][32] NCHW tile (w fastest in global) -> tile[w][c], pitch C + 1.
+__device__ __forceinline__ void load_tile_transposed(const float* __restrict__ fmap, float* tile, int pitch,
+                                                     int b, int h, int w0, int C, int H, int W) {
+    const int tid = threadIdx.x;
+    const int w4 = (tid & 7) * 4;
+    const int c_off = tid >> 3;
+    const bool vec_ok = ((W & 3) == 0) && (w0 + w4 + 3 < W);
+    const size_t plane = (size_t)H * W;
+    const float* src = fmap + ((size_t)b * C * H + h) * W + w0 + w4;
+    for (int c = c_off; c < C; c += kWarpThreads / 8) {
+        const float* p = src + (size_t)c * plane;
+        float v[4];
+        if (vec_ok) {
+            const float4 t = ldg_stream_f4(reinterpret_cast<const float4*>(p));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = (w0 + w4 + i < W) ? __ldg(p + i) : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tile[(w4 + i) * pitch + c] = v[i];
+    }
+}
+
+// ---- forward warp, kernel B: soft-splat -----------------------------------------------------------------------
+template <int kGroups>  // C / 128
+__global__ void __launch_bounds__(kWarpThreads)
+warp_splat_kernel(const float* __restrict__ fmap, const float* __restrict__ disp1, const float* __restrict__ tx,
+                  const float* __restrict__ ty, const float* __restrict__ valid, const double* __restrict__ sums,
+                  float* __restrict__ accum, int B, int H, int W, int per_sample_mean) {
+    constexpr int C = kGroups * 128;
+    constexpr int CP = C + 4;
+    constexpr int pitch = C + 1;
+    extern __shared__ float tile[];  // [32][C + 1]
+    const int w0 = blockIdx.x * kTileW, h = blockIdx.y, b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    load_tile_transposed(fmap, tile, pitch, b, h, w0, C, H, W);
+
+    // softsplat metric: disparity minus its mean (geo_utils.py:193); batch-global unless asked otherwise
+    float mean;
+    {
+        double s = 0.0, n;
+        if (per_sample_mean) {
+            s = sums[b];
+            n = (double)H * W;
+        } else {
+            for (int i = 0; i < B; ++i) s += sums[i];
+            n = (double)B * H * W;
+        }
+        mean = (float)(s / n);
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int i = 0; i < kTileW / 8; ++i) {
+        const int wl = warp * (kTileW / 8) + i;
+        const int w = w0 + wl;
+        if (w >= W) break;
+        const size_t idx = ((size_t)b * H + h) * W + w;
+        if (__ldg(valid + idx) == 0.0f) continue;          // in * valid == 0: contributes nothing
+        const float fx_ = __ldg(tx + idx), fy_ = __ldg(ty + idx);
+        if (!isfinite(fx_) || !isfinite(fy_)) continue;    // softsplat.py:300-301
+        const float d1 = __ldg(disp1 + idx);
+        const float e = expf(fminf(fmaxf(__fsub_rn(d1, mean), -50.0f), 50.0f));
+        const int nwx = (int)floorf(fx_), nwy = (int)floorf(fy_);
+        const int sex = nwx + 1, sey = nwy + 1;
+        // softsplat.py:314-317
+        const float wt[4] = {__fmul_rn(__fsub_rn((float)sex, fx_), __fsub_rn((float)sey, fy_)),    // NW
+                             __fmul_rn(__fsub_rn(fx_, (float)nwx), __fsub_rn((float)sey, fy_)),    // NE
+                             __fmul_rn(__fsub_rn((float)sex, fx_), __fsub_rn(fy_, (float)nwy)),    // SW
+                             __fmul_rn(__fsub_rn(fx_, (float)nwx), __fsub_rn(fy_, (float)nwy))};   // SE
+        const int txs[4] = {nwx, sex, nwx, sex};
+        const int tys[4] = {nwy, nwy, sey, sey};
+        float v[kGroups * 4];
+        const float* row = tile + wl * pitch;
+#pragma unroll
+        for (int k = 0; k < kGroups * 4; ++k) v[k] = __fmul_rn(row[lane + 32 * k], e);
+        const float tail0 = __fmul_rn(d1, e);  // the disparity channel and the normaliser channel
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (txs[t] < 0 || txs[t] >= W || tys[t] < 0 || tys[t] >= H) continue;
+            float* dst = accum + (((size_t)b * H + tys[t]) * W + txs[t]) * CP;
+            const float wgt = wt[t];
+#pragma unroll
+            for (int j = 0; j < kGroups; ++j)
+                red_add_v4(dst + j * 128 + 4 * lane, __fmul_rn(v[4 * j], wgt), __fmul_rn(v[4 * j + 1], wgt),
+                           __fmul_rn(v[4 * j + 2], wgt), __fmul_rn(v[4 * j + 3], wgt));
+            if (lane == 0) red_add_v2(dst + C, __fmul_rn(tail0, wgt), __fmul_rn(e, wgt));
+        }
+    }
+}
+
+// ---- forward warp, kernel C: normalise, mask, NCHW re-layout, matching cost -------------------------------------
+template <int kGroups>
+__global__ void __launch_bounds__(kWarpThreads)
+warp_finalize_kernel(const float* __restrict__ accum, const float* __restrict__ cur_fmap,
+                     float* __restrict__ out_disp, float* __restrict__ out_fmap, float* __restrict__ out_mask,
+                     float* __restrict__ out_cost, int H, int W) {
+    constexpr int C = kGroups * 128;
+    constexpr int CP = C + 4;
+    extern __shared__ float tile[];            // [C][33] then red[8][32][3] then maskv[32]
+    float* red = tile + C * 33;
+    float* maskv = red + 8 * 32 * 3;
+    const int w0 = blockIdx.x * kTileW, h = blockIdx.y, b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+#pragma unroll 1
+    for (int i = 0; i < kTileW / 8; ++i) {
+        const int wl = warp * (kTileW / 8) + i;
+        const int w = w0 + wl;
+        if (w >= W) {
+#pragma unroll
+            for (int k = 0; k < kGroups * 4; ++k) tile[(lane + 32 * k) * 33 + wl] = 0.0f;
+            if (lane == 0) maskv[wl] = 0.0f;
+            continue;
+        }
+        const size_t idx = ((size_t)b * H + h) * W + w;
+        const float* src = accum + idx * CP;
+        const float2 tail = *reinterpret_cast<const float2*>(src + C);
+        const float nrm = fmaxf(tail.y, 1e-7f);                 // clip(1e-7, None)   softsplat.py:268
+        const float m = (tail.y != 0.0f) ? 1.0f : 0.0f;         // softsplat.py:258
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j) {
+            const float4 a = *reinterpret_cast<const float4*>(src + j * 128 + 4 * lane);
+            tile[(lane + 32 * (4 * j + 0)) * 33 + wl] = __fdiv_rn(a.x, nrm);
+            tile[(lane + 32 * (4 * j + 1)) * 33 + wl] = __fdiv_rn(a.y, nrm);
+            tile[(lane + 32 * (4 * j + 2)) * 33 + wl] = __fdiv_rn(a.z, nrm);
+            tile[(lane + 32 * (4 * j + 3)) * 33 + wl] = __fdiv_rn(a.w, nrm);
+        }
+        if (lane == 0) {
+            out_disp[idx] = __fdiv_rn(tail.x, nrm);
+            out_mask[idx] = m;
+            maskv[wl] = m;
+        }
+    }
+    __syncthreads();
+
+    const int w = w0 + lane;
+    const bool in_w = w < W;
+    const size_t plane = (size_t)H * W;
+    const size_t base = ((size_t)b * C * H + h) * W + w;
+    float dot = 0.0f, s1 = 0.0f, sw = 0.0f;
+#pragma unroll 4
+    for (int c = warp; c < C; c += 8) {
+        const float v = tile[c * 33 + lane];
+        if (in_w) {
+            stg_stream_f1(out_fmap + base + (size_t)c * plane, v);
+            if (cur_fmap != nullptr) {
+                const float f = __ldg(cur_fmap + base + (size_t)c * plane);
+                dot = fmaf(f, v, dot);
+                s1 = fmaf(f, f, s1);
+                sw = fmaf(v, v, sw);
+            }
+        }
+    }
+    if (out_cost == nullptr || cur_fmap == nullptr) return;
+    red[(warp * 32 + lane) * 3 + 0] = dot;
+    red[(warp * 32 + lane) * 3 + 1] = s1;
+    red[(warp * 32 + lane) * 3 + 2] = sw;
+    __syncthreads();
+    if (warp == 0 && in_w) {
+        dot = s1 = sw = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            dot += red[(k * 32 + lane) * 3 + 0];
+            s1 += red[(k * 32 + lane) * 3 + 1];
+            sw += red[(k * 32 + lane) * 3 + 2];
+        }
+        // sum_c normalize(f)_c * normalize(v)_c  (F.normalize eps 1e-12), times the splat mask (tc_stereo.py:139-140)
+        const float den = __fmul_rn(fmaxf(sqrtf(s1), 1e-12f), fmaxf(sqrtf(sw), 1e-12f));
+        out_cost[((size_t)b * H + h) * W + w] = __fmul_rn(__fdiv_rn(dot, den), maskv[lane]);
+    }
+}
+
+// ---- get_backward_grid ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+backward_grid_kernel(const float* __restrict__ disp, const float* __restrict__ rel_T, const float* __restrict__ K,
+                     const float* __restrict__ K_inv, const float* __restrict__ baseline, float* __restrict__ grid,
+                     int H, int W) {
+    const int b = blockIdx.y;
+    const int HW = H * W;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW) return;
+    const Cam c = load_cam(rel_T, K, K_inv, baseline, b);
+    const int y = i / W, x = i - y * W;
+    const float d = fmaxf(__ldg(disp + (size_t)b * HW + i), 0.01f);            // geo_utils.py:217
+    const float depth = __fdiv_rn(c.bf, fmaxf(d, 0.001f));
+    float P[3];
+    project(c, depth, (float)x, (float)y, P);
+    float u, v;
+    reproject(c, P, u, v);
+    if (!(P[2] > 0.0f)) { u = -1.0f; v = -1.0f; }                              // geo_utils.py:229,233
+    grid[((size_t)b * 2 + 0) * HW + i] = u;
+    grid[((size_t)b * 2 + 1) * HW + i] = v;
+}
+
+// ---- bilinear_sampler --------------------------------------------------------------------------------------------------
+// grid_sample(bilinear, zeros, align_corners=True) on pixel coordinates, including the wrapper's normalise and
+// ATen's un-normalise round trip.  One thread per (output pixel, channel slice); weights computed once.
+__global__ void __launch_bounds__(256)
+bilinear_sample_kernel(const float* __restrict__ img, const float* __restrict__ grid_xy, float* __restrict__ out,
+                       int C, int Hi, int Wi, int Ho, int Wo, int c_per_slice) {
+    const int b = blockIdx.z;
+    const int HWo = Ho * Wo;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HWo) return;
+    const float gx = __ldg(grid_xy + ((size_t)b * 2 + 0) * HWo + i);
+    const float gy = __ldg(grid_xy + ((size_t)b * 2 + 1) * HWo + i);
+    const float wm1 = (float)(Wi - 1), hm1 = (float)(Hi - 1);
+    const float xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, gx), wm1), 1.0f);                  // utils.py:86
+    const float yn = (Hi > 1) ? __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, gy), hm1), 1.0f) : gy;  // utils.py:87-88
+    const float ix = __fmul_rn(__fmul_rn(__fadd_rn(xn, 1.0f), 0.5f), wm1);
+    const float iy = __fmul_rn(__fmul_rn(__fadd_rn(yn, 1.0f), 0.5f), hm1);
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float x1f = __fadd_rn(x0f, 1.0f), y1f = __fadd_rn(y0f, 1.0f);
+    const float w_nw = __fmul_rn(__fsub_rn(x1f, ix), __fsub_rn(y1f, iy));
+    const float w_ne = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(y1f, iy));
+    const float w_sw = __fmul_rn(__fsub_rn(x1f, ix), __fsub_rn(iy, y0f));
+    const float w_se = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(iy, y0f));
+    // NaN / huge coordinates fall out of range on every corner (float compares, then the int cast is safe)
+    const bool xin0 = (x0f >= 0.0f) && (x0f <= wm1), xin1 = (x1f >= 0.0f) && (x1f <= wm1);
+    const bool yin0 = (y0f >= 0.0f) && (y0f <= hm1), yin1 = (y1f >= 0.0f) && (y1f <= hm1);
+    const int x0 = xin0 ? (int)x0f : 0, x1 = xin1 ? (int)x1f : 0;
+    const int y0 = yin0 ? (int)y0f : 0, y1 = yin1 ? (int)y1f : 0;
+    const bool nw = xin0 && yin0, ne = xin1 && yin0, sw = xin0 && yin1, se = xin1 && yin1;
+    const size_t plane_i = (size_t)Hi * Wi;
+    const int c_begin = blockIdx.y * c_per_slice;
+    const int c_end = min(C, c_begin + c_per_slice);
+    const float* src = img + ((size_t)b * C + c_begin) * plane_i;
+    float* dst = out + ((size_t)b * C + c_begin) * HWo + i;
+    for (int c = c_begin; c < c_end; ++c, src += plane_i, dst += HWo) {
+        float r = 0.0f;
+        if (nw) r = __fmul_rn(__ldg(src + (size_t)y0 * Wi + x0), w_nw);
+        if (ne) r = __fadd_rn(r, __fmul_rn(__ldg(src + (size_t)y0 * Wi + x1), w_ne));
+        if (sw) r = __fadd_rn(r, __fmul_rn(__ldg(src + (size_t)y1 * Wi + x0), w_sw));
+        if (se) r = __fadd_rn(r, __fmul_rn(__ldg(src + (size_t)y1 * Wi + x1), w_se));
+        *dst = r;
+    }
+}
+
+// ---- 0.5 * interpolate(grid, 0.5, bilinear, align_corners=True) ------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grid_halve_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int Ho, int Wo, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int xo = (int)(i % Wo);
+    const int yo = (int)((i / Wo) % Ho);
+    const long long bc = i / ((long long)Wo * Ho);
+    // ATen area_pixel_compute_scale with align_corners: (in - 1) / (out - 1), 0 when out == 1
+    const float sh = (Ho > 1) ? __fdiv_rn((float)(H - 1), (float)(Ho - 1)) : 0.0f;
+    const float sw = (Wo > 1) ? __fdiv_rn((float)(W - 1), (float)(Wo - 1)) : 0.0f;
+    const float ys = __fmul_rn(sh, (float)yo), xs = __fmul_rn(sw, (float)xo);
+    const int y0 = (int)ys, x0 = (int)xs;
+    const int yp = (y0 < H - 1) ? 1 : 0, xp = (x0 < W - 1) ? 1 : 0;
+    const float ly1 = __fsub_rn(ys, (float)y0), ly0 = __fsub_rn(1.0f, ly1);
+    const float lx1 = __fsub_rn(xs, (float)x0), lx0 = __fsub_rn(1.0f, lx1);
+    const float* p = in + bc * (long long)H * W + (long long)y0 * W + x0;
+    const float v00 = __ldg(p), v01 = __ldg(p + xp), v10 = __ldg(p + (long long)yp * W), v11 = __ldg(p + (long long)yp * W + xp);
+    const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
+    const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
+    out[i] = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot)));
+}
+
+static size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
+
+struct WarpScratch {
+    size_t sums, accum, disp1, tx, ty, valid, total;
+};
+static WarpScratch warp_scratch_layout(int B, int C, int H, int W) {
+    WarpScratch s;
+    const size_t npix = (size_t)B * H * W;
+    s.sums = 0;
+    s.accum = align256((size_t)B * sizeof(double));
+    s.disp1 = s.accum + align256(npix * (C + 4) * sizeof(float));
+    s.tx = s.disp1 + align256(npix * sizeof(float));
+    s.ty = s.tx + align256(npix * sizeof(float));
+    s.valid = s.ty + align256(npix * sizeof(float));
+    s.total = s.valid + align256(npix * sizeof(float));
+    return s;
+}
+
+}  // namespace tcs
+
+extern "C" long long tcs_warp_scratch_bytes(int B, int C, int H, int W) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    return (long long)tcs::warp_scratch_layout(B, C, H, W).total;
+}
+
+extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const float* rel_T, const float* K,
+                                const float* K_inv, const float* baseline, const float* cur_fmap,
+                                float* out_disp, float* out_fmap, float* out_mask, float* out_cost,
+                                void* scratch, int B, int C, int H, int W, int per_sample_mean, void* stream) {
+    using namespace tcs;
+    TCS_REQUIRE(disp && fmap && rel_T && K && K_inv && baseline && out_disp && out_fmap && out_mask && scratch,
+                TCS_E_BADARG, "tcs_warp_forward: null pointer");
+    TCS_REQUIRE(out_cost == nullptr || cur_fmap != nullptr, TCS_E_BADARG, "tcs_warp_forward: out_cost needs cur_fmap");
+    TCS_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, TCS_E_BADARG, "tcs_warp_forward: non-positive size");
+    TCS_REQUIRE(C == 128 || C == 256 || C == 384 || C == 512, TCS_E_SHAPE, "tcs_warp_forward: C=%d must be 128, 256, 384 or 512", C);
+    TCS_REQUIRE(H <= 65535 && B <= 65535, TCS_E_SHAPE, "tcs_warp_forward: H and B must be <= 65535");
+    TCS_REQUIRE(aligned16(fmap) && aligned16(scratch) && aligned16(cur_fmap), TCS_E_ALIGN,
+                "tcs_warp_forward: fmap, cur_fmap and scratch must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const WarpScratch L = warp_scratch_layout(B, C, H, W);
+    char* base = static_cast<char*>(scratch);
+    double* sums = reinterpret_cast<double*>(base + L.sums);
+    float* accum = reinterpret_cast<float*>(base + L.accum);
+    float* disp1 = reinterpret_cast<float*>(base + L.disp1);
+    float* tx = reinterpret_cast<float*>(base + L.tx);
+    float* ty = reinterpret_cast<float*>(base + L.ty);
+    float* valid = reinterpret_cast<float*>(base + L.valid);
+
+    TCS_CHECK_CUDA(cudaMemsetAsync(base, 0, L.disp1, s));   // sums + accumulator
+    {
+        dim3 grid(ceil_div(H * W, 256), B);
+        warp_geometry_kernel<<<grid, 256, 0, s>>>(disp, rel_T, K, K_inv, baseline, disp1, tx, ty, valid, sums, H, W);
+        TCS_CHECK_LAUNCH("tcs_warp_forward(geometry)");
+    }
+    const dim3 grid(ceil_div(W, kTileW), H, B);
+    const size_t smem_splat = (size_t)kTileW * (C + 1) * sizeof(float);
+    const size_t smem_fin = ((size_t)C * 33 + 8 * 32 * 3 + 32) * sizeof(float);
+#define TCS_WARP_CASE(G)                                                                                              \
+    case G: {                                                                                                         \
+        static bool attr_done = false;                                                                                \
+        if (!attr_done) {                                                                                             \
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_splat_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_splat)); \
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_finalize_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin)); \
+            attr_done = true;                                                                                         \
+        }                                                                                                             \
+        warp_splat_kernel<G><<<grid, kWarpThreads, smem_splat, s>>>(fmap, disp1, tx, ty, valid, sums, accum, B, H, W, per_sample_mean); \
+        TCS_CHECK_LAUNCH("tcs_warp_forward(splat)");                                                                  \
+        warp_finalize_kernel<G><<<grid, kWarpThreads, smem_fin, s>>>(accum, cur_fmap, out_disp, out_fmap, out_mask, out_cost, H, W); \
+        TCS_CHECK_LAUNCH("tcs_warp_forward(finalize)");                                                               \
+    } break;
+    switch (C / 128) {
+        TCS_WARP_CASE(1)
+        TCS_WARP_CASE(2)
+        TCS_WARP_CASE(3)
+        TCS_WARP_CASE(4)
+    }
+#undef TCS_WARP_CASE
+    return 0;
+}
+
+extern "C" int tcs_backward_grid(const float* disp, const float* rel_T, const float* K, const float* K_inv,
+                                 const float* baseline, float* grid, int B, int H, int W, void* stream) {
+    using namespace tcs;
+    TCS_REQUIRE(disp && rel_T && K && K_inv && baseline && grid, TCS_E_BADARG, "tcs_backward_grid: null pointer");
+    TCS_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, TCS_E_BADARG, "tcs_backward_grid: bad sizes");
+    dim3 g(ceil_div(H * W, 256), B);
+    backward_grid_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(disp, rel_T, K, K_inv, baseline, grid, H, W);
+    TCS_CHECK_LAUNCH("tcs_backward_grid");
+    return 0;
+}
+
+extern "C" int tcs_bilinear_sample(const float* img, const float* grid_xy, float* out,
+                                   int B, int C, int Hi, int Wi, int Ho, int Wo, void* stream) {
+    using namespace tcs;
+    TCS_REQUIRE(img && grid_xy && out, TCS_E_BADARG, "tcs_bilinear_sample: null pointer");
+    TCS_REQUIRE(B > 0 && B <= 65535 && C > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, TCS_E_BADARG, "tcs_bilinear_sample: bad sizes");
+    // enough CTAs to fill the machine, few enough slices that the weights are amortised
+    const int pix_blocks = ceil_div(Ho * Wo, 256);
+    int slices = ceil_div(4 * num_sms(), pix_blocks * B);
+    slices = slices < 1 ? 1 : (slices > C ? C : slices);
+    const int c_per_slice = ceil_div(C, slices);
+    slices = ceil_div(C, c_per_slice);
+    TCS_REQUIRE(slices <= 65535, TCS_E_SHAPE, "tcs_bilinear_sample: too many channel slices");
+    dim3 g(pix_blocks, slices, B);
+    bilinear_sample_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(img, grid_xy, out, C, Hi, Wi, Ho, Wo, c_per_slice);
+    TCS_CHECK_LAUNCH("tcs_bilinear_sample");
+    return 0;
+}
+
+extern "C" int tcs_grid_halve(const float* in, float* out, int B, int H, int W, void* stream) {
+    using namespace tcs;
+    TCS_REQUIRE(in && out, TCS_E_BADARG, "tcs_grid_halve: null pointer");
+    TCS_REQUIRE(B > 0 && H >= 2 && W >= 2, TCS_E_SHAPE, "tcs_grid_halve: need H, W >= 2");
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = (long long)B * 2 * Ho * Wo;
+    grid_halve_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, H, W, Ho, Wo, total);
+    TCS_CHECK_LAUNCH("tcs_grid_halve");
+    return 0;
+}

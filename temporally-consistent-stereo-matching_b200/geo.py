@@ -1,0 +1,158 @@
+"""Temporal step on top of libtcs_b200.so — the reference's geometry functions, same names and meaning.
+
+Mirrors core/utils/geo_utils.py (warp :158-198, get_backward_grid :201-236, cal_relative_transformation
+:148-155) and core/utils/utils.py (bilinear_sampler :82-97) of the reference, plus the hidden-state warp
+loop of core/tc_stereo.py:159-163.  CUDA tensors only, inference only, no fallback.
+"""
+import torch
+
+from . import _lib
+
+_scratch = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(name, t, shape=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor (libtcs_b200 has no CPU path)" % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return t
+
+
+def _warp_scratch(B, C, H, W, device):
+    """Scratch of tcs_warp_forward, cached per shape and stream-ordered like any torch buffer."""
+    key = (device.index, B, C, H, W)
+    buf = _scratch.get(key)
+    if buf is None:
+        n = _lib.warp_scratch_bytes(B, C, H, W)
+        if n <= 0:
+            raise ValueError("bad warp shape B=%d C=%d H=%d W=%d" % (B, C, H, W))
+        buf = torch.empty(n, dtype=torch.uint8, device=device)
+        _scratch.clear()          # one shape at a time is the common case; do not hoard HBM
+        _scratch[key] = buf
+    return buf
+
+
+def _camera_args(relative_T, K, K_inv, baseline, B):
+    relative_T = _f32c("relative_T", relative_T, (B, 4, 4))
+    K = _f32c("K", K, (B, 3, 3))
+    K_inv = _f32c("K_inv", K_inv, (B, 3, 3))
+    baseline = _f32c("baseline", baseline).reshape(-1)
+    if baseline.numel() != B:
+        raise ValueError("baseline must have %d entries, got %d" % (B, baseline.numel()))
+    return relative_T, K, K_inv, baseline
+
+
+def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, per_sample_mean=False):
+    """warp() plus the matching cost of core/tc_stereo.py:139-140 fused into the normalise kernel.
+
+    -> (disp', fmap', mask, cost)  with cost None when cur_fmap is None."""
+    disp = _f32c("disp", disp)
+    fmap = _f32c("fmap", fmap)
+    if disp.dim() != 4 or disp.shape[1] != 1:
+        raise ValueError("disp must be [B,1,H,W], got %s" % (tuple(disp.shape),))
+    B, _, H, W = disp.shape
+    if fmap.dim() != 4 or fmap.shape[0] != B or fmap.shape[2:] != disp.shape[2:]:
+        raise ValueError("fmap must be [B,C,H,W] matching disp, got %s" % (tuple(fmap.shape),))
+    C = fmap.shape[1]
+    relative_T, K, K_inv, baseline = _camera_args(relative_T, K, K_inv, baseline, B)
+    if cur_fmap is not None:
+        cur_fmap = _f32c("cur_fmap", cur_fmap, fmap.shape)
+    dev = disp.device
+    out_disp = torch.empty_like(disp)
+    out_fmap = torch.empty_like(fmap)
+    out_mask = torch.empty_like(disp)
+    out_cost = torch.empty_like(disp) if cur_fmap is not None else None
+    with torch.cuda.device(dev):
+        scratch = _warp_scratch(B, C, H, W, dev)
+        _lib.call("tcs_warp_forward", disp.data_ptr(), fmap.data_ptr(), relative_T.data_ptr(), K.data_ptr(),
+                  K_inv.data_ptr(), baseline.data_ptr(), cur_fmap.data_ptr() if cur_fmap is not None else None,
+                  out_disp.data_ptr(), out_fmap.data_ptr(), out_mask.data_ptr(),
+                  out_cost.data_ptr() if out_cost is not None else None, scratch.data_ptr(),
+                  B, C, H, W, 1 if per_sample_mean else 0, _stream())
+    return out_disp, out_fmap, out_mask, out_cost
+
+
+def warp(disp, fmap, relative_T, K, K_inv, baseline):
+    """ref: geo_utils.py:158-198.  -> (current_disp [B,1,H,W], current_fmap [B,C,H,W], warped_mask [B,1,H,W])."""
+    d, f, m, _ = warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline)
+    return d, f, m
+
+
+def get_backward_grid(disp, relative_T, K, K_inv, baseline):
+    """ref: geo_utils.py:201-236.  disp [B,1,H,W] -> previous-frame pixel coordinates [B,2,H,W] (x, y)."""
+    disp = _f32c("disp", disp)
+    if disp.dim() != 4 or disp.shape[1] != 1:
+        raise ValueError("disp must be [B,1,H,W], got %s" % (tuple(disp.shape),))
+    B, _, H, W = disp.shape
+    relative_T, K, K_inv, baseline = _camera_args(relative_T, K, K_inv, baseline, B)
+    grid = torch.empty((B, 2, H, W), dtype=torch.float32, device=disp.device)
+    with torch.cuda.device(disp.device):
+        _lib.call("tcs_backward_grid", disp.data_ptr(), relative_T.data_ptr(), K.data_ptr(), K_inv.data_ptr(),
+                  baseline.data_ptr(), grid.data_ptr(), B, H, W, _stream())
+    return grid
+
+
+def sample_planar(img, grid_xy):
+    """img [B,C,Hi,Wi] sampled at pixel coordinates grid_xy [B,2,Ho,Wo] (x plane, y plane)."""
+    img = _f32c("img", img)
+    grid_xy = _f32c("grid_xy", grid_xy)
+    B, C, Hi, Wi = img.shape
+    if grid_xy.dim() != 4 or grid_xy.shape[0] != B or grid_xy.shape[1] != 2:
+        raise ValueError("grid_xy must be [B,2,Ho,Wo], got %s" % (tuple(grid_xy.shape),))
+    Ho, Wo = grid_xy.shape[2:]
+    out = torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.call("tcs_bilinear_sample", img.data_ptr(), grid_xy.data_ptr(), out.data_ptr(), B, C, Hi, Wi, Ho, Wo, _stream())
+    return out
+
+
+def bilinear_sampler(img, coords, mode='bilinear', mask=False, align_corners=True):
+    """ref: utils.py:82-97.  coords [B,Ho,Wo,2] in pixels (x, y).  Only the reference's own use
+    (bilinear, align_corners=True) is implemented."""
+    if mode != 'bilinear' or not align_corners:
+        raise NotImplementedError("libtcs_b200 implements bilinear_sampler(mode='bilinear', align_corners=True) only")
+    if coords.dim() != 4 or coords.shape[-1] != 2:
+        raise ValueError("coords must be [B,Ho,Wo,2], got %s" % (tuple(coords.shape),))
+    out = sample_planar(img, coords.permute(0, 3, 1, 2))   # a no-copy view when coords came from a planar grid
+    if mask:
+        H, W = img.shape[-2:]
+        xg = 2 * coords[..., :1] / (W - 1) - 1
+        yg = 2 * coords[..., 1:] / (H - 1) - 1 if H > 1 else coords[..., 1:]
+        return out, ((xg > -1) & (yg > -1) & (xg < 1) & (yg < 1)).float()
+    return out
+
+
+def halve_grid(grid_xy):
+    """ref: tc_stereo.py:163.  0.5 * F.interpolate(grid, scale_factor=0.5, 'bilinear', align_corners=True)."""
+    grid_xy = _f32c("grid_xy", grid_xy)
+    B, two, H, W = grid_xy.shape
+    if two != 2:
+        raise ValueError("grid_xy must be [B,2,H,W]")
+    out = torch.empty((B, 2, H // 2, W // 2), dtype=torch.float32, device=grid_xy.device)
+    with torch.cuda.device(grid_xy.device):
+        _lib.call("tcs_grid_halve", grid_xy.data_ptr(), out.data_ptr(), B, H, W, _stream())
+    return out
+
+
+def warp_hidden_states(net_list, backward_grid):
+    """ref: tc_stereo.py:159-163.  Sample each hidden-state level with the (progressively halved) grid."""
+    out = []
+    grid = backward_grid
+    for i, net in enumerate(net_list):
+        out.append(sample_planar(net, grid))
+        if i + 1 < len(net_list):
+            grid = halve_grid(grid)
+    return out
+
+
+def cal_relative_transformation(T1, T2):
+    """ref: geo_utils.py:148-155.  T2 @ inv(T1) for world2cam poses.  4x4 bookkeeping, stays in torch."""
+    return torch.matmul(T2, torch.linalg.inv(T1))

@@ -1,0 +1,147 @@
+"""CPU-side checks: the C-ABI library loads and exports exactly what include/tcs_b200.h declares, the host
+logic (sharding, shapes, drop-in rebinding) behaves, and the 2-rank gloo path reduces metrics."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "tcs_b200.h")
+
+
+def header_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tcs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import tcs_b200
+    lib = ctypes.CDLL(tcs_b200._lib.LIB_PATH)
+    names = header_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "libtcs_b200.so does not export %s" % n
+    assert sorted(tcs_b200._lib.SIGNATURES) == names, "ctypes signatures and header disagree"
+    assert lib.tcs_abi_version() == 1
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    """Validation happens before any CUDA call, so the status codes can be checked on a CPU-only host."""
+    import tcs_b200
+    lib = tcs_b200._lib.load()
+    assert lib.tcs_corr_lookup(None, None, None, None, None, 0, None, 1, 1, 1, 16, 4, 4, None) == -1
+    assert b"null" in lib.tcs_last_error()
+    assert lib.tcs_corr_prepass(ctypes.c_void_p(256), ctypes.c_void_p(256), None, None, 1, 100, 1, 1, 0, None) == -2
+    assert lib.tcs_warp_scratch_bytes(0, 256, 4, 4) == 0
+    n = lib.tcs_warp_scratch_bytes(2, 256, 136, 240)
+    assert n >= 2 * 136 * 240 * 260 * 4 and n % 256 == 0
+    with pytest.raises(tcs_b200._lib.TcsError):
+        tcs_b200._lib.call("tcs_grid_halve", None, None, 1, 4, 4, None)
+
+
+def test_no_cpu_fallback():
+    import tcs_b200
+    f = torch.randn(1, 64, 2, 16)
+    with pytest.raises(TypeError):
+        tcs_b200.CorrBlock1D(f, f)
+    with pytest.raises(TypeError):
+        tcs_b200.warp(torch.ones(1, 1, 2, 16), torch.randn(1, 128, 2, 16), torch.eye(4)[None], torch.eye(3)[None],
+                      torch.eye(3)[None], torch.ones(1, 1))
+    src = ""
+    pkg = os.path.join(ROOT, "temporally-consistent-stereo-matching_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src += open(os.path.join(pkg, fn)).read()
+    assert "import oracle" not in src and "from oracle" not in src and "tcs_oracle" not in src, "the product must not touch the oracle"
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    code = ("import importlib, sys; sys.path.insert(0, %r);"
+            "m = importlib.import_module('temporally-consistent-stereo-matching_b200._lib');"
+            "m.LIB_PATH = %r; m._lib = None; m.load()") % (ROOT, str(tmp_path / "nope.so"))
+    # import of the package itself loads the real library; point the loader elsewhere afterwards
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0 and "not built" in r.stderr
+
+
+def test_sharding_covers_every_sequence_once():
+    import tcs_b200
+    for n in (1, 2, 4, 8):
+        seen = []
+        for r in range(n):
+            seen += tcs_b200.shard_sequences(64, n, r)
+        assert sorted(seen) == list(range(64))
+        assert all(len(tcs_b200.shard_sequences(64, n, r)) == 64 // n for r in range(n))
+    with pytest.raises(ValueError):
+        tcs_b200.shard_sequences(4, 2, 2)
+
+
+def test_feature_shapes_of_the_baseline_configs():
+    from tcs_b200 import sequence
+    assert sequence.feature_shape(540, 960) == (136, 240)
+    assert sequence.feature_shape(480, 640) == (120, 160)
+    assert sequence.feature_shape(375, 1242) == (96, 312)
+    assert sequence.feature_shape(1080, 1920) == (272, 480)
+
+
+def test_relative_pose_round_trip():
+    from tcs_b200 import sequence
+    prev = torch.stack([sequence.synthetic_pose(3, s) for s in range(4)])
+    cur = torch.stack([sequence.synthetic_pose(4, s) for s in range(4)])
+    fwd, inv = sequence.relative_pose(prev, cur)
+    eye = torch.eye(4).expand(4, 4, 4)
+    assert torch.allclose(fwd @ inv, eye, atol=1e-6)
+    assert torch.allclose(fwd @ prev, cur, atol=1e-6)        # world2cam convention (geo_utils.py:148-155)
+
+
+def test_dropin_rebinds_and_restores_names():
+    import tcs_b200
+    fake = types.ModuleType("core.tc_stereo")
+    sentinel = object()
+    for n in ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler"):
+        setattr(fake, n, sentinel)
+    new = tcs_b200.install(fake, precision="bf16")
+    assert fake.warp is tcs_b200.warp and fake.get_backward_grid is tcs_b200.get_backward_grid
+    assert issubclass(fake.CorrBlock1D, tcs_b200.CorrBlock1D) and fake.CorrBlock1D.__name__ == "CorrBlock1D"
+    assert set(new) == {"CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler"}
+    tcs_b200.uninstall(fake)
+    assert fake.warp is sentinel and fake.CorrBlock1D is sentinel
+    with pytest.raises(AttributeError):
+        tcs_b200.install(types.ModuleType("empty"))
+
+
+GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+import tcs_b200
+from tcs_b200 import sequence
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"], rank=int(os.environ["RANK"]), world_size=2)
+mine = tcs_b200.shard_sequences(10, 2, dist.get_rank())
+frames = float(len(mine) * 5)
+tot = sequence.reduce_metrics([frames, float(sum(mine))])
+assert tot == [50.0, 45.0], tot
+dist.barrier()
+dist.destroy_process_group()
+print("ok", dist.get_rank() if False else os.environ["RANK"])
+"""
+
+
+def test_two_rank_gloo_metric_reduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER % ROOT)
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0 and "ok" in out, out

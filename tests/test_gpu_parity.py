@@ -1,0 +1,349 @@
+"""Parity of the CUDA path (through the C-ABI of libtcs_b200.so) with the oracle and the golden vectors.
+
+Gates: integer-valued / mask outputs bit-exact; fp32 floats |d| <= 1e-6 + 1e-5 |ref|;
+plain bf16 build |d corr| <= 2^-8; bf16x3 / fp16x3 build at fp32 level.  Outputs whose conditioning is
+set by pixel coordinates (splat, backward grid, hidden-state gather) carry the looser bound stated inline.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, assert_exact, load_golden
+from oracle import tcs_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tcs():
+    import tcs_b200
+    return tcs_b200
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def make_fmaps(B, C, H, W, seed, shift=0):
+    g = torch.Generator().manual_seed(seed)
+    f1 = torch.randn(B, C, H, W, generator=g)
+    f2 = torch.roll(f1, -shift, dims=3) + 0.3 * torch.randn(B, C, H, W, generator=g) if shift else torch.randn(B, C, H, W, generator=g)
+    return f1, f2
+
+
+def make_coords(B, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    xs = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+    c = xs - torch.rand(B, 1, H, W, generator=g) * (W / 4)
+    flat = c.view(-1)
+    n = flat.numel()
+    pick = torch.randperm(n, generator=g)
+    flat[pick[: n // 100]] = -9.0
+    flat[pick[n // 100: n // 50]] = W + 7.5
+    flat[pick[n // 50: n // 10]] = flat[pick[n // 50: n // 10]].round()
+    return c
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (1) build
+# ---------------------------------------------------------------------------------------------------------
+
+def test_prepass_normalise(tcs):
+    f1, _ = make_fmaps(2, 256, 5, 37, 7)
+    hi, lo, n32 = tcs.normalized_operands(f1.cuda(), "bf16x3", want_n32=True)
+    ref = orc.normalize_features(f1.numpy()).transpose(0, 2, 3, 1)
+    assert_close(host(n32), ref, rtol=1e-6, atol=1e-7, what="n32")
+    split = host(hi.float()) + host(lo.float())
+    assert np.abs(split - host(n32)).max() <= 2.0 ** -16 * np.abs(host(n32)).max(), "hi+lo does not carry 16 mantissa bits"
+    hi16, lo16, _ = tcs.normalized_operands(f1.cuda(), "fp16x3")
+    split16 = (host(hi16.float()) + host(lo16.float())) / 256.0
+    assert np.abs(split16 - host(n32)).max() <= 2.0 ** -20, "fp16 hi+lo"
+
+
+@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth"])
+@pytest.mark.parametrize("precision,rtol,atol", [("fp32", 1e-5, 1e-6), ("bf16x3", 1e-5, 2e-6), ("fp16x3", 1e-5, 1e-6),
+                                                 ("bf16", 0.0, 2.0 ** -8), ("fp16", 0.0, 2.0 ** -10)])
+def test_build_golden(tcs, case, precision, rtol, atol):
+    g = load_golden(case)
+    _, levels = tcs.build_pyramid(cuda(g["fmap1"]), cuda(g["fmap2"]), 4, precision)
+    for l in range(4):
+        assert_close(host(levels[l]), g["level%d" % l], rtol=rtol, atol=atol, what="%s %s level %d" % (case, precision, l))
+
+
+SHAPES = [(1, 136, 240), (2, 120, 160), (1, 96, 312), (1, 17, 100), (1, 3, 250)]
+
+
+@pytest.mark.parametrize("B,H,W", SHAPES)
+@pytest.mark.parametrize("precision,rtol,atol", [("fp32", 1e-5, 1e-6), ("bf16x3", 1e-5, 2e-6), ("bf16", 0.0, 2.0 ** -8)])
+def test_build_full_size(tcs, B, H, W, precision, rtol, atol):
+    f1, f2 = make_fmaps(B, 256, H, W, 1234 + H, shift=7)
+    _, levels = tcs.build_pyramid(f1.cuda(), f2.cuda(), 4, precision)
+    ref64 = orc.corr_volume(f1.numpy(), f2.numpy(), np.float64)
+    lv = [host(x) for x in levels]
+    assert_close(lv[0], ref64, rtol=rtol, atol=atol, what="%s level 0 %dx%d" % (precision, H, W))
+    # pooling is exact arithmetic on the kernel's own level below: (a + b) * 0.5 in fp32
+    pooled = orc.corr_pyramid(lv[0], 4)
+    for l in range(1, 4):
+        assert lv[l].shape[-1] == W >> l
+        assert_exact(lv[l], pooled[l], what="%s level %d is not the exact pool of level %d" % (precision, l, l - 1))
+
+
+def test_build_properties_540p(tcs):
+    """Size-independent properties at the headline shape: self-correlation has a unit diagonal, symmetric
+    volume, values in [-1, 1], level means preserved."""
+    f1, _ = make_fmaps(1, 256, 136, 240, 99)
+    _, levels = tcs.build_pyramid(f1.cuda(), f1.cuda(), 4, "bf16x3")
+    v = levels[0]
+    diag = torch.diagonal(v, dim1=2, dim2=3)
+    assert (diag - 1).abs().max().item() < 2e-6
+    assert (v - v.transpose(2, 3)).abs().max().item() < 1e-6
+    assert v.abs().max().item() <= 1 + 2e-6
+    for l in range(1, 4):
+        assert abs(levels[l].double().mean().item() - v.double().mean().item()) < 1e-7
+
+
+def test_build_two_n_tiles_and_m_tail(tcs):
+    """W2 > 256 takes two UMMA N tiles; W1 not a multiple of 128 exercises the masked M tail."""
+    g = torch.Generator().manual_seed(5)
+    f1 = torch.randn(1, 128, 4, 200, generator=g)
+    f2 = torch.randn(1, 128, 4, 480, generator=g)
+    _, levels = tcs.build_pyramid(f1.cuda(), f2.cuda(), 4, "bf16x3")
+    ref = orc.corr_volume(f1.numpy(), f2.numpy(), np.float64)
+    assert_close(host(levels[0]), ref, rtol=1e-5, atol=2e-6, what="W1=200 W2=480")
+    pooled = orc.corr_pyramid(host(levels[0]), 4)
+    for l in range(1, 4):
+        assert_exact(host(levels[l]), pooled[l], what="level %d" % l)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (2) lookup, (3) alternate
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth"])
+def test_lookup_golden(tcs, case):
+    g = load_golden(case)
+    blk = tcs.CorrBlock1D.from_levels([cuda(g["level%d" % l]) for l in range(4)], radius=4)
+    out = blk(cuda(g["coords"]))
+    assert out.shape == g["lookup"].shape and out.is_contiguous() and out.dtype == torch.float32
+    assert_close(host(out), g["lookup"], what=case + " lookup vs reference")
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 136, 240), (3, 120, 160), (1, 96, 312), (1, 5, 67)])
+@pytest.mark.parametrize("radius", [4, 3])
+def test_lookup_full_size(tcs, B, H, W, radius):
+    f1, f2 = make_fmaps(B, 128, H, W, 11 + W)
+    blk = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), num_levels=4, radius=radius, precision="fp32")
+    coords = make_coords(B, H, W, 3)
+    out = blk(coords.cuda())
+    ref = orc.corr_lookup([host(x) for x in blk._levels], coords.numpy(), radius)
+    assert_close(host(out), ref, what="lookup %dx%dx%d r=%d" % (B, H, W, radius))
+
+
+def test_lookup_integer_coords_return_volume_entries(tcs):
+    f1, f2 = make_fmaps(1, 128, 8, 64, 21)
+    blk = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), precision="fp32")
+    xs = torch.arange(64, dtype=torch.float32).view(1, 1, 1, 64).expand(1, 1, 8, 64).contiguous()
+    out = host(blk(xs.cuda()))                       # tap k of level 0 == volume[w1, w1 + k]
+    vol = host(blk._levels[0])
+    for k in range(-4, 5):
+        w1 = np.arange(max(0, -k), min(64, 64 - k))
+        np.testing.assert_array_equal(out[0, k + 4][:, w1], vol[0][:, w1, w1 + k])
+
+
+def test_lookup_coords_view_and_nan(tcs):
+    g = load_golden("corr_small")
+    blk = tcs.CorrBlock1D.from_levels([cuda(g["level%d" % l]) for l in range(4)])
+    two = cuda(g["coords"])                          # [B,2,H,W]: channel 0 is read in place
+    one = two[:, :1].contiguous()
+    assert torch.equal(blk(two), blk(one))
+    bad = one.clone()
+    bad[0, 0, 0, :5] = float("nan")
+    bad[0, 0, 1, :5] = float("inf")
+    out = blk(bad)                                   # must not fault; other pixels unchanged
+    assert torch.equal(out[1], blk(one)[1])
+
+
+@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth"])
+def test_alternate_golden(tcs, case):
+    g = load_golden(case)
+    blk = tcs.CorrBlock1D(cuda(g["fmap1"]), cuda(g["fmap2"]), mode="alternate")
+    out = blk(cuda(g["coords"]))
+    assert_close(host(out), g["lookup"], rtol=1e-5, atol=2e-6, what=case + " alternate lookup vs reference")
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 136, 240), (1, 96, 312)])
+def test_alternate_equals_pyramid(tcs, B, H, W):
+    f1, f2 = make_fmaps(B, 256, H, W, 5)
+    coords = make_coords(B, H, W, 9).cuda()
+    a = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), mode="alternate")(coords)
+    p = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), mode="pyramid", precision="fp32")(coords)
+    assert_close(host(a), host(p), rtol=1e-5, atol=2e-6, what="alternate vs pyramid")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# first frame: argmax_disp, cost volume
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth"])
+def test_argmax_and_cost_volume_golden(tcs, case):
+    g = load_golden(case)
+    blk = tcs.CorrBlock1D.from_levels([cuda(g["level%d" % l]) for l in range(4)])
+    sparse_disp, main_cost, mask = blk.argmax_disp()
+    assert_exact(host(mask), g["mask"], what="argmax mask")
+    assert_exact(host(sparse_disp), g["sparse_disp"], what="sparse_disp")
+    assert_exact(host(main_cost), g["main_cost"], what="main_cost")
+    assert_exact(host(blk.get_cost_volume()), g["cost_volume"], what="cost volume")
+
+
+@pytest.mark.parametrize("B,H,W,shift", [(1, 136, 240, 9), (2, 60, 160, 3), (1, 20, 312, 0)])
+def test_argmax_full_size(tcs, B, H, W, shift):
+    f1, f2 = make_fmaps(B, 128, H, W, 77, shift=shift)
+    blk = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), precision="fp32")
+    outs = blk.argmax_disp()
+    ref = orc.argmax_disp(host(blk._levels[0]))
+    for name, a, r in zip(("sparse_disp", "main_cost", "mask"), outs, ref):
+        assert_exact(host(a), r, what="%s %dx%d" % (name, H, W))
+    if shift:
+        assert host(outs[2]).mean() > 0.5 and np.median(host(outs[0])[host(outs[2]) > 0]) == shift
+    assert_exact(host(blk.get_cost_volume()), orc.masked_cost_volume(host(blk._levels[0])), what="cost volume")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (4) temporal step
+# ---------------------------------------------------------------------------------------------------------
+
+def test_warp_golden(tcs):
+    g = load_golden("warp_small")
+    args = [cuda(g[k]) for k in ("disp", "fmap", "rel_T", "K", "K_inv", "baseline")]
+    d, f, m, c = tcs.warp_with_cost(*args, cur_fmap=cuda(g["cur_fmap"]))
+    assert_exact(host(m), g["warped_mask"], what="splat mask vs reference")
+    # splat outputs are ratios of sums weighted by (x - floor x): conditioned by the target coordinates' ulp
+    assert_close(host(d), g["warped_disp"], rtol=1e-5, atol=1e-5, what="warped disparity vs reference")
+    assert_close(host(f), g["warped_fmap"], rtol=1e-5, atol=1e-5, what="warped features vs reference")
+    assert_close(host(c), g["cost"], rtol=1e-5, atol=2e-6, what="matching cost vs reference")
+    d2, f2, m2 = tcs.warp(*args)
+    assert torch.equal(m2, m)
+
+
+def camera(B, H, W, seed):
+    rng = np.random.default_rng(seed)
+    K = np.zeros((B, 3, 3))
+    K[:, 0, 0] = K[:, 1, 1] = 0.5 * W
+    K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = 0.5 * W - 0.5, 0.5 * H - 0.5, 1.0
+    T = np.tile(np.eye(4), (B, 1, 1))
+    for b in range(B):
+        yaw = np.deg2rad(rng.uniform(-0.6, 0.6))
+        c, s = np.cos(yaw), np.sin(yaw)
+        cam2world = np.array([[c, 0, s, rng.uniform(-0.03, 0.03)], [0, 1, 0, rng.uniform(-0.01, 0.01)],
+                              [-s, 0, c, rng.uniform(0.02, 0.15)], [0, 0, 0, 1.0]])
+        T[b] = np.linalg.inv(cam2world)
+    f32 = lambda a: a.astype(np.float32)
+    return f32(K), f32(np.linalg.inv(K)), f32(T), f32(np.linalg.inv(T)), f32(np.full((B, 1), 0.25))
+
+
+@pytest.mark.parametrize("B,H,W,per_sample", [(1, 120, 160, False), (2, 136, 240, False), (2, 30, 75, True)])
+def test_warp_full_size(tcs, B, H, W, per_sample):
+    K, Kinv, T, Tinv, base = camera(B, H, W, 3)
+    g = torch.Generator().manual_seed(17)
+    disp = 0.5 + torch.rand(B, 1, H, W, generator=g) * (W / 16)
+    disp.view(-1)[::53] = 0.0
+    fmap = torch.randn(B, 256, H, W, generator=g)
+    cur = torch.randn(B, 256, H, W, generator=g)
+    d, f, m, c = tcs.warp_with_cost(disp.cuda(), fmap.cuda(), cuda(T), cuda(K), cuda(Kinv), cuda(base),
+                                    cur_fmap=cur.cuda(), per_sample_mean=per_sample)
+    rd, rf, rm = orc.warp(disp.numpy(), fmap.numpy(), T, K, Kinv, base, per_sample_mean=per_sample)
+    assert_exact(host(m), rm, what="splat mask")
+    assert 0.5 < rm.mean() < 1.0
+    assert_close(host(d), rd, rtol=1e-4, atol=1e-4, what="warped disparity")   # atomics order + exp ulp
+    assert_close(host(f), rf, rtol=1e-4, atol=1e-4, what="warped features")
+    rc = orc.matching_cost(cur.numpy(), host(f), host(m))
+    assert_close(host(c), rc, rtol=1e-5, atol=2e-6, what="matching cost")
+
+
+def test_warp_identity_pose_keeps_everything(tcs):
+    """Zero motion: every pixel lands on itself, the splat is the identity and the mask is all ones."""
+    B, H, W = 1, 24, 48
+    K, Kinv, _, _, base = camera(B, H, W, 1)
+    K[:, 0, 2], K[:, 1, 2] = 24.0, 12.0            # exactly representable intrinsics keep x -> x exact
+    Kinv = np.linalg.inv(K.astype(np.float64)).astype(np.float32)
+    T = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1))
+    g = torch.Generator().manual_seed(2)
+    disp = 1.0 + torch.rand(B, 1, H, W, generator=g) * 4
+    fmap = torch.randn(B, 128, H, W, generator=g)
+    d, f, m = tcs.warp(disp.cuda(), fmap.cuda(), cuda(T), cuda(K), cuda(Kinv), cuda(base))
+    rd, rf, rm = orc.warp(disp.numpy(), fmap.numpy(), T, K, Kinv, base)
+    assert_exact(host(m), rm, what="mask")
+    assert_close(host(d), rd, rtol=1e-4, atol=1e-4, what="disp")
+    assert_close(host(f), rf, rtol=1e-4, atol=1e-4, what="fmap")
+
+
+def test_backward_grid_and_hidden_states_golden(tcs):
+    g = load_golden("warp_small")
+    grid = tcs.get_backward_grid(cuda(g["disp_init"]), cuda(g["rel_T_inv"]), cuda(g["K"]), cuda(g["K_inv"]), cuda(g["baseline"]))
+    assert_close(host(grid), g["backward_grid"], rtol=1e-5, atol=1e-4, what="backward grid vs reference")
+    assert_exact(host(grid), orc.backward_grid(g["disp_init"], g["rel_T_inv"], g["K"], g["K_inv"], g["baseline"]),
+                 what="backward grid vs oracle (same arithmetic, bit for bit)")
+    for i in range(3):
+        gi = cuda(g["grid%d" % i])
+        out = tcs.sample_planar(cuda(g["net%d" % i]), gi)
+        assert_close(host(out), g["warped_net%d" % i], rtol=1e-5, atol=2e-6, what="hidden state %d vs reference" % i)
+        out2 = tcs.bilinear_sampler(cuda(g["net%d" % i]), gi.permute(0, 2, 3, 1))
+        assert torch.equal(out, out2)
+        if i < 2:
+            assert_close(host(tcs.halve_grid(gi)), g["grid%d" % (i + 1)], rtol=1e-5, atol=1e-5, what="halved grid %d" % i)
+
+
+def test_backward_grid_behind_camera_is_minus_one(tcs):
+    B, H, W = 1, 16, 32
+    K, Kinv, _, _, base = camera(B, H, W, 1)
+    T = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1))
+    T[:, 2, 3] = -100.0                              # everything ends up behind the camera
+    disp = torch.full((B, 1, H, W), 4.0)
+    grid = tcs.get_backward_grid(disp.cuda(), cuda(T), cuda(K), cuda(Kinv), cuda(base))
+    assert (grid == -1).all()
+    assert_exact(host(grid), orc.backward_grid(disp.numpy(), T, K, Kinv, base))
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 128, 136, 240), (2, 128, 68, 120), (1, 16, 34, 60), (1, 3, 7, 9)])
+def test_bilinear_sample_and_halve_full_size(tcs, B, C, H, W):
+    g = torch.Generator().manual_seed(4)
+    img = torch.tanh(torch.randn(B, C, H, W, generator=g))
+    grid = torch.stack([torch.rand(B, H, W, generator=g) * (W + 4) - 2, torch.rand(B, H, W, generator=g) * (H + 4) - 2], 1)
+    grid.view(-1)[::41] = -1.0
+    grid[:, :, 0, 0] = float("nan")
+    out = tcs.sample_planar(img.cuda(), grid.cuda())
+    assert_close(host(out), orc.bilinear_sample(img.numpy(), grid.numpy()), rtol=1e-5, atol=1e-6, what="bilinear sample")
+    if H >= 4:
+        clean = torch.nan_to_num(grid, nan=0.0)
+        assert_exact(host(tcs.halve_grid(clean.cuda())), orc.grid_halve(clean.numpy()), what="halved grid")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# error behaviour: loud failures, no fallback
+# ---------------------------------------------------------------------------------------------------------
+
+def test_cpu_tensors_are_rejected(tcs):
+    f = torch.randn(1, 64, 2, 16)
+    with pytest.raises(TypeError):
+        tcs.CorrBlock1D(f, f)
+    with pytest.raises(TypeError):
+        tcs.get_backward_grid(torch.zeros(1, 1, 2, 2), torch.eye(4)[None], torch.eye(3)[None], torch.eye(3)[None], torch.ones(1, 1))
+
+
+def test_bad_shapes_raise(tcs):
+    f = torch.randn(1, 100, 2, 16).cuda()           # C not a multiple of 64
+    with pytest.raises(RuntimeError):
+        tcs.CorrBlock1D(f, f)
+    f = torch.randn(1, 64, 2, 16).cuda()
+    with pytest.raises(ValueError):
+        tcs.CorrBlock1D(f, f, radius=20)
+    blk = tcs.CorrBlock1D(f, f)
+    with pytest.raises(ValueError):
+        blk(torch.zeros(1, 1, 3, 16).cuda())
+    with pytest.raises(RuntimeError):                # warp needs C in {128,...,512}
+        tcs.warp(torch.ones(1, 1, 2, 16).cuda(), f, torch.eye(4)[None].cuda(), torch.eye(3)[None].cuda(),
+                 torch.eye(3)[None].cuda(), torch.ones(1, 1).cuda())

