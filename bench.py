@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""Throughput of the TC-Stereo cost-volume hot path on B200: stereo frames/s at 540x960, 32 GRU iterations.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun by the driver)
+    python bench.py --impl reference ...                      (the CPU port of the reference's path)
+
+A step = the hot path's share of ONE temporal frame for every sequence this GPU owns (B sequences batched
+along the batch axis): 2 normalise pre-passes + tcgen05 correlation build of all 4 levels, forward warp of the
+previous disparity/features + matching cost, backward grid + 3-level hidden-state gather, and 32 pyramid
+lookups.  Inputs (feature maps, per-iteration coordinates, hidden states, poses) are synthetic and already
+resident in HBM for `value`; `e2e` feeds the same step from pinned HOST buffers through the public Python API
+(H2D of the feature maps and D2H of the results inside the timed region).  Sequences are independent, so
+N GPUs run N*B sequences with no data-path collective (weak scaling); NCCL is used for the barrier and the
+max-over-ranks of the timings.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "stereo frames/s at 540x960 (32 iters), cost-volume hot path"
+C = 256
+LEVELS = 4
+RADIUS = 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seqs-per-gpu", type=int, default=8)
+    ap.add_argument("--height", type=int, default=540)
+    ap.add_argument("--width", type=int, default=960)
+    ap.add_argument("--iters", type=int, default=32)
+    ap.add_argument("--precision", default="fp16x3")
+    ap.add_argument("--mode", default="pyramid", choices=["pyramid", "alternate"])
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def feature_hw(h, w):
+    return ((h + 31) // 32 * 32) // 4, ((w + 31) // 32 * 32) // 4
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------------------
+
+def make_slot(B, H, W, iters, seed, device, pin=False):
+    """One frame's inputs for B sequences: what the learned blocks around the hot path would deliver."""
+    g = torch.Generator().manual_seed(seed)
+    f1 = torch.randn(B, C, H, W, generator=g)
+    f2 = torch.roll(f1, -5, dims=3) + 0.3 * torch.randn(B, C, H, W, generator=g)
+    xs = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+    disp = 0.5 + torch.rand(B, 1, H, W, generator=g) * (W / 16.0)
+    walk = torch.cumsum(0.05 * torch.randn(iters, B, 1, H, W, generator=g), 0)
+    coords = xs - (disp[None] + walk)                                   # coords1 = coords0 - disp
+    last_disp = (xs - coords[-1]).clamp_min(0)                          # what the next frame warps
+    nets = [torch.tanh(torch.randn(B, 128, H >> i, W >> i, generator=g)) for i in range(3)]
+    host = {"f1": f1, "f2": f2}
+    if pin:
+        host = {k: v.pin_memory() for k, v in host.items()}
+    dev = {"f1": f1.to(device), "f2": f2.to(device), "coords": coords.to(device), "last_disp": last_disp.to(device),
+           "nets": [n.to(device) for n in nets]}
+    return host, dev
+
+
+def camera(B, H, W, device, frame):
+    from tcs_b200 import sequence
+    K, K_inv = sequence.synthetic_intrinsics(B, 4 * H, 4 * W, device)
+    prev = torch.stack([sequence.synthetic_pose(frame - 1, s) for s in range(B)])
+    cur = torch.stack([sequence.synthetic_pose(frame, s) for s in range(B)])
+    fwd, inv = sequence.relative_pose(prev, cur)
+    return {"K": K, "K_inv": K_inv, "rel_T": fwd.to(device), "rel_T_inv": inv.to(device),
+            "baseline": torch.full((B, 1), 0.25, device=device)}
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arms (the reference's path on the host cores)
+# ------------------------------------------------------------------------------------------------------------
+
+def cpu_frames_per_second(H, W, iters, budget_s, steps=None, warmup=1):
+    """torch-CPU port of the reference's call sequence (oracle/torch_port.py), one sequence per step."""
+    from oracle import torch_port as tp
+    from tcs_b200 import sequence
+    g = torch.Generator().manual_seed(7)
+    f = [torch.randn(1, C, H, W, generator=g) for _ in range(2)]
+    xs = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+    disp = 0.5 + torch.rand(1, 1, H, W, generator=g) * (W / 16.0)
+    coords = xs - (disp[None] + torch.cumsum(0.05 * torch.randn(iters, 1, 1, H, W, generator=g), 0))
+    nets = [torch.tanh(torch.randn(1, 128, H >> i, W >> i, generator=g)) for i in range(3)]
+    K, K_inv = sequence.synthetic_intrinsics(1, 4 * H, 4 * W, "cpu")
+    fwd, inv = sequence.relative_pose(sequence.synthetic_pose(0)[None], sequence.synthetic_pose(1)[None])
+    base = torch.full((1, 1), 0.25)
+
+    def one():
+        with torch.no_grad():
+            tp.frame(f[0], f[1], coords, state=(disp, f[1], nets), rel_T=fwd, rel_T_inv=inv, K=K, K_inv=K_inv, baseline=base)
+
+    for _ in range(warmup):
+        one()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        one()
+        n += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or (steps is None and (el >= budget_s or n >= 50)):
+            break
+    return n / el, n, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    H, W = feature_hw(args.height, args.width)
+    fps, n, el = cpu_frames_per_second(H, W, args.iters, 0, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    cores = torch.get_num_threads()
+    sample = "1 sequence per step (%d temporal frames of %dx%d, %d lookups each) on %d host threads" % (n, args.height, args.width, args.iters, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%dx%d temporal frames, %d lookup iters, 4-level pyramid r=4, C=256" % (args.height, args.width, args.iters),
+                   "feature_hw": [H, W]},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    import tcs_b200
+    from tcs_b200 import sequence
+
+    B, iters = args.seqs_per_gpu, args.iters
+    H, W = feature_hw(args.height, args.width)
+    K_steps, W_steps = args.steps, max(args.warmup, 3)
+    pk = peaks()
+
+    slots_host, slots = [], []
+    for s in range(2):
+        h, d = make_slot(B, H, W, iters, 1234 + 17 * s + 1000 * rank, device, pin=not args.skip_e2e)
+        slots_host.append(h)
+        slots.append(d)
+    cam = camera(B, H, W, device, 1)
+    kw = dict(num_levels=LEVELS, radius=RADIUS, precision=args.precision, mode=args.mode)
+    live = [{}, {}]
+
+    def phase_build(s):
+        live[s]["blk"] = tcs_b200.CorrBlock1D(slots[s]["f1"], slots[s]["f2"], **kw)
+
+    def phase_warp(s):
+        o = slots[1 - s]
+        d, _, m, c = tcs_b200.warp_with_cost(o["last_disp"], o["f1"], cam["rel_T"], cam["K"], cam["K_inv"], cam["baseline"],
+                                             cur_fmap=slots[s]["f1"], per_sample_mean=True)
+        grid = tcs_b200.get_backward_grid(d, cam["rel_T_inv"], cam["K"], cam["K_inv"], cam["baseline"])
+        live[s]["init"] = (d, c, m)
+        live[s]["nets"] = tcs_b200.warp_hidden_states(o["nets"], grid)
+
+    def phase_lookup(s):
+        blk, coords = live[s]["blk"], slots[s]["coords"]
+        out = None
+        for it in range(iters):
+            out = blk(coords[it])
+        live[s]["corr"] = out
+
+    phases = (phase_build, phase_warp, phase_lookup)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: a first frame (argmax initialisation), then temporal frames, eagerly
+    first = tcs_b200.hot_path_frame(slots[0]["f1"], slots[0]["f2"], slots[0]["coords"], state=None, **kw)
+    del first
+    for k in range(W_steps):
+        for ph in phases:
+            ph(k % 2)
+    torch.cuda.synchronize()
+
+    graphs = None
+    if not args.no_graph:
+        pool = torch.cuda.graph_pool_handle()
+        graphs = [[None] * 3 for _ in range(2)]
+        for s in range(2):
+            for i, ph in enumerate(phases):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    ph(s)
+                graphs[s][i] = g
+        for s in range(2):                     # one untimed replay of everything
+            for g in graphs[s]:
+                g.replay()
+        torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, device-timed, phase boundaries marked with events
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K_steps)]
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    barrier()
+    for k in range(K_steps):
+        s = k % 2
+        for i in range(3):
+            ev[k][i].record()
+            if graphs is not None:
+                graphs[s][i].replay()
+            else:
+                phases[i](s)
+        ev[k][3].record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = ev[0][0].elapsed_time(ev[-1][3])
+    phase_ms = [sum(ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(K_steps)) / K_steps for i in range(3)]
+    tmax = torch.tensor([total_ms] + phase_ms, dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms, phase_ms = tmax[0].item(), tmax[1:].tolist()
+    frames = world * B * K_steps
+    value = frames / (total_ms * 1e-3)
+    checksum = float(live[(K_steps - 1) % 2]["corr"].double().sum().item())
+
+    # ---- e2e: same step through the public API, inputs in pinned host memory, results read back
+    e2e = None
+    if not args.skip_e2e:
+        copy_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        # three device staging buffers: previous frame (read by the warp), current frame, next frame (in flight)
+        stage = [{"f1": torch.empty_like(slots[0]["f1"]), "f2": torch.empty_like(slots[0]["f2"])} for _ in range(3)]
+        res_host = [torch.empty((B, LEVELS * (2 * RADIUS + 1) + 3, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+        n_e2e = 2 + K_steps
+        copied = [torch.cuda.Event() for _ in range(n_e2e + 1)]
+        done = [torch.cuda.Event() for _ in range(n_e2e + 1)]
+        h2d = 2 * slots[0]["f1"].numel() * 4
+        d2h = res_host[0].numel() * 4
+
+        def upload(k):
+            with torch.cuda.stream(copy_stream):
+                if k >= 2:
+                    copy_stream.wait_event(done[k - 2])         # step k-2 was the last reader of stage[k % 3]
+                stage[k % 3]["f1"].copy_(slots_host[k % 2]["f1"], non_blocking=True)
+                stage[k % 3]["f2"].copy_(slots_host[k % 2]["f2"], non_blocking=True)
+                copied[k].record(copy_stream)
+
+        def e2e_step(k):
+            s = k % 2
+            if k + 1 < n_e2e:
+                upload(k + 1)                                   # next frame's H2D overlaps this frame's kernels
+            main.wait_event(copied[k])
+            o = slots[1 - s]
+            cur, prev = stage[k % 3], stage[(k - 1) % 3]
+            out = tcs_b200.hot_path_frame(cur["f1"], cur["f2"], slots[s]["coords"],
+                                          state=(o["last_disp"], prev["f1"], o["nets"]), rel_T=cam["rel_T"],
+                                          rel_T_inv=cam["rel_T_inv"], K=cam["K"], K_inv=cam["K_inv"], baseline=cam["baseline"], **kw)
+            r = res_host[s]
+            r[:, :36].copy_(out["corr"], non_blocking=True)
+            r[:, 36:37].copy_(out["sparse_disp"], non_blocking=True)
+            r[:, 37:38].copy_(out["cost"], non_blocking=True)
+            r[:, 38:39].copy_(out["mask"], non_blocking=True)
+            done[k].record(main)
+
+        stage[2]["f1"].copy_(slots[1]["f1"])                    # "frame -1" features for the first warp
+        upload(0)
+        for k in range(2):                                       # warm-up of the e2e loop itself
+            e2e_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(2, n_e2e):
+            e2e_step(k)
+        barrier()
+        el = time.perf_counter() - t0
+        tt = torch.tensor([el], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": frames / tt.item(), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "note": "pinned host fmaps -> H2D (copy stream, double-buffered) -> hot_path_frame (eager public API) -> D2H of lookup+init"}
+
+    # ---- rooflines
+    npix = B * H * W
+    lookup_bytes = 308 * npix                                   # 4 coord + 4*10*4 taps + 4*9*4 out per pixel
+    lookup_ms = phase_ms[2] / iters
+    traffic = None
+    tp_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp_path):
+        traffic = json.load(open(tp_path)).get("corr_lookup_bytes_per_launch_B%d" % B)
+    roofline = {"kernel": "corr_lookup_r4_kernel", "bound": "hbm", "achieved": lookup_bytes / (lookup_ms * 1e-3) / 1e9,
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": lookup_bytes / (lookup_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                "traffic": traffic, "peak_source": pk["source"], "launches_per_step": iters,
+                "algorithmic_bytes_per_launch": lookup_bytes}
+    build_flops = 2.0 * npix * W * C
+    build_bytes = 2 * npix * C * 4 + npix * W * 4 * (1 + 0.5 + 0.25 + 0.125)
+    warp_bytes = npix * (4 + 1024 + 1024 + 4 + 1024 + 4 + 4 + 1344)
+    phases_out = {
+        "build_ms": phase_ms[0], "warp_ms": phase_ms[1], "lookups_ms": phase_ms[2],
+        "build": {"note": "2 pre-passes + tcgen05 build, fp32 fmaps in, fp32 levels out", "algorithmic_bytes": build_bytes,
+                  "hbm_gbs": build_bytes / (phase_ms[0] * 1e-3) / 1e9, "hbm_frac": build_bytes / (phase_ms[0] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                  "tflops": build_flops / (phase_ms[0] * 1e-3) / 1e12, "tensor_frac": build_flops / (phase_ms[0] * 1e-3) / 1e12 / pk["bf16_tflops"]},
+        "warp": {"algorithmic_bytes": warp_bytes, "hbm_gbs": warp_bytes / (phase_ms[1] * 1e-3) / 1e9,
+                 "hbm_frac": warp_bytes / (phase_ms[1] * 1e-3) / 1e9 / pk["hbm_gbs"]},
+    }
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        fps, n, el = cpu_frames_per_second(H, W, iters, args.cpu_seconds)
+        cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "%d temporal frames of 1 sequence (%dx%d, %d lookups) in %.1f s, oracle/torch_port.py" % (n, args.height, args.width, iters, el)}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K_steps, "warmup": W_steps,
+            "ms_per_step": total_ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp16x3": "f16x3->f32", "bf16x3": "bf16x3->f32", "bf16": "bf16->f32", "fp16": "f16->f32", "fp32": "f32"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "%dx%d temporal frames, %d lookup iters, 4-level pyramid r=4, C=256, %d sequences per GPU batched"
+                                   % (args.height, args.width, iters, B),
+                       "feature_hw": [H, W], "seqs_per_gpu": B, "precision": args.precision, "mode": args.mode,
+                       "cuda_graphs": graphs is not None, "l2": "inputs larger than L2 (%.0f MB of feature maps per step, 2 alternating slots)" % (2 * npix * C * 4 / 1e6),
+                       "parallelism": "sequences sharded per GPU, no data-path collective"},
+            "e2e": e2e, "gpu_launches": K_steps * sequence.launches_per_frame(iters, False, mode=args.mode),
+            "clocks": clocks, "roofline": roofline, "phases": phases_out, "cpu_baseline": cpu, "checksum": checksum,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-_DEFAULT_PRECISION = os.environ.get("TCS_B200_PRECISION", "bf16x3")
+_DEFAULT_PRECISION = os.environ.get("TCS_B200_PRECISION", "fp16x3")
 _DEFAULT_MODE = os.environ.get("TCS_B200_CORR_MODE", "pyramid")
 
 

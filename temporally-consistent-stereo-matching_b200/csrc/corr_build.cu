@@ -328,7 +328,9 @@ extern "C" int tcs_corr_build(const void* a_hi, const void* a_lo, const void* b_
     p.W1 = W1; p.W2 = W2; p.num_levels = num_levels;
     p.num_m = ceil_div(W1, kBlockM);
     p.n_tiles = ceil_div(W2, kMaxBlockN);
-    p.block_n = ceil_div(ceil_div(W2, p.n_tiles), 16) * 16;
+    // UMMA N must be a multiple of 16; with several N tiles every tile must also start on a 32-column
+    // boundary so that the level-3 float4 stores (one per 32 level-0 columns) stay 16-byte aligned.
+    p.block_n = ceil_div(ceil_div(W2, p.n_tiles), p.n_tiles > 1 ? 32 : 16) * (p.n_tiles > 1 ? 32 : 16);
     const long long total = (long long)B * H * p.num_m * p.n_tiles;
     TCS_REQUIRE(total < 0x7fffffffLL, TCS_E_SHAPE, "tcs_corr_build: too many tiles");
     p.total_tiles = (int)total;

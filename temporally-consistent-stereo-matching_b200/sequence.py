@@ -75,15 +75,55 @@ def relative_pose(prev_T, cur_T):
     return fwd.float(), torch.linalg.inv(fwd).float()
 
 
-class HotPathRunner:
-    """Runs the hot path of one frame for B batched sequences and carries the temporal state."""
+def hot_path_frame(fmap1, fmap2, coords_seq, state=None, disp_init=None, rel_T=None, rel_T_inv=None, K=None,
+                   K_inv=None, baseline=None, num_levels=4, radius=4, precision=None, mode=None, per_sample_mean=True):
+    """The hot path's share of one frame for B batched sequences (order of core/tc_stereo.py:114-177).
 
-    def __init__(self, num_levels=4, radius=4, precision="bf16x3", mode="pyramid", per_sample_mean=True):
-        self.num_levels = num_levels
-        self.radius = radius
-        self.precision = precision
-        self.mode = mode
-        self.per_sample_mean = per_sample_mean   # independent sequences must not share the splat metric mean
+      fmap1, fmap2  [B,C,H,W] features of the current stereo pair
+      coords_seq    [iters,B,1,H,W] x-coordinate queried by each GRU iteration (tc_stereo.py:176-177)
+      state         None on a first frame, else (last_disp [B,1,H,W], last_fmap1 [B,C,H,W], last_net_list or None)
+      disp_init     [B,1,H,W] completed disparity the backward grid is built from (tc_stereo.py:159);
+                    defaults to the warped disparity (get_backward_grid clips it at 0.01 itself)
+      rel_T, rel_T_inv  previous->current and current->previous camera transforms [B,4,4]
+    Returns a dict: the last lookup, the sparse initialisation (disp, cost, mask), the warped hidden states.
+    Every device operation inside is a libtcs_b200 kernel (plus one memset)."""
+    corr_fn = CorrBlock1D(fmap1, fmap2, num_levels=num_levels, radius=radius, precision=precision, mode=mode)
+    warped_net = None
+    if state is None:
+        sparse_disp, cost, mask = corr_fn.argmax_disp()
+    else:
+        last_disp, last_fmap1, last_net_list = state
+        sparse_disp, _, mask, cost = geo.warp_with_cost(last_disp, last_fmap1, rel_T, K, K_inv, baseline,
+                                                        cur_fmap=fmap1, per_sample_mean=per_sample_mean)
+        if last_net_list is not None:
+            grid = geo.get_backward_grid(disp_init if disp_init is not None else sparse_disp,   # the kernel clips at 0.01
+                                         rel_T_inv, K, K_inv, baseline)
+            warped_net = geo.warp_hidden_states(last_net_list, grid)
+    out = None
+    for it in range(coords_seq.shape[0]):
+        out = corr_fn(coords_seq[it])
+    return {"corr": out, "sparse_disp": sparse_disp, "cost": cost, "mask": mask, "warped_net": warped_net,
+            "corr_fn": corr_fn}
+
+
+def launches_per_frame(iters, first_frame, hidden_levels=3, mode="pyramid", num_levels=4):
+    """Number of libtcs_b200 kernel launches hot_path_frame issues (memset nodes not counted)."""
+    n = 2 + 1 if mode == "pyramid" else 2 + (num_levels - 1)      # prepass x2 + build | prepass x2 + pools
+    if first_frame:
+        n += 1 if mode == "pyramid" else 2                         # argmax (+ an on-demand level-0 build)
+        if mode != "pyramid":
+            n += 2                                                 # its prepasses
+    else:
+        n += 3 + 1 + hidden_levels + (hidden_levels - 1)           # geometry, splat, finalize; grid; gathers; halves
+    return n + iters
+
+
+class HotPathRunner:
+    """Carries the temporal state of B batched sequences from frame to frame (evaluate_stereo.py:192-197)."""
+
+    def __init__(self, num_levels=4, radius=4, precision=None, mode=None, per_sample_mean=True):
+        self.kw = dict(num_levels=num_levels, radius=radius, precision=precision, mode=mode,
+                       per_sample_mean=per_sample_mean)   # independent sequences must not share the splat mean
         self.reset()
 
     def reset(self):
@@ -91,36 +131,12 @@ class HotPathRunner:
         self.last_fmap1 = None
         self.last_net_list = None
 
-    def frame(self, fmap1, fmap2, coords_seq, disp_init=None, rel_T=None, rel_T_inv=None, K=None, K_inv=None,
-              baseline=None, net_list=None):
-        """One frame.
-          fmap1, fmap2  [B,C,H,W] features of the current stereo pair
-          coords_seq    [iters,B,1,H,W] x-coordinate queried by each GRU iteration (tc_stereo.py:176-177)
-          disp_init     [B,1,H,W] completed disparity the backward grid is built from (tc_stereo.py:159);
-                        defaults to the warped disparity
-          rel_T, rel_T_inv  previous->current and current->previous transforms, frames t >= 1
-          net_list      this frame's hidden states, carried to the next frame
-        Returns a dict with the last lookup, the sparse initialisation and the warped hidden states."""
-        corr_fn = CorrBlock1D(fmap1, fmap2, num_levels=self.num_levels, radius=self.radius,
-                              precision=self.precision, mode=self.mode)
-        warped_net = None
-        if self.last_disp is None:
-            sparse_disp, cost, mask = corr_fn.argmax_disp()
-        else:
-            sparse_disp, _, mask, cost = geo.warp_with_cost(self.last_disp, self.last_fmap1, rel_T, K, K_inv, baseline,
-                                                            cur_fmap=fmap1, per_sample_mean=self.per_sample_mean)
-            if self.last_net_list is not None:
-                grid = geo.get_backward_grid(disp_init if disp_init is not None else sparse_disp.clamp_min(0),
-                                             rel_T_inv, K, K_inv, baseline)
-                warped_net = geo.warp_hidden_states(self.last_net_list, grid)
-        out = None
-        for it in range(coords_seq.shape[0]):
-            out = corr_fn(coords_seq[it])
-        # temporal state for the next frame (evaluate_stereo.py:192-197)
-        H, W = fmap1.shape[2:]
+    def frame(self, fmap1, fmap2, coords_seq, net_list=None, **camera):
+        state = None if self.last_disp is None else (self.last_disp, self.last_fmap1, self.last_net_list)
+        out = hot_path_frame(fmap1, fmap2, coords_seq, state=state, **camera, **self.kw)
+        W = fmap1.shape[3]
         xs = torch.arange(W, device=fmap1.device, dtype=torch.float32).view(1, 1, 1, W)
-        self.last_disp = (xs - coords_seq[-1]).clamp_min(0)      # disp = coords0 - coords1, flow_q clipped at 0
+        self.last_disp = (xs - coords_seq[-1]).clamp_min(0)      # disp = coords0 - coords1; flow_q is clipped at 0
         self.last_fmap1 = fmap1
         self.last_net_list = net_list
-        return {"corr": out, "sparse_disp": sparse_disp, "cost": cost, "mask": mask, "warped_net": warped_net,
-                "corr_fn": corr_fn}
+        return out

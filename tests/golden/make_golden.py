@@ -135,8 +135,8 @@ def main():
     torch.manual_seed(1234)
     rcorr, rutils, rgeo = import_reference()
     with torch.no_grad():
-        corr_case(rcorr, "corr_small", B=2, C=64, H=3, W=40, seed=1234, correlated_shift=5)
-        corr_case(rcorr, "corr_oddwidth", B=1, C=64, H=2, W=78, seed=4321, correlated_shift=0)
+        corr_case(rcorr, "corr_small", B=2, C=128, H=3, W=40, seed=1234, correlated_shift=5)
+        corr_case(rcorr, "corr_oddwidth", B=1, C=128, H=2, W=78, seed=4321, correlated_shift=0)
         warp_case(rutils, rgeo, "warp_small", B=2, C=128, H=12, W=16, seed=1234)
 
 

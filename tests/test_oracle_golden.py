@@ -84,3 +84,30 @@ def test_lookup_far_out_of_range_is_zero():
     assert not orc.corr_lookup(lv, coords, 4).any()
     coords[:] = np.nan
     assert not np.isnan(orc.corr_lookup(lv, coords, 4)).all() or True  # NaN coords must not crash
+
+
+def test_torch_port_matches_golden():
+    """The multi-threaded torch CPU port used as bench.py's CPU baseline computes the same things."""
+    import torch
+    from oracle import torch_port as tp
+    t = torch.from_numpy
+    for case in CORR_CASES:
+        g = load_golden(case)
+        pyr, cv = tp.build_block(t(g["fmap1"]), t(g["fmap2"]))
+        B, H, W = g["level0"].shape[:3]
+        for l in range(4):
+            assert_close(pyr[l].view(B, H, W, -1).numpy(), g["level%d" % l], what="port level %d" % l)
+        assert_close(tp.lookup(pyr, t(g["coords"])).numpy(), g["lookup"], what="port lookup")
+        d, c, m = tp.argmax_disp(cv)
+        assert_exact(m.numpy(), g["mask"], what="port argmax mask")
+        assert_exact(d.numpy(), g["sparse_disp"], what="port sparse_disp")
+    g = load_golden("warp_small")
+    d, f, m = tp.warp(t(g["disp"]), t(g["fmap"]), t(g["rel_T"]), t(g["K"]), t(g["K_inv"]), t(g["baseline"]))
+    assert_exact(m.numpy(), g["warped_mask"], what="port splat mask")
+    assert_close(f.numpy(), g["warped_fmap"], rtol=1e-5, atol=1e-5, what="port warped features")
+    assert_close(tp.matching_cost(t(g["cur_fmap"]), f, m).numpy(), g["cost"], rtol=1e-5, atol=2e-6, what="port cost")
+    grid = tp.backward_grid(t(g["disp_init"]), t(g["rel_T_inv"]), t(g["K"]), t(g["K_inv"]), t(g["baseline"]))
+    assert_close(grid.numpy(), g["backward_grid"], rtol=1e-5, atol=1e-4, what="port backward grid")
+    outs = tp.warp_hidden([t(g["net%d" % i]) for i in range(3)], t(g["backward_grid"]))
+    for i in range(3):
+        assert_close(outs[i].numpy(), g["warped_net%d" % i], rtol=1e-5, atol=2e-6, what="port hidden %d" % i)
