@@ -4,11 +4,12 @@
 //
 // Structure (one persistent CTA per SM, 192 threads, warp-specialised):
 //   warp 0      TMA producer: cp.async.bulk.tensor.3d of [128 x 64] (A) and [block_n x 64] (B) 16-bit
-//               K-major tiles, SWIZZLE_128B, into a 4-stage shared-memory ring (mbarrier complete_tx).
+//               K-major tiles, SWIZZLE_128B, into a 3-stage shared-memory ring (mbarrier complete_tx).
 //   warp 1      tcgen05.mma issuer (one thread): UMMA 128 x block_n x 16, fp32 accumulators in TMEM,
 //               two accumulator stages (2 x 256 columns) so the MMAs of tile i+1 overlap the epilogue of
 //               tile i; tcgen05.commit releases smem stages and publishes finished accumulators.
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers (thread = one w1 row, so the
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, taking even / odd column chunks):
+//               tcgen05.ld 32 lanes x 32 columns -> registers (thread = one w1 row, so the
 //               avg-pool cascade along w2 is purely intra-thread), swizzled smem transpose for L0/L1,
 //               coalesced 16-byte global stores of levels 0..3.
 // The *X3 precisions run three MMA passes per K block (hi*hi, hi*lo, lo*hi) into the same accumulator.
@@ -23,15 +24,15 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 x 16 bit = 128 B: one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
 constexpr int kMaxBlockN = 256;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kABytes = kBlockM * kBlockK * 2;     // 16 KB
 constexpr int kBBytes = kMaxBlockN * kBlockK * 2;  // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;     // 48 KB
 constexpr int kAccStages = 2;
 constexpr int kAccCols = 256;
 constexpr int kTmemCols = kAccStages * kAccCols;   // 512: the whole TMEM of the SM (1 CTA / SM)
-constexpr int kEpiWarps = 4;
-constexpr int kBuildThreads = 64 + 32 * kEpiWarps; // 192
+constexpr int kEpiWarps = 8;                      // two per TMEM lane quarter: even / odd 32-column chunks
+constexpr int kBuildThreads = 64 + 32 * kEpiWarps; // 320
 constexpr int kEpiStageBytes = 4096 + 2048;        // per epilogue warp: L0 [32][32] + L1 [32][16] fp32
 constexpr int kBarrierBytes = 256;
 constexpr int kBuildSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kBarrierBytes;
@@ -181,10 +182,16 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             ptx::tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols;
             const int n_chunks = (n_end - n0 + 31) >> 5;
-            for (int ch = 0; ch < n_chunks; ++ch) {
+            const int ch_first = ew >> 2;                       // this warp's parity among the chunks
+            const int ch_last = ch_first + ((n_chunks - 1 - ch_first) & ~1);   // its last chunk (or < ch_first: none)
+            if (ch_first >= n_chunks) {                         // nothing to read: release the accumulator at once
+                ptx::tc_fence_before_sync();
+                ptx::mbar_arrive(bar_tempty + 8 * acc);
+            }
+            for (int ch = ch_first; ch < n_chunks; ch += 2) {
                 float v[32];
                 ptx::tmem_ld_32x32(taddr + ch * 32, v);
-                if (ch == n_chunks - 1) {
+                if (ch == ch_last) {
                     // all TMEM reads of this accumulator are done: hand it back to the MMA warp
                     ptx::tc_fence_before_sync();
                     ptx::mbar_arrive(bar_tempty + 8 * acc);

@@ -21,66 +21,77 @@ __device__ __forceinline__ float sample_pos(float xk, float wm1) {
     return __fmul_rn(__fmul_rn(__fadd_rn(xg, 1.0f), 0.5f), wm1);                 // ATen unnormalize, align_corners
 }
 
-// ---- fused lookup, radius 4: 4 lanes per (pixel, level) -------------------------------------------
-// Each quad fetches the 64-byte, 16-byte-aligned superset of its pixel's 12-float window with one
-// ld.global.v4 per lane, parks it in shared memory and interpolates 9 taps from there.
+// grid_sample position of tap xk on a level of width wm1 + 1: same roundings as sample_pos();
+// 2*x and *0.5 are exact, so they are folded into their neighbours (hwm1 = 0.5 * wm1).
+__device__ __forceinline__ float sample_pos_fast(float xk, float wm1, float rc, float hwm1) {
+    const float xg = __fmaf_rn(2.0f, div_by_const(xk, wm1, rc), -1.0f);
+    return __fmul_rn(__fadd_rn(xg, 1.0f), hwm1);
+}
+
+// ---- fused lookup, radius 4: one thread per (pixel, level) ---------------------------------------------
+// The 9 taps of a pixel read in-row indices [fc-5, fc+6] of the pixel's own row (fc = floor(coords/2^l);
+// a tap can land one off the centre estimate after grid_sample's round trip).  The thread fetches the
+// 16-byte-aligned quads covering that window (3 or 4 LDG.128, none for quads outside the row), parks them
+// in its own column of a transposed shared-memory tile (conflict-free both ways, and private to the
+// thread, so no barrier) and interpolates the taps from there.  Lanes are consecutive pixels, so every
+// output store is a full 128-byte line of one tap plane.
 constexpr int kLookThreads = 256;
 
 __global__ void __launch_bounds__(kLookThreads)
 corr_lookup_r4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
-                      float* __restrict__ out, int HW, int W2, int num_levels, long long npix) {
-    __shared__ float4 win[kLookThreads];  // [64 quads][4]
+                      float* __restrict__ out, int HW, int W2, int num_levels, long long total_floats_l0) {
+    __shared__ float win[16][kLookThreads];
     const int tid = threadIdx.x;
-    const int quad = tid >> 2, j = tid & 3;
     const int l = blockIdx.y;
-    const long long p = (long long)blockIdx.x * (kLookThreads / 4) + quad;
-    const bool active = p < npix;
+    const int b = blockIdx.z;
+    const int hw = blockIdx.x * kLookThreads + tid;
+    if (hw >= HW) return;
     const int Wl = W2 >> l;
     const float wm1 = (float)(Wl - 1);
+    const float rc = __frcp_rn(wm1);
+    const float hwm1 = __fmul_rn(0.5f, wm1);
     const float* __restrict__ base = lv.p[l];
-    const long long total4 = ((npix * Wl + 3) >> 2) << 2;  // readable length (caller pads to 16 B)
+    const long long p = (long long)b * HW + hw;
+    const long long row_start = p * Wl;
+    const long long readable = (((long long)gridDim.z * HW * Wl + 3) >> 2) << 2;   // caller pads each level to 16 B
 
-    float cl = 0.0f;
-    long long b = 0, hw = 0;
-    if (active) {
-        b = p / HW;
-        hw = p - b * HW;
-        cl = __ldg(coords + b * coords_bstride + hw) * (1.0f / (float)(1 << l));   // coords / 2**l (exact)
-    }
-    // window = in-row indices [fc-5, fc+6] (taps can land one off the centre estimate after rounding)
+    const float cl = __ldg(coords + b * coords_bstride + hw) * (1.0f / (float)(1 << l));   // coords / 2**l (exact)
     const float fcf = fminf(fmaxf(floorf(cl), -16.0f), (float)(Wl + 16));
     const int wfirst = (int)fcf - 5;
-    const long long row_start = p * Wl;
     const long long a_abs = ((row_start + wfirst) >> 2) << 2;   // floor to a multiple of 4 floats (16 B)
     const int win_first = (int)(a_abs - row_start);             // in-row index of win[0]
-    {
-        const long long idx = a_abs + 4 * j;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active && idx >= 0 && idx + 3 < total4) v = __ldg(reinterpret_cast<const float4*>(base + idx));
-        win[tid] = v;
-    }
-    __syncwarp();
-    if (active) {
-        const float* w = reinterpret_cast<const float*>(win) + quad * 16;
-        float* o = out + ((b * num_levels + l) * 9) * (long long)HW + hw;
+    const int need_lo = max(wfirst, 0), need_hi = min(wfirst + 11, Wl - 1);
 #pragma unroll
-        for (int t = j; t < 9; t += 4) {
-            const float xk = __fadd_rn((float)(t - 4), cl);     // corr.py:43  dx + coords/2^i
-            const float ix = sample_pos(xk, wm1);
-            float r = 0.0f;
-            if (ix > -1.0f && ix < (float)Wl) {                 // otherwise both taps are out of range
-                const float x0f = floorf(ix);
-                const int x0 = (int)x0f;
-                const float w_hi = __fsub_rn(ix, x0f);
-                const float w_lo = __fsub_rn(__fadd_rn(x0f, 1.0f), ix);
-                const int i0 = x0 - win_first;
-                float v0 = 0.0f, v1 = 0.0f;
-                if (x0 >= 0 && (unsigned)i0 < 16u) v0 = w[i0];
-                if (x0 + 1 < Wl && (unsigned)(i0 + 1) < 16u) v1 = w[i0 + 1];
-                r = fmaf(v1, w_hi, __fmul_rn(v0, w_lo));
-            }
-            o[(long long)t * HW] = r;
+    for (int k = 0; k < 4; ++k) {
+        const int q_lo = win_first + 4 * k;                     // in-row index of this quad's first float
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const long long idx = a_abs + 4 * k;
+        if (q_lo + 3 >= need_lo && q_lo <= need_hi && idx >= 0 && idx + 3 < readable)
+            v = ldg_stream_f4(reinterpret_cast<const float4*>(base + idx));
+        win[4 * k + 0][tid] = v.x;
+        win[4 * k + 1][tid] = v.y;
+        win[4 * k + 2][tid] = v.z;
+        win[4 * k + 3][tid] = v.w;
+    }
+    float* o = out + (((long long)b * num_levels + l) * 9) * HW + hw;
+    const float Wlf = (float)Wl;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const float xk = __fadd_rn((float)(t - 4), cl);         // corr.py:43  dx + coords/2^i
+        const float ix = sample_pos_fast(xk, wm1, rc, hwm1);
+        float r = 0.0f;
+        if (ix > -1.0f && ix < Wlf) {                           // otherwise both taps are out of range
+            const float x0f = floorf(ix);
+            const int x0 = (int)x0f;
+            const float w_hi = __fsub_rn(ix, x0f);
+            const float w_lo = __fsub_rn(__fadd_rn(x0f, 1.0f), ix);
+            const int i0 = x0 - win_first;
+            float v0 = 0.0f, v1 = 0.0f;
+            if (x0 >= 0 && (unsigned)i0 < 16u) v0 = win[i0][tid];
+            if (x0 + 1 < Wl && (unsigned)(i0 + 1) < 16u) v1 = win[i0 + 1][tid];
+            r = fmaf(v1, w_hi, __fmul_rn(v0, w_lo));
         }
+        stg_stream_f1(o + (long long)t * HW, r);
     }
 }
 
@@ -343,8 +354,9 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
     const long long npix = (long long)B * H * W1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (radius == 4) {
-        dim3 grid((unsigned)ceil_div_ll(npix, kLookThreads / 4), num_levels);
-        corr_lookup_r4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels, npix);
+        TCS_REQUIRE(B <= 65535, TCS_E_SHAPE, "tcs_corr_lookup: B must be <= 65535");
+        dim3 grid((unsigned)ceil_div(H * W1, kLookThreads), num_levels, B);
+        corr_lookup_r4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels, 0);
     } else {
         dim3 grid((unsigned)ceil_div_ll(npix, 256), num_levels);
         corr_lookup_generic_kernel<<<grid, 256, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels, radius, npix);

@@ -68,26 +68,39 @@ corr_prepass_kernel(const float* __restrict__ fmap, uint32_t* __restrict__ hi, u
     }
     __syncthreads();
 
-    // ---- per pixel: norm over channels, normalise, emit
+    // ---- per pixel: norm over channels, normalise, emit.  Each warp owns 4 pixels; their reductions are
+    // interleaved (independent shuffle chains) and x / denom uses the exact 3-instruction division by a
+    // loop-invariant denominator.
+    constexpr int kPix = kPreTileW / (kPreThreads / 32);   // 4
     const int pairs = C >> 6;  // channel pairs per lane: channels 2*lane + 64*k, +1
-#pragma unroll 1
-    for (int i = 0; i < kPreTileW / (kPreThreads / 32); ++i) {
-        const int wl = warp * (kPreTileW / (kPreThreads / 32)) + i;
+    float ss[kPix];
+#pragma unroll
+    for (int i = 0; i < kPix; ++i) {
+        const float* row = tile + (warp * kPix + i) * pitch;
+        float acc = 0.0f;
+        for (int c = lane; c < C; c += 32) {
+            const float v = row[c];
+            acc = fmaf(v, v, acc);
+        }
+        ss[i] = acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < kPix; ++i) ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], o);
+#pragma unroll
+    for (int i = 0; i < kPix; ++i) {
+        const int wl = warp * kPix + i;
         const int w = w0 + wl;
         if (w >= W) break;  // warp-uniform
         const float* row = tile + wl * pitch;
-        float ss = 0.0f;
-        for (int c = lane; c < C; c += 32) {
-            float v = row[c];
-            ss = fmaf(v, v, ss);
-        }
-        ss = warp_sum(ss);
-        const float denom = fmaxf(sqrtf(ss), 1e-12f);
+        const float denom = fmaxf(sqrtf(ss[i]), 1e-12f);
+        const float rden = __frcp_rn(denom);
         const size_t pix = ((size_t)b * H + h) * W + w;
         for (int k = 0; k < pairs; ++k) {
             const int c = 2 * lane + 64 * k;
-            const float a = row[c] / denom;
-            const float d = row[c + 1] / denom;
+            const float a = div_by_const(row[c], denom, rden);
+            const float d = div_by_const(row[c + 1], denom, rden);
             if (n32 != nullptr) *reinterpret_cast<float2*>(n32 + pix * C + c) = make_float2(a, d);
             if (hi != nullptr) {
                 uint32_t lo_pack;

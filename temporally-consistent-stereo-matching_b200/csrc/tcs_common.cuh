@@ -60,11 +60,32 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// x / c for a loop-invariant c, correctly rounded (bit-identical to IEEE division) in three FP
+// instructions: with rc = RN(1/c), q0 = RN(x*rc), r = x - q0*c (exact in an FMA), q = RN(q0 + r*rc)
+// (Markstein).  Checked against x / c for every c = 1..4096 and 8e7 numerators on the host.
+__device__ __forceinline__ float div_by_const(float x, float c, float rc) {
+    const float q0 = __fmul_rn(x, rc);
+    const float r = __fmaf_rn(-q0, c, x);
+    return __fmaf_rn(r, rc, q0);
+}
+
 // Streaming (read-once / write-once) global accesses: keep them out of L1.
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+// Read-only load that keeps its place in program order (volatile asm): used to issue a batch of independent
+// loads back to back where the compiler would otherwise sink them next to their uses.
+__device__ __forceinline__ float ldg_ordered_f1(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void stg_stream_f4(float4* p, const float4& v) {

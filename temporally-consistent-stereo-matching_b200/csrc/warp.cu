@@ -224,57 +224,69 @@ warp_finalize_kernel(const float* __restrict__ accum, const float* __restrict__ 
     float* maskv = red + 8 * 32 * 3;
     const int w0 = blockIdx.x * kTileW, h = blockIdx.y, b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kPerWarp = C / 8;            // channels warp + 8k of phase 2
 
-#pragma unroll 1
-    for (int i = 0; i < kTileW / 8; ++i) {
-        const int wl = warp * (kTileW / 8) + i;
-        const int w = w0 + wl;
-        if (w >= W) {
-#pragma unroll
-            for (int k = 0; k < kGroups * 4; ++k) tile[(lane + 32 * k) * 33 + wl] = 0.0f;
-            if (lane == 0) maskv[wl] = 0.0f;
-            continue;
-        }
-        const size_t idx = ((size_t)b * H + h) * W + w;
-        const float* src = accum + idx * CP;
-        const float2 tail = *reinterpret_cast<const float2*>(src + C);
-        const float nrm = fmaxf(tail.y, 1e-7f);                 // clip(1e-7, None)   softsplat.py:268
-        const float m = (tail.y != 0.0f) ? 1.0f : 0.0f;         // softsplat.py:258
-#pragma unroll
-        for (int j = 0; j < kGroups; ++j) {
-            const float4 a = *reinterpret_cast<const float4*>(src + j * 128 + 4 * lane);
-            tile[(lane + 32 * (4 * j + 0)) * 33 + wl] = __fdiv_rn(a.x, nrm);
-            tile[(lane + 32 * (4 * j + 1)) * 33 + wl] = __fdiv_rn(a.y, nrm);
-            tile[(lane + 32 * (4 * j + 2)) * 33 + wl] = __fdiv_rn(a.z, nrm);
-            tile[(lane + 32 * (4 * j + 3)) * 33 + wl] = __fdiv_rn(a.w, nrm);
-        }
-        if (lane == 0) {
-            out_disp[idx] = __fdiv_rn(tail.x, nrm);
-            out_mask[idx] = m;
-            maskv[wl] = m;
-        }
-    }
-    __syncthreads();
-
+    // phase 0: the current frame's features for the cost are independent of everything else: fetch them first
     const int w = w0 + lane;
     const bool in_w = w < W;
     const size_t plane = (size_t)H * W;
     const size_t base = ((size_t)b * C * H + h) * W + w;
-    float dot = 0.0f, s1 = 0.0f, sw = 0.0f;
-#pragma unroll 4
-    for (int c = warp; c < C; c += 8) {
-        const float v = tile[c * 33 + lane];
-        if (in_w) {
-            stg_stream_f1(out_fmap + base + (size_t)c * plane, v);
-            if (cur_fmap != nullptr) {
-                const float f = __ldg(cur_fmap + base + (size_t)c * plane);
-                dot = fmaf(f, v, dot);
-                s1 = fmaf(f, f, s1);
-                sw = fmaf(v, v, sw);
+    const bool want_cost = (out_cost != nullptr) && (cur_fmap != nullptr);
+    float f[kPerWarp];
+#pragma unroll
+    for (int k = 0; k < kPerWarp; ++k)
+        f[k] = (want_cost && in_w) ? ldg_stream_f1(cur_fmap + base + (size_t)(warp + 8 * k) * plane) : 0.0f;
+
+    // phase 1: accumulator (channels-last, permuted) -> normalised values in tile[c][w]
+    float2 tail[kTileW / 8];
+    float4 a[kTileW / 8][kGroups];
+#pragma unroll
+    for (int i = 0; i < kTileW / 8; ++i) {
+        const int wl = warp * (kTileW / 8) + i;
+        const bool live = w0 + wl < W;
+        const size_t idx = ((size_t)b * H + h) * W + (live ? w0 + wl : 0);
+        const float* src = accum + idx * CP;
+        tail[i] = live ? *reinterpret_cast<const float2*>(src + C) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j)
+            a[i][j] = live ? *reinterpret_cast<const float4*>(src + j * 128 + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < kTileW / 8; ++i) {
+        const int wl = warp * (kTileW / 8) + i;
+        const bool live = w0 + wl < W;
+        const float nrm = fmaxf(tail[i].y, 1e-7f);              // clip(1e-7, None)   softsplat.py:268
+        const float m = (tail[i].y != 0.0f) ? 1.0f : 0.0f;      // softsplat.py:258
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j) {
+            tile[(lane + 32 * (4 * j + 0)) * 33 + wl] = __fdiv_rn(a[i][j].x, nrm);
+            tile[(lane + 32 * (4 * j + 1)) * 33 + wl] = __fdiv_rn(a[i][j].y, nrm);
+            tile[(lane + 32 * (4 * j + 2)) * 33 + wl] = __fdiv_rn(a[i][j].z, nrm);
+            tile[(lane + 32 * (4 * j + 3)) * 33 + wl] = __fdiv_rn(a[i][j].w, nrm);
+        }
+        if (lane == 0) {
+            maskv[wl] = live ? m : 0.0f;
+            if (live) {
+                const size_t idx = ((size_t)b * H + h) * W + w0 + wl;
+                out_disp[idx] = __fdiv_rn(tail[i].x, nrm);
+                out_mask[idx] = m;
             }
         }
     }
-    if (out_cost == nullptr || cur_fmap == nullptr) return;
+    __syncthreads();
+
+    // phase 2: NCHW stores (one 128-byte line per channel and warp) + the per-pixel dot products of the cost
+    float dot = 0.0f, s1 = 0.0f, sw = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kPerWarp; ++k) {
+        const int c = warp + 8 * k;
+        const float v = tile[c * 33 + lane];
+        if (in_w) stg_stream_f1(out_fmap + base + (size_t)c * plane, v);
+        dot = fmaf(f[k], v, dot);
+        s1 = fmaf(f[k], f[k], s1);
+        sw = fmaf(v, v, sw);
+    }
+    if (!want_cost) return;
     red[(warp * 32 + lane) * 3 + 0] = dot;
     red[(warp * 32 + lane) * 3 + 1] = s1;
     red[(warp * 32 + lane) * 3 + 2] = sw;
@@ -317,10 +329,15 @@ backward_grid_kernel(const float* __restrict__ disp, const float* __restrict__ r
 
 // ---- bilinear_sampler --------------------------------------------------------------------------------------------------
 // grid_sample(bilinear, zeros, align_corners=True) on pixel coordinates, including the wrapper's normalise and
-// ATen's un-normalise round trip.  One thread per (output pixel, channel slice); weights computed once.
+// ATen's un-normalise round trip.  One thread per (output pixel, group of 8 channels): the four weights are
+// computed once, then the 32 corner loads of the group are issued back to back (memory-level parallelism),
+// lanes being consecutive output pixels so that loads and stores of one channel plane coalesce.
+constexpr int kSampleCh = 8;
+
+template <bool kFull>   // kFull: C is a multiple of kSampleCh, no per-channel guards (keeps the loads batched)
 __global__ void __launch_bounds__(256)
 bilinear_sample_kernel(const float* __restrict__ img, const float* __restrict__ grid_xy, float* __restrict__ out,
-                       int C, int Hi, int Wi, int Ho, int Wo, int c_per_slice) {
+                       int C, int Hi, int Wi, int Ho, int Wo) {
     const int b = blockIdx.z;
     const int HWo = Ho * Wo;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -334,28 +351,42 @@ bilinear_sample_kernel(const float* __restrict__ img, const float* __restrict__ 
     const float iy = __fmul_rn(__fmul_rn(__fadd_rn(yn, 1.0f), 0.5f), hm1);
     const float x0f = floorf(ix), y0f = floorf(iy);
     const float x1f = __fadd_rn(x0f, 1.0f), y1f = __fadd_rn(y0f, 1.0f);
-    const float w_nw = __fmul_rn(__fsub_rn(x1f, ix), __fsub_rn(y1f, iy));
-    const float w_ne = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(y1f, iy));
-    const float w_sw = __fmul_rn(__fsub_rn(x1f, ix), __fsub_rn(iy, y0f));
-    const float w_se = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(iy, y0f));
-    // NaN / huge coordinates fall out of range on every corner (float compares, then the int cast is safe)
+    // NaN / huge coordinates fall out of range on every corner (float compares, then the int cast is safe);
+    // an out-of-range corner gets weight 0 and a clamped (valid) address, so the loads need no predicates
     const bool xin0 = (x0f >= 0.0f) && (x0f <= wm1), xin1 = (x1f >= 0.0f) && (x1f <= wm1);
     const bool yin0 = (y0f >= 0.0f) && (y0f <= hm1), yin1 = (y1f >= 0.0f) && (y1f <= hm1);
     const int x0 = xin0 ? (int)x0f : 0, x1 = xin1 ? (int)x1f : 0;
     const int y0 = yin0 ? (int)y0f : 0, y1 = yin1 ? (int)y1f : 0;
     const bool nw = xin0 && yin0, ne = xin1 && yin0, sw = xin0 && yin1, se = xin1 && yin1;
+    const float w_nw = __fmul_rn(__fsub_rn(x1f, ix), __fsub_rn(y1f, iy));
+    const float w_ne = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(y1f, iy));
+    const float w_sw = __fmul_rn(__fsub_rn(x1f, ix), __fsub_rn(iy, y0f));
+    const float w_se = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(iy, y0f));
+    const int o_nw = y0 * Wi + x0, o_ne = y0 * Wi + x1, o_sw = y1 * Wi + x0, o_se = y1 * Wi + x1;
     const size_t plane_i = (size_t)Hi * Wi;
-    const int c_begin = blockIdx.y * c_per_slice;
-    const int c_end = min(C, c_begin + c_per_slice);
+    const int c_begin = blockIdx.y * kSampleCh;
     const float* src = img + ((size_t)b * C + c_begin) * plane_i;
     float* dst = out + ((size_t)b * C + c_begin) * HWo + i;
-    for (int c = c_begin; c < c_end; ++c, src += plane_i, dst += HWo) {
+    float v[kSampleCh][4];
+#pragma unroll
+    for (int k = 0; k < kSampleCh; ++k) {
+        const bool live = kFull || (c_begin + k < C);
+        const float* s = src + (live ? (size_t)k * plane_i : 0);
+        v[k][0] = ldg_ordered_f1(s + o_nw);
+        v[k][1] = ldg_ordered_f1(s + o_ne);
+        v[k][2] = ldg_ordered_f1(s + o_sw);
+        v[k][3] = ldg_ordered_f1(s + o_se);
+    }
+#pragma unroll
+    for (int k = 0; k < kSampleCh; ++k) {
+        if (!kFull && c_begin + k >= C) break;
+        // corners accumulate in the order nw, ne, sw, se; a corner outside the image contributes nothing
         float r = 0.0f;
-        if (nw) r = __fmul_rn(__ldg(src + (size_t)y0 * Wi + x0), w_nw);
-        if (ne) r = __fadd_rn(r, __fmul_rn(__ldg(src + (size_t)y0 * Wi + x1), w_ne));
-        if (sw) r = __fadd_rn(r, __fmul_rn(__ldg(src + (size_t)y1 * Wi + x0), w_sw));
-        if (se) r = __fadd_rn(r, __fmul_rn(__ldg(src + (size_t)y1 * Wi + x1), w_se));
-        *dst = r;
+        if (nw) r = __fmul_rn(v[k][0], w_nw);
+        if (ne) r = __fadd_rn(r, __fmul_rn(v[k][1], w_ne));
+        if (sw) r = __fadd_rn(r, __fmul_rn(v[k][2], w_sw));
+        if (se) r = __fadd_rn(r, __fmul_rn(v[k][3], w_se));
+        stg_stream_f1(dst + (size_t)k * HWo, r);
     }
 }
 
@@ -478,15 +509,14 @@ extern "C" int tcs_bilinear_sample(const float* img, const float* grid_xy, float
     using namespace tcs;
     TCS_REQUIRE(img && grid_xy && out, TCS_E_BADARG, "tcs_bilinear_sample: null pointer");
     TCS_REQUIRE(B > 0 && B <= 65535 && C > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, TCS_E_BADARG, "tcs_bilinear_sample: bad sizes");
-    // enough CTAs to fill the machine, few enough slices that the weights are amortised
-    const int pix_blocks = ceil_div(Ho * Wo, 256);
-    int slices = ceil_div(4 * num_sms(), pix_blocks * B);
-    slices = slices < 1 ? 1 : (slices > C ? C : slices);
-    const int c_per_slice = ceil_div(C, slices);
-    slices = ceil_div(C, c_per_slice);
-    TCS_REQUIRE(slices <= 65535, TCS_E_SHAPE, "tcs_bilinear_sample: too many channel slices");
-    dim3 g(pix_blocks, slices, B);
-    bilinear_sample_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(img, grid_xy, out, C, Hi, Wi, Ho, Wo, c_per_slice);
+    const int groups = ceil_div(C, kSampleCh);
+    TCS_REQUIRE(groups <= 65535, TCS_E_SHAPE, "tcs_bilinear_sample: C too large");
+    TCS_REQUIRE((long long)Hi * Wi < 0x7fffffffLL, TCS_E_SHAPE, "tcs_bilinear_sample: image plane too large");
+    dim3 g(ceil_div(Ho * Wo, 256), groups, B);
+    if (C % kSampleCh == 0)
+        bilinear_sample_kernel<true><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(img, grid_xy, out, C, Hi, Wi, Ho, Wo);
+    else
+        bilinear_sample_kernel<false><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(img, grid_xy, out, C, Hi, Wi, Ho, Wo);
     TCS_CHECK_LAUNCH("tcs_bilinear_sample");
     return 0;
 }
