@@ -17,7 +17,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -100,47 +99,55 @@ def camera(B, H, W, device, frame):
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), sampled through NVML every
+    2 ms from a thread (the timed region is tens of milliseconds: nvidia-smi -lms is too coarse for it)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.sm, self.bits, self.power, self.mx, self.err = index, [], 0, [], None, None
+        self._stop = threading.Event()
+        self.t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    phys = int(ids[self.index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = "nvml unavailable: %s" % (e,)
+            return
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+                except Exception as e:  # noqa: BLE001
+                    self.err = str(e)
+                    return
+                time.sleep(0.002)
+
+        self.t = threading.Thread(target=loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx = float(f[1])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self.t is not None:
+            self.t.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [self.err or "no samples"]}
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.bits & bit)
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.mx, "reasons": reasons,
+                "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None}
 
 
 # ------------------------------------------------------------------------------------------------------------

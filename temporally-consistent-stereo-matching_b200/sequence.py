@@ -72,7 +72,7 @@ def relative_pose(prev_T, cur_T):
     p = prev_T.double()
     c = cur_T.double()
     fwd = c @ torch.linalg.inv(p)
-    return fwd.float(), torch.linalg.inv(fwd).float()
+    return fwd.float().contiguous(), torch.linalg.inv(fwd).float().contiguous()   # inv() returns column-major
 
 
 def hot_path_frame(fmap1, fmap2, coords_seq, state=None, disp_init=None, rel_T=None, rel_T_inv=None, K=None,
