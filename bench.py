@@ -158,6 +158,10 @@ def cpu_frames_per_second(H, W, iters, budget_s, steps=None, warmup=1):
     """torch-CPU port of the reference's call sequence (oracle/torch_port.py), one sequence per step."""
     from oracle import torch_port as tp
     from tcs_b200 import sequence
+    try:   # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, RuntimeError):
+        pass
     g = torch.Generator().manual_seed(7)
     f = [torch.randn(1, C, H, W, generator=g) for _ in range(2)]
     xs = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
@@ -313,40 +317,42 @@ def run_b200(args):
     # ---- e2e: same step through the public API, inputs in pinned host memory, results read back
     e2e = None
     if not args.skip_e2e:
-        copy_stream = torch.cuda.Stream()
+        copy_streams = [torch.cuda.Stream(), torch.cuda.Stream()]   # one DMA queue per feature map (55 vs 38 GB/s)
         main = torch.cuda.current_stream()
         # three device staging buffers: previous frame (read by the warp), current frame, next frame (in flight)
         stage = [{"f1": torch.empty_like(slots[0]["f1"]), "f2": torch.empty_like(slots[0]["f2"])} for _ in range(3)]
-        res_host = [torch.empty((B, LEVELS * (2 * RADIUS + 1) + 3, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+        res_host = [{"corr": torch.empty((B, LEVELS * (2 * RADIUS + 1), H, W), dtype=torch.float32).pin_memory(),
+                     "init": [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(3)]} for _ in range(2)]
         n_e2e = 2 + K_steps
-        copied = [torch.cuda.Event() for _ in range(n_e2e + 1)]
+        copied = [[torch.cuda.Event() for _ in range(2)] for _ in range(n_e2e + 1)]
         done = [torch.cuda.Event() for _ in range(n_e2e + 1)]
         h2d = 2 * slots[0]["f1"].numel() * 4
-        d2h = res_host[0].numel() * 4
+        d2h = (res_host[0]["corr"].numel() + 3 * res_host[0]["init"][0].numel()) * 4
 
         def upload(k):
-            with torch.cuda.stream(copy_stream):
-                if k >= 2:
-                    copy_stream.wait_event(done[k - 2])         # step k-2 was the last reader of stage[k % 3]
-                stage[k % 3]["f1"].copy_(slots_host[k % 2]["f1"], non_blocking=True)
-                stage[k % 3]["f2"].copy_(slots_host[k % 2]["f2"], non_blocking=True)
-                copied[k].record(copy_stream)
+            for j, name in enumerate(("f1", "f2")):
+                cs = copy_streams[j]
+                with torch.cuda.stream(cs):
+                    if k >= 2:
+                        cs.wait_event(done[k - 2])              # step k-2 was the last reader of stage[k % 3]
+                    stage[k % 3][name].copy_(slots_host[k % 2][name], non_blocking=True)
+                    copied[k][j].record(cs)
 
         def e2e_step(k):
             s = k % 2
             if k + 1 < n_e2e:
                 upload(k + 1)                                   # next frame's H2D overlaps this frame's kernels
-            main.wait_event(copied[k])
+            main.wait_event(copied[k][0])
+            main.wait_event(copied[k][1])
             o = slots[1 - s]
             cur, prev = stage[k % 3], stage[(k - 1) % 3]
             out = tcs_b200.hot_path_frame(cur["f1"], cur["f2"], slots[s]["coords"],
                                           state=(o["last_disp"], prev["f1"], o["nets"]), rel_T=cam["rel_T"],
                                           rel_T_inv=cam["rel_T_inv"], K=cam["K"], K_inv=cam["K_inv"], baseline=cam["baseline"], **kw)
             r = res_host[s]
-            r[:, :36].copy_(out["corr"], non_blocking=True)
-            r[:, 36:37].copy_(out["sparse_disp"], non_blocking=True)
-            r[:, 37:38].copy_(out["cost"], non_blocking=True)
-            r[:, 38:39].copy_(out["mask"], non_blocking=True)
+            r["corr"].copy_(out["corr"], non_blocking=True)
+            for dst, name in zip(r["init"], ("sparse_disp", "cost", "mask")):
+                dst.copy_(out[name], non_blocking=True)
             done[k].record(main)
 
         stage[2]["f1"].copy_(slots[1]["f1"])                    # "frame -1" features for the first warp
