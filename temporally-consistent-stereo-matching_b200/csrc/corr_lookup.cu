@@ -14,6 +14,11 @@ namespace tcs {
 struct LevelPtrs {
     const float* p[TCS_MAX_LEVELS];
 };
+// Kernel parameters live in constant memory; indexing the array with a run-time value would make the compiler
+// copy it to local memory first (STL/LDL on the critical path).  Select with compares instead.
+__device__ __forceinline__ const float* level_ptr(const LevelPtrs& lv, int l) {
+    return l == 0 ? lv.p[0] : l == 1 ? lv.p[1] : l == 2 ? lv.p[2] : lv.p[3];
+}
 
 // grid_sample's normalise / un-normalise round trip, step by step in fp32 (no contraction).
 __device__ __forceinline__ float sample_pos(float xk, float wm1) {
@@ -28,41 +33,74 @@ __device__ __forceinline__ float sample_pos_fast(float xk, float wm1, float rc, 
     return __fmul_rn(__fadd_rn(xg, 1.0f), hwm1);
 }
 
-// ---- fused lookup, radius 4: one thread per (pixel, level) ---------------------------------------------
-// The 9 taps of a pixel read in-row indices [fc-5, fc+6] of the pixel's own row (fc = floor(coords/2^l);
-// a tap can land one off the centre estimate after grid_sample's round trip).  The thread fetches the
-// 16-byte-aligned quads covering that window (3 or 4 LDG.128, none for quads outside the row), parks them
-// in its own column of a transposed shared-memory tile (conflict-free both ways, and private to the
-// thread, so no barrier) and interpolates the taps from there.  Lanes are consecutive pixels, so every
-// output store is a full 128-byte line of one tap plane.
+// ---- fused lookup, radius 4: one thread per (pixel, level pair) -----------------------------------------
+// Bytes, not instructions, bound this kernel: a 40-byte tap window costs whole 128-byte lines, and at the
+// coarse levels neighbouring rows are so short that a call drags the entire level through DRAM.  So only
+// EVEN levels are read: the thread fetches one span of 24 floats of level 2g — in-row indices
+// [2(fu-5), 2(fu+6)+1], fu = floor(coords / 2^(2g+1)) — which contains both the 12-float window of level 2g
+// and, as pairs, the 12-entry window of level 2g+1, whose values are recomputed on the fly as
+// (a + b) * 0.5: the very expression the build epilogue (and avg_pool2d) used, hence bit-identical.
+// The span is fetched as 16-byte-aligned quads (at most 7 LDG.128, none outside the row), parked in the
+// thread's own column of a transposed shared-memory tile (conflict-free, private, so no barrier) and the
+// 2 x 9 taps are interpolated from there.  Lanes are consecutive pixels: every store is a full 128-byte
+// line of one tap plane.
 constexpr int kLookThreads = 256;
+constexpr int kLookQuads = 7;
+
+// One tap, branch-free: position -> (x0, weights); taps that fall outside the level get weight 0 on both
+// sides and a clamped (always valid) shared-memory index, so the loads need no predicate.
+struct TapPos {
+    float w_lo, w_hi;   // already zeroed for entries outside [0, W)
+    int x0;
+};
+
+__device__ __forceinline__ TapPos tap_position(float xk, float wm1, float rc, float hwm1, int W) {
+    TapPos t;
+    const float ix = sample_pos_fast(xk, wm1, rc, hwm1);
+    const float x0f = floorf(ix);
+    // NaN / far-away positions: the float compares fail, the weights vanish and x0 is forced to 0
+    const bool in0 = (x0f >= 0.0f) && (x0f <= wm1);                 // x0 inside the level
+    const bool in1 = (x0f >= -1.0f) && (x0f < wm1);                 // x0 + 1 inside the level
+    t.x0 = (in0 || in1) ? (int)x0f : 0;
+    t.w_hi = in1 ? __fsub_rn(ix, x0f) : 0.0f;
+    t.w_lo = in0 ? __fsub_rn(__fadd_rn(x0f, 1.0f), ix) : 0.0f;
+    (void)W;
+    return t;
+}
 
 __global__ void __launch_bounds__(kLookThreads)
 corr_lookup_r4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
-                      float* __restrict__ out, int HW, int W2, int num_levels, long long total_floats_l0) {
-    __shared__ float win[16][kLookThreads];
+                      float* __restrict__ out, int HW, int W2, int num_levels) {
+    __shared__ float win[4 * kLookQuads][kLookThreads];
     const int tid = threadIdx.x;
-    const int l = blockIdx.y;
+    const int lb = 2 * blockIdx.y;                              // the level that is read
+    const bool upper = lb + 1 < num_levels;                     // whether level lb + 1 is produced as well
     const int b = blockIdx.z;
     const int hw = blockIdx.x * kLookThreads + tid;
     if (hw >= HW) return;
-    const int Wl = W2 >> l;
-    const float wm1 = (float)(Wl - 1);
-    const float rc = __frcp_rn(wm1);
-    const float hwm1 = __fmul_rn(0.5f, wm1);
-    const float* __restrict__ base = lv.p[l];
+    const int Wb = W2 >> lb, Wu = Wb >> 1;
+    const float* __restrict__ base = level_ptr(lv, lb);
     const long long p = (long long)b * HW + hw;
-    const long long row_start = p * Wl;
-    const long long readable = (((long long)gridDim.z * HW * Wl + 3) >> 2) << 2;   // caller pads each level to 16 B
+    const long long row_start = p * Wb;
+    const long long readable = (((long long)gridDim.z * HW * Wb + 3) >> 2) << 2;   // caller pads each level to 16 B
 
-    const float cl = __ldg(coords + b * coords_bstride + hw) * (1.0f / (float)(1 << l));   // coords / 2**l (exact)
-    const float fcf = fminf(fmaxf(floorf(cl), -16.0f), (float)(Wl + 16));
-    const int wfirst = (int)fcf - 5;
-    const long long a_abs = ((row_start + wfirst) >> 2) << 2;   // floor to a multiple of 4 floats (16 B)
-    const int win_first = (int)(a_abs - row_start);             // in-row index of win[0]
-    const int need_lo = max(wfirst, 0), need_hi = min(wfirst + 11, Wl - 1);
+    const float cb = __ldg(coords + b * coords_bstride + hw) * (1.0f / (float)(1 << lb));   // coords / 2**lb (exact)
+    const float cu = cb * 0.5f;
+    int span_first, span_last;                                  // in-row indices of level lb that may be needed
+    if (upper) {
+        const int fu = (int)fminf(fmaxf(floorf(cu), -16.0f), (float)(Wu + 16));
+        span_first = 2 * (fu - 5);
+        span_last = 2 * (fu + 6) + 1;
+    } else {
+        const int fb = (int)fminf(fmaxf(floorf(cb), -16.0f), (float)(Wb + 16));
+        span_first = fb - 5;
+        span_last = fb + 6;
+    }
+    const long long a_abs = ((row_start + span_first) >> 2) << 2;   // floor to a multiple of 4 floats (16 B)
+    const int win_first = (int)(a_abs - row_start);                  // in-row index of win[0]
+    const int need_lo = max(span_first, 0), need_hi = min(span_last, Wb - 1);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kLookQuads; ++k) {
         const int q_lo = win_first + 4 * k;                     // in-row index of this quad's first float
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         const long long idx = a_abs + 4 * k;
@@ -73,25 +111,38 @@ corr_lookup_r4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long
         win[4 * k + 2][tid] = v.z;
         win[4 * k + 3][tid] = v.w;
     }
-    float* o = out + (((long long)b * num_levels + l) * 9) * HW + hw;
-    const float Wlf = (float)Wl;
+    constexpr int kWin = 4 * kLookQuads;
+    const float* col = &win[0][tid];                            // entry i of this thread's span: col[i * kLookThreads]
+    {   // ---- level lb: taps straight from the span
+        const float wm1 = (float)(Wb - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
+        float* o = out + (((long long)b * num_levels + lb) * 9) * HW + hw;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        const float xk = __fadd_rn((float)(t - 4), cl);         // corr.py:43  dx + coords/2^i
-        const float ix = sample_pos_fast(xk, wm1, rc, hwm1);
-        float r = 0.0f;
-        if (ix > -1.0f && ix < Wlf) {                           // otherwise both taps are out of range
-            const float x0f = floorf(ix);
-            const int x0 = (int)x0f;
-            const float w_hi = __fsub_rn(ix, x0f);
-            const float w_lo = __fsub_rn(__fadd_rn(x0f, 1.0f), ix);
-            const int i0 = x0 - win_first;
-            float v0 = 0.0f, v1 = 0.0f;
-            if (x0 >= 0 && (unsigned)i0 < 16u) v0 = win[i0][tid];
-            if (x0 + 1 < Wl && (unsigned)(i0 + 1) < 16u) v1 = win[i0 + 1][tid];
-            r = fmaf(v1, w_hi, __fmul_rn(v0, w_lo));
+        for (int t = 0; t < 9; ++t) {
+            const TapPos tp = tap_position(__fadd_rn((float)(t - 4), cb), wm1, rc, hwm1, Wb);   // corr.py:43
+            const int i0 = min(max(tp.x0 - win_first, 0), kWin - 2);
+            const float v0 = col[i0 * kLookThreads], v1 = col[(i0 + 1) * kLookThreads];
+            // a zero weight stands for "outside the level" (zeros padding): the product must be 0 even if the
+            // clamped slot holds a non-finite value
+            const float a0 = (tp.w_lo != 0.0f) ? __fmul_rn(v0, tp.w_lo) : 0.0f;
+            const float r = (tp.w_hi != 0.0f) ? fmaf(v1, tp.w_hi, a0) : a0;
+            stg_stream_f1(o, r);
+            o += HW;
         }
-        stg_stream_f1(o + (long long)t * HW, r);
+    }
+    if (upper) {   // ---- level lb + 1: entries re-pooled from pairs of the span
+        const float wm1 = (float)(Wu - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
+        float* o = out + (((long long)b * num_levels + lb + 1) * 9) * HW + hw;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const TapPos tp = tap_position(__fadd_rn((float)(t - 4), cu), wm1, rc, hwm1, Wu);
+            const int i0 = min(max(2 * tp.x0 - win_first, 0), kWin - 4);   // span index of the pair behind entry x0
+            const float v0 = __fmul_rn(__fadd_rn(col[i0 * kLookThreads], col[(i0 + 1) * kLookThreads]), 0.5f);
+            const float v1 = __fmul_rn(__fadd_rn(col[(i0 + 2) * kLookThreads], col[(i0 + 3) * kLookThreads]), 0.5f);
+            const float a0 = (tp.w_lo != 0.0f) ? __fmul_rn(v0, tp.w_lo) : 0.0f;
+            const float r = (tp.w_hi != 0.0f) ? fmaf(v1, tp.w_hi, a0) : a0;
+            stg_stream_f1(o, r);
+            o += HW;
+        }
     }
 }
 
@@ -106,7 +157,7 @@ corr_lookup_generic_kernel(const LevelPtrs lv, const float* __restrict__ coords,
     const float wm1 = (float)(Wl - 1);
     const long long b = p / HW, hw = p - b * HW;
     const float cl = __ldg(coords + b * coords_bstride + hw) * (1.0f / (float)(1 << l));
-    const float* __restrict__ row = lv.p[l] + p * Wl;
+    const float* __restrict__ row = level_ptr(lv, l) + p * Wl;
     const int taps = 2 * radius + 1;
     float* o = out + ((b * num_levels + l) * taps) * (long long)HW + hw;
     for (int t = 0; t < taps; ++t) {
@@ -155,7 +206,7 @@ corr_lookup_alt_kernel(const float* __restrict__ a, const LevelPtrs bl, const fl
         const float cl = c0 * (1.0f / (float)(1 << l));
         const float fcf = fminf(fmaxf(floorf(cl), -32.0f), (float)(Wl + 32));
         const int col0 = (int)fcf - radius - 1;
-        const float* __restrict__ brow = bl.p[l] + bh * (long long)Wl * C;
+        const float* __restrict__ brow = level_ptr(bl, l) + bh * (long long)Wl * C;
         // dots[g][i]: partial sums of columns col0 + 16*g + i  (ncols <= 20 -> up to two groups of 16)
         for (int g = 0; g * 16 < ncols; ++g) {
             float part[16];
@@ -355,8 +406,14 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (radius == 4) {
         TCS_REQUIRE(B <= 65535, TCS_E_SHAPE, "tcs_corr_lookup: B must be <= 65535");
-        dim3 grid((unsigned)ceil_div(H * W1, kLookThreads), num_levels, B);
-        corr_lookup_r4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels, 0);
+        dim3 grid((unsigned)ceil_div(H * W1, kLookThreads), (num_levels + 1) / 2, B);
+        static bool attr_done = false;
+        if (!attr_done) {   // leave most of the unified array to L1: the loads stream through it (31 vs 68 us)
+            const int carve = carveout_percent("TCS_CARVE_LOOKUP", 40);
+            if (carve >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_r4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            attr_done = true;
+        }
+        corr_lookup_r4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels);
     } else {
         dim3 grid((unsigned)ceil_div_ll(npix, 256), num_levels);
         corr_lookup_generic_kernel<<<grid, 256, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels, radius, npix);

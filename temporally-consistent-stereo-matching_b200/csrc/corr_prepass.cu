@@ -148,6 +148,7 @@ extern "C" int tcs_corr_prepass(const float* fmap, void* hi, void* lo, float* n3
         static bool attr_done = false;
         if (!attr_done) {
             TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 513 * 4));
+            { const int cv = carveout_percent("TCS_CARVE_PREPASS", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); }
             attr_done = true;
         }
         corr_prepass_kernel<true><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W);
@@ -155,6 +156,7 @@ extern "C" int tcs_corr_prepass(const float* fmap, void* hi, void* lo, float* n3
         static bool attr_done = false;
         if (!attr_done) {
             TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 513 * 4));
+            { const int cv = carveout_percent("TCS_CARVE_PREPASS", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); }
             attr_done = true;
         }
         corr_prepass_kernel<false><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W);

@@ -2,6 +2,7 @@
 #include "tcs_common.cuh"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 namespace tcs {
@@ -26,6 +27,13 @@ int num_sms() {
         slot = n;
     }
     return slot;
+}
+
+int carveout_percent(const char* env, int tuned_default) {
+    const char* e = getenv(env);
+    if (e == nullptr || *e == '\0') return tuned_default;
+    const int v = atoi(e);
+    return v < 0 ? -1 : (v > 100 ? 100 : v);
 }
 
 }  // namespace tcs

@@ -46,6 +46,10 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 int num_sms();  // cached SM count of the current device
+// Shared-memory carve-out (percent of the unified L1/shared array) to request for a kernel: the tuned default,
+// or the value of environment variable `env` when set (development aid).  Kernels that stage tiles in shared
+// memory but stream through L1 starve when resident CTAs take the whole array as shared memory.
+int carveout_percent(const char* env, int tuned_default);
 
 // ---- device helpers ----------------------------------------------------------------------------
 #ifdef __CUDACC__

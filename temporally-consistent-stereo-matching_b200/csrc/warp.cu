@@ -476,6 +476,8 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
         if (!attr_done) {                                                                                             \
             TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_splat_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_splat)); \
             TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_finalize_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin)); \
+            { const int cv = carveout_percent("TCS_CARVE_SPLAT", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_splat_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); } \
+            { const int cv = carveout_percent("TCS_CARVE_FINALIZE", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_finalize_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); } \
             attr_done = true;                                                                                         \
         }                                                                                                             \
         warp_splat_kernel<G><<<grid, kWarpThreads, smem_splat, s>>>(fmap, disp1, tx, ty, valid, sums, accum, B, H, W, per_sample_mean); \
