@@ -70,6 +70,15 @@ int tcs_corr_build(const void* a_hi, const void* a_lo, const void* b_hi, const v
                    float* lvl0, float* lvl1, float* lvl2, float* lvl3,
                    int B, int H, int W1, int W2, int C, int num_levels, int prec, void* stream);
 
+/* The same result in ONE kernel straight from the fp32 NCHW feature maps: normalisation, the 16-bit hi/lo
+ * split and the K-major operand layout happen on chip, so the operands never make a round trip through HBM
+ * (halves the build's traffic).  ref: core/corr.py:54-62 + :15-23.
+ *   fmap1 [B,C,H,W1], fmap2 [B,C,H,W2] fp32;  lvl[l] as for tcs_corr_build.
+ * Requires C % 64 == 0, 8 <= W2 <= 240, W1 <= 384 (TCS_E_SHAPE otherwise: use the two-step path). */
+int tcs_corr_build_fused(const float* fmap1, const float* fmap2,
+                         float* lvl0, float* lvl1, float* lvl2, float* lvl3,
+                         int B, int H, int W1, int W2, int C, int num_levels, int prec, void* stream);
+
 /* Exact-fp32 CUDA-core build (no tensor cores): the strict-parity mode and the in-library check of
  * the tensor-core path.  Same outputs as tcs_corr_build; operands are the fp32 normalised
  * channels-last features written by tcs_corr_prepass (n32). */

@@ -27,6 +27,7 @@ SIGNATURES = {
     "tcs_last_error": (ctypes.c_char_p, []),
     "tcs_corr_prepass": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_build": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "tcs_corr_build_fused": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_build_fp32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_lookup": (_i, [_p, _p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_fmap_pool_w": (_i, [_p, _p, _i, _i, _i, _i, _p]),

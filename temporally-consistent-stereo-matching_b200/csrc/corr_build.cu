@@ -17,6 +17,7 @@
 // Roofline: HBM-write-bound (fp32 levels: 7.5 B per 512 FLOP); see DESIGN.md.
 #include "tcs_common.cuh"
 #include "sm100_ptx.cuh"
+#include "corr_epilogue.cuh"
 
 namespace tcs {
 
@@ -47,17 +48,6 @@ struct BuildParams {
     uint32_t idesc;
     float scale;
 };
-
-__device__ __forceinline__ void store4(float* __restrict__ row, int col, int limit, bool vec_ok, const float4& v) {
-    if (vec_ok && col + 3 < limit) {
-        *reinterpret_cast<float4*>(row + col) = v;
-    } else {
-        if (col < limit) row[col] = v.x;
-        if (col + 1 < limit) row[col + 1] = v.y;
-        if (col + 2 < limit) row[col + 2] = v.z;
-        if (col + 3 < limit) row[col + 3] = v.w;
-    }
-}
 
 __global__ void __launch_bounds__(kBuildThreads, 1)
 corr_build_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -162,10 +152,10 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const int quarter = warp & 3;       // TMEM lane quarter this warp may access
         float4* stage0 = reinterpret_cast<float4*>(epi_base + ew * kEpiStageBytes);  // [32 rows][8 slots]
         float4* stage1 = stage0 + 256;                                                // [32 rows][4 slots]
-        const int W1 = p.W1, W2 = p.W2;
-        const int W2_1 = W2 >> 1, W2_2 = W2 >> 2, W2_3 = W2 >> 3;
-        const bool vec0 = (W2 & 3) == 0, vec1 = (W2_1 & 3) == 0, vec2 = (W2_2 & 3) == 0, vec3 = (W2_3 & 3) == 0;
-        const float scale = p.scale;
+        EpilogueArgs ea;
+#pragma unroll
+        for (int l = 0; l < TCS_MAX_LEVELS; ++l) ea.lvl[l] = p.lvl[l];
+        ea.W1 = p.W1; ea.W2 = p.W2; ea.num_levels = p.num_levels; ea.scale = p.scale;
         int iter = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
             const int n_t = tile % p.n_tiles;
@@ -174,92 +164,12 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             const uint32_t acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
             const int n0 = n_t * p.block_n;
-            const int n_end = min(n0 + p.block_n, W2);   // exclusive column limit of this tile at level 0
-            const int row0 = m_t * kBlockM + quarter * 32;
-            const size_t rbase = (size_t)bh * W1;
-
+            const int n_end = min(n0 + p.block_n, p.W2);   // exclusive column limit of this tile at level 0
             ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
             ptx::tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols;
-            const int n_chunks = (n_end - n0 + 31) >> 5;
-            const int ch_first = ew >> 2;                       // this warp's parity among the chunks
-            const int ch_last = ch_first + ((n_chunks - 1 - ch_first) & ~1);   // its last chunk (or < ch_first: none)
-            if (ch_first >= n_chunks) {                         // nothing to read: release the accumulator at once
-                ptx::tc_fence_before_sync();
-                ptx::mbar_arrive(bar_tempty + 8 * acc);
-            }
-            for (int ch = ch_first; ch < n_chunks; ch += 2) {
-                float v[32];
-                ptx::tmem_ld_32x32(taddr + ch * 32, v);
-                if (ch == ch_last) {
-                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-                    ptx::tc_fence_before_sync();
-                    ptx::mbar_arrive(bar_tempty + 8 * acc);
-                }
-                const int cg = n0 + ch * 32;  // first level-0 column of the chunk
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] *= scale;
-                // ---- level 0: transpose through smem so that each store instruction covers 4 full 128 B rows
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    stage0[lane * 8 + (s ^ (lane & 7))] = make_float4(v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]);
-                // ---- level 1 (needed by every deeper level too)
-                float l1[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) l1[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
-                if (p.num_levels > 1) {
-#pragma unroll
-                    for (int s = 0; s < 4; ++s)
-                        stage1[lane * 4 + (s ^ ((lane >> 1) & 3))] = make_float4(l1[4 * s], l1[4 * s + 1], l1[4 * s + 2], l1[4 * s + 3]);
-                }
-                __syncwarp();
-                {
-                    const int s = lane & 7;
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rr = it * 4 + (lane >> 3);
-                        const int row = row0 + rr;
-                        if (row < W1) {
-                            const float4 val = stage0[rr * 8 + (s ^ (rr & 7))];
-                            store4(p.lvl[0] + (rbase + row) * W2, cg + 4 * s, n_end, vec0, val);
-                        }
-                    }
-                }
-                if (p.num_levels > 1) {
-                    const int s = lane & 3;
-                    const int lim = min(n_end >> 1, W2_1);
-#pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int rr = it * 8 + (lane >> 2);
-                        const int row = row0 + rr;
-                        if (row < W1) {
-                            const float4 val = stage1[rr * 4 + (s ^ ((rr >> 1) & 3))];
-                            store4(p.lvl[1] + (rbase + row) * W2_1, (cg >> 1) + 4 * s, lim, vec1, val);
-                        }
-                    }
-                }
-                __syncwarp();
-                // ---- levels 2 and 3: 32 B / 16 B per row, written straight from the owning thread
-                if (p.num_levels > 2) {
-                    float l2[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) l2[j] = (l1[2 * j] + l1[2 * j + 1]) * 0.5f;
-                    const int row = row0 + lane;
-                    if (row < W1) {
-                        float* r2 = p.lvl[2] + (rbase + row) * W2_2;
-                        const int lim2 = min(n_end >> 2, W2_2);
-                        store4(r2, (cg >> 2), lim2, vec2, make_float4(l2[0], l2[1], l2[2], l2[3]));
-                        store4(r2, (cg >> 2) + 4, lim2, vec2, make_float4(l2[4], l2[5], l2[6], l2[7]));
-                        if (p.num_levels > 3) {
-                            float* r3 = p.lvl[3] + (rbase + row) * W2_3;
-                            const int lim3 = min(n_end >> 3, W2_3);
-                            store4(r3, (cg >> 3), lim3, vec3,
-                                   make_float4((l2[0] + l2[1]) * 0.5f, (l2[2] + l2[3]) * 0.5f,
-                                               (l2[4] + l2[5]) * 0.5f, (l2[6] + l2[7]) * 0.5f));
-                        }
-                    }
-                }
-            }
+            epilogue_tile<false>(ea, taddr, n0, n_end, m_t * kBlockM + quarter * 32, (size_t)bh * p.W1, ew >> 2, lane,
+                                 stage0, stage1, bar_tempty + 8 * acc);
         }
     }
 

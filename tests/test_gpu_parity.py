@@ -92,6 +92,33 @@ def test_build_full_size(tcs, B, H, W, precision, rtol, atol):
         assert_exact(lv[l], pooled[l], what="%s level %d is not the exact pool of level %d" % (precision, l, l - 1))
 
 
+@pytest.mark.parametrize("B,H,W1,W2", [(1, 136, 240, 240), (2, 120, 160, 160), (1, 9, 200, 72), (1, 5, 300, 240), (3, 2, 17, 40)])
+@pytest.mark.parametrize("precision", ["fp16x3", "bf16x3", "fp16", "bf16"])
+def test_build_fused_matches_two_step(tcs, B, H, W1, W2, precision):
+    """The single fused kernel (normalise + split + UMMA + pyramid) against the pre-pass + build pair: same
+    operands up to the last ulp of x/||x||, so the volumes agree far inside either precision's error."""
+    g = torch.Generator().manual_seed(W1 * 7 + W2)
+    f1 = torch.randn(B, 256, H, W1, generator=g).cuda()
+    f2 = torch.randn(B, 256, H, W2, generator=g).cuda()
+    _, fused = tcs.build_pyramid(f1, f2, 4, precision, fused=True)
+    _, two = tcs.build_pyramid(f1, f2, 4, precision, fused=False)
+    tol = {"fp16x3": 2e-6, "bf16x3": 2e-6, "fp16": 1e-4, "bf16": 1e-3}[precision]   # an operand ulp can flip a 16-bit rounding
+    for l in range(4):
+        assert_close(host(fused[l]), host(two[l]), rtol=0.0, atol=tol, what="%s level %d" % (precision, l))
+    pooled = orc.corr_pyramid(host(fused[0]), 4)
+    for l in range(1, 4):
+        assert_exact(host(fused[l]), pooled[l], what="fused level %d is not the exact pool" % l)
+    if precision == "fp16x3":
+        assert_close(host(fused[0]), orc.corr_volume(f1.cpu().numpy(), f2.cpu().numpy(), np.float64), rtol=1e-5, atol=1e-6, what="fused vs fp64")
+
+
+def test_build_fused_rejects_wide_rows(tcs):
+    f = torch.randn(1, 64, 2, 312).cuda()
+    with pytest.raises(RuntimeError):
+        tcs.build_pyramid(f, f, 4, "fp16x3", fused=True)
+    tcs.build_pyramid(f, f, 4, "fp16x3")            # default falls back to the two-step path
+
+
 def test_build_properties_540p(tcs):
     """Size-independent properties at the headline shape: self-correlation has a unit diagonal, symmetric
     volume, values in [-1, 1], level means preserved."""

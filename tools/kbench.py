@@ -88,6 +88,13 @@ for prec in ("fp16", "fp16x3", "bf16x3"):
                                                   b_hi.data_ptr(), b_lo.data_ptr() if b_lo is not None else None, *ptrs, B, H, W, W, C, 4,
                                                   _lib.PRECISIONS[prec], st()), nb, flops=2.0 * npix * W * C * (3 if "x3" in prec else 1))
     del a_hi, a_lo, b_hi, b_lo, flat, levels
+for prec in ("fp16", "fp16x3"):
+    flat, levels = tcs_b200.corr.alloc_pyramid(B, H, W, W, 4, dev)
+    ptrs = [lv.data_ptr() for lv in levels]
+    nb = npix * C * 8 + npix * W * 4 * 1.875
+    timeit("fused[%s]" % prec, lambda: _lib.call("tcs_corr_build_fused", f1.data_ptr(), f2.data_ptr(), *ptrs, B, H, W, W, C, 4,
+                                                   _lib.PRECISIONS[prec], st()), nb, flops=2.0 * npix * W * C * (3 if "x3" in prec else 1))
+    del flat, levels
 blk = tcs_b200.CorrBlock1D(f1, f2, precision="fp16x3")
 timeit("lookup", lambda: blk(coords), 308 * npix)
 timeit("argmax", lambda: blk.argmax_disp(), npix * W * 4)
