@@ -227,6 +227,8 @@ def run_b200(args):
 
     B, iters = args.seqs_per_gpu, args.iters
     H, W = feature_hw(args.height, args.width)
+    fused_build = (args.mode == "pyramid" and args.precision != "fp32" and W <= 240 and W % 4 == 0
+                   and os.environ.get("TCS_B200_FUSED_BUILD", "1") != "0")
     K_steps, W_steps = args.steps, max(args.warmup, 3)
     pk = peaks()
 
@@ -388,7 +390,7 @@ def run_b200(args):
     warp_bytes = npix * (4 + 1024 + 1024 + 4 + 1024 + 4 + 4 + 1344)
     phases_out = {
         "build_ms": phase_ms[0], "warp_ms": phase_ms[1], "lookups_ms": phase_ms[2],
-        "build": {"note": "2 pre-passes + tcgen05 build, fp32 fmaps in, fp32 levels out", "algorithmic_bytes": build_bytes,
+        "build": {"note": ("fused normalise + split + tcgen05 build" if fused_build else "2 pre-passes + tcgen05 build") + ", fp32 fmaps in, fp32 levels out", "algorithmic_bytes": build_bytes,
                   "hbm_gbs": build_bytes / (phase_ms[0] * 1e-3) / 1e9, "hbm_frac": build_bytes / (phase_ms[0] * 1e-3) / 1e9 / pk["hbm_gbs"],
                   "tflops": build_flops / (phase_ms[0] * 1e-3) / 1e12, "tensor_frac": build_flops / (phase_ms[0] * 1e-3) / 1e12 / pk["bf16_tflops"]},
         "warp": {"algorithmic_bytes": warp_bytes, "hbm_gbs": warp_bytes / (phase_ms[1] * 1e-3) / 1e9,
@@ -410,9 +412,9 @@ def run_b200(args):
             "config": {"workload": "%dx%d temporal frames, %d lookup iters, 4-level pyramid r=4, C=256, %d sequences per GPU batched"
                                    % (args.height, args.width, iters, B),
                        "feature_hw": [H, W], "seqs_per_gpu": B, "precision": args.precision, "mode": args.mode,
-                       "cuda_graphs": graphs is not None, "l2": "inputs larger than L2 (%.0f MB of feature maps per step, 2 alternating slots)" % (2 * npix * C * 4 / 1e6),
+                       "cuda_graphs": graphs is not None, "fused_build": fused_build, "l2": "inputs larger than L2 (%.0f MB of feature maps per step, 2 alternating slots)" % (2 * npix * C * 4 / 1e6),
                        "parallelism": "sequences sharded per GPU, no data-path collective"},
-            "e2e": e2e, "gpu_launches": K_steps * sequence.launches_per_frame(iters, False, mode=args.mode),
+            "e2e": e2e, "gpu_launches": K_steps * sequence.launches_per_frame(iters, False, mode=args.mode, fused_build=fused_build),
             "clocks": clocks, "roofline": roofline, "phases": phases_out, "cpu_baseline": cpu, "checksum": checksum,
         }))
     if world > 1:

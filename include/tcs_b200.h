@@ -74,7 +74,8 @@ int tcs_corr_build(const void* a_hi, const void* a_lo, const void* b_hi, const v
  * split and the K-major operand layout happen on chip, so the operands never make a round trip through HBM
  * (halves the build's traffic).  ref: core/corr.py:54-62 + :15-23.
  *   fmap1 [B,C,H,W1], fmap2 [B,C,H,W2] fp32;  lvl[l] as for tcs_corr_build.
- * Requires C % 64 == 0, 8 <= W2 <= 240, W1 <= 384 (TCS_E_SHAPE otherwise: use the two-step path). */
+ * Requires C % 32 == 0, 8 <= W2 <= 240, W1 <= 256, W1 and W2 multiples of 4 and 16-byte aligned maps
+ * (TCS_E_SHAPE otherwise: use the two-step path). */
 int tcs_corr_build_fused(const float* fmap1, const float* fmap2,
                          float* lvl0, float* lvl1, float* lvl2, float* lvl3,
                          int B, int H, int W1, int W2, int C, int num_levels, int prec, void* stream);

@@ -70,16 +70,16 @@ def alloc_pyramid(B, H, W1, W2, num_levels, device):
 
 
 FUSED_MAX_W2 = 240
-FUSED_MAX_W1 = 384
+FUSED_MAX_W1 = 256
 
 
 def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3", fused=None):
     """All pyramid levels of the 1-D all-pairs cosine correlation (ref: corr.py:54-62 + :15-23).
 
     precision: 'bf16' | 'bf16x3' | 'fp16' | 'fp16x3' (tcgen05 tensor cores) or 'fp32' (CUDA cores).
-    fused: True = the single fused kernel (normalise + split + UMMA + pyramid; needs W2 <= 240, W1 <= 384);
-    False / None = the pre-pass + build pair, which is currently the faster of the two on B200 (DESIGN.md 3.1);
-    TCS_B200_FUSED_BUILD=1 makes None mean "fused whenever the shape allows"."""
+    fused: None = the single fused kernel (normalise + split + UMMA + pyramid, no operand round trip through HBM)
+    whenever the shape allows it (W2 <= 240, W1 <= 256, both multiples of 4), else the pre-pass + build pair;
+    True / False force one of the two.  TCS_B200_FUSED_BUILD=0 makes None mean "never fused"."""
     fmap1 = _check_fmap("fmap1", fmap1)
     fmap2 = _check_fmap("fmap2", fmap2)
     B, C, H, W1 = fmap1.shape
@@ -98,9 +98,9 @@ def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3", fused=None):
         else:
             if precision not in _lib.PRECISIONS:
                 raise ValueError("unknown precision %r" % (precision,))
-            fits = 8 <= W2 <= FUSED_MAX_W2 and W1 <= FUSED_MAX_W1
+            fits = 8 <= W2 <= FUSED_MAX_W2 and W1 <= FUSED_MAX_W1 and W1 % 4 == 0 and W2 % 4 == 0 and C % 32 == 0
             if fused is None:
-                fused = fits and os.environ.get("TCS_B200_FUSED_BUILD", "0") == "1"
+                fused = fits and os.environ.get("TCS_B200_FUSED_BUILD", "1") != "0"
             if fused:
                 _lib.call("tcs_corr_build_fused", fmap1.data_ptr(), fmap2.data_ptr(), *ptrs, B, H, W1, W2, C, num_levels,
                           _lib.PRECISIONS[precision], _stream())

@@ -18,6 +18,7 @@
 #include "tcs_common.cuh"
 #include "sm100_ptx.cuh"
 #include "corr_epilogue.cuh"
+#include "tma_host.cuh"
 
 namespace tcs {
 
@@ -150,8 +151,8 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         // ================= epilogue =================
         const int ew = warp - 2;            // staging buffer index
         const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-        float4* stage0 = reinterpret_cast<float4*>(epi_base + ew * kEpiStageBytes);  // [32 rows][8 slots]
-        float4* stage1 = stage0 + 256;                                                // [32 rows][4 slots]
+        const uint32_t stage0 = smem_u32(epi_base + ew * kEpiStageBytes);   // [32 rows][8 float4]
+        const uint32_t stage1 = stage0 + 4096;                              // [32 rows][4 float4]
         EpilogueArgs ea;
 #pragma unroll
         for (int l = 0; l < TCS_MAX_LEVELS; ++l) ea.lvl[l] = p.lvl[l];
@@ -184,24 +185,6 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
 
 // Operand [BH, W, C] 16-bit, channels contiguous; box = [1, box_w, 64], 128 B swizzle.
 static int make_operand_map(CUtensorMap* tm, const void* base, int BH, int W, int C, int box_w, bool fp16) {

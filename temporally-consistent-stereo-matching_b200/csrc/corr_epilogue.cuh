@@ -26,31 +26,31 @@ __device__ __forceinline__ void store4(float* __restrict__ row, int col, int lim
 }
 
 // One epilogue warp's share of a tile.  The warp owns TMEM lanes [32*quarter, +32) (= tile rows) and the
-// 32-column chunks of parity `parity` (two warps per quarter split the columns).  After tcgen05.ld each
+// 32-column chunks parity, parity + kChunkStride, ... (kChunkStride warps per quarter split the columns).  After tcgen05.ld each
 // thread holds one w1 row, so the pooling cascade along w2 is intra-thread.  Levels 0 and 1 go through a
 // swizzled shared-memory transpose so that each store instruction covers whole 128-byte row segments;
 // levels 2 and 3 (32 B / 16 B per row and chunk) are written by the owning thread.
 //   taddr       TMEM address of (lane quarter, first column of the accumulator)
 //   n0, n_end   level-0 column range of the tile (n0 a multiple of 32)
 //   row0        first w1 row of this warp's quarter;  rbase = (b*H + h) * W1
-//   stage0/1    per-warp staging: [32 rows][8 float4] and [32 rows][4 float4]; they may alias when
-//               kAliasedStage (then an extra warp barrier separates the two uses)
+//   stage0/1    per-warp staging (32-bit shared addresses): [32 rows][8 float4] and [32 rows][4 float4]; they
+//               may alias when kAliasedStage (then an extra warp barrier separates the two uses)
 //   bar_tempty  mbarrier to arrive on (all 32 lanes) once this warp has read its last chunk from TMEM
-template <bool kAliasedStage>
+template <bool kAliasedStage, int kChunkStride = 2>
 __device__ __forceinline__ void epilogue_tile(const EpilogueArgs& p, uint32_t taddr, int n0, int n_end, int row0,
-                                              size_t rbase, int parity, int lane, float4* stage0, float4* stage1,
+                                              size_t rbase, int parity, int lane, uint32_t stage0, uint32_t stage1,
                                               uint32_t bar_tempty) {
     const int W1 = p.W1, W2 = p.W2;
     const int W2_1 = W2 >> 1, W2_2 = W2 >> 2, W2_3 = W2 >> 3;
     const bool vec0 = (W2 & 3) == 0, vec1 = (W2_1 & 3) == 0, vec2 = (W2_2 & 3) == 0, vec3 = (W2_3 & 3) == 0;
     const float scale = p.scale;
     const int n_chunks = (n_end - n0 + 31) >> 5;
-    const int ch_last = parity + ((n_chunks - 1 - parity) & ~1);   // this warp's last chunk (only meaningful if any)
+    const int ch_last = parity + ((n_chunks - 1 - parity) / kChunkStride) * kChunkStride;   // this warp's last chunk (if any)
     if (parity >= n_chunks) {                                      // nothing to read: release the accumulator at once
         ptx::tc_fence_before_sync();
         ptx::mbar_arrive(bar_tempty);
     }
-    for (int ch = parity; ch < n_chunks; ch += 2) {
+    for (int ch = parity; ch < n_chunks; ch += kChunkStride) {
         float v[32];
         ptx::tmem_ld_32x32(taddr + ch * 32, v);
         if (ch == ch_last) {
@@ -64,7 +64,7 @@ __device__ __forceinline__ void epilogue_tile(const EpilogueArgs& p, uint32_t ta
         // ---- level 0: transpose through smem so that each store instruction covers 4 full 128 B rows
 #pragma unroll
         for (int s = 0; s < 8; ++s)
-            stage0[lane * 8 + (s ^ (lane & 7))] = make_float4(v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]);
+            sts_v4_f32(stage0 + 16u * (lane * 8 + (s ^ (lane & 7))), make_float4(v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]));
         // ---- level 1 (needed by every deeper level too)
         float l1[16];
 #pragma unroll
@@ -72,7 +72,7 @@ __device__ __forceinline__ void epilogue_tile(const EpilogueArgs& p, uint32_t ta
         if (!kAliasedStage && p.num_levels > 1) {
 #pragma unroll
             for (int s = 0; s < 4; ++s)
-                stage1[lane * 4 + (s ^ ((lane >> 1) & 3))] = make_float4(l1[4 * s], l1[4 * s + 1], l1[4 * s + 2], l1[4 * s + 3]);
+                sts_v4_f32(stage1 + 16u * (lane * 4 + (s ^ ((lane >> 1) & 3))), make_float4(l1[4 * s], l1[4 * s + 1], l1[4 * s + 2], l1[4 * s + 3]));
         }
         __syncwarp();
         {
@@ -82,7 +82,7 @@ __device__ __forceinline__ void epilogue_tile(const EpilogueArgs& p, uint32_t ta
                 const int rr = it * 4 + (lane >> 3);
                 const int row = row0 + rr;
                 if (row < W1) {
-                    const float4 val = stage0[rr * 8 + (s ^ (rr & 7))];
+                    const float4 val = lds_v4_f32(stage0 + 16u * (rr * 8 + (s ^ (rr & 7))));
                     store4(p.lvl[0] + (rbase + row) * W2, cg + 4 * s, n_end, vec0, val);
                 }
             }
@@ -91,7 +91,7 @@ __device__ __forceinline__ void epilogue_tile(const EpilogueArgs& p, uint32_t ta
             __syncwarp();   // level-0 reads of the shared staging area are done; reuse it for level 1
 #pragma unroll
             for (int s = 0; s < 4; ++s)
-                stage1[lane * 4 + (s ^ ((lane >> 1) & 3))] = make_float4(l1[4 * s], l1[4 * s + 1], l1[4 * s + 2], l1[4 * s + 3]);
+                sts_v4_f32(stage1 + 16u * (lane * 4 + (s ^ ((lane >> 1) & 3))), make_float4(l1[4 * s], l1[4 * s + 1], l1[4 * s + 2], l1[4 * s + 3]));
             __syncwarp();
         }
         if (p.num_levels > 1) {
@@ -102,7 +102,7 @@ __device__ __forceinline__ void epilogue_tile(const EpilogueArgs& p, uint32_t ta
                 const int rr = it * 8 + (lane >> 2);
                 const int row = row0 + rr;
                 if (row < W1) {
-                    const float4 val = stage1[rr * 4 + (s ^ ((rr >> 1) & 3))];
+                    const float4 val = lds_v4_f32(stage1 + 16u * (rr * 4 + (s ^ ((rr >> 1) & 3))));
                     store4(p.lvl[1] + (rbase + row) * W2_1, (cg >> 1) + 4 * s, lim, vec1, val);
                 }
             }

@@ -73,6 +73,29 @@ __device__ __forceinline__ float div_by_const(float x, float c, float rc) {
     return __fmaf_rn(r, rc, q0);
 }
 
+// Explicit shared-space accesses by 32-bit shared address.  Pointers into dynamically carved shared memory
+// lose their address space in the compiler's eyes and turn into generic LD/ST (slower, and tracked on the
+// long scoreboard); these keep them LDS/STS.  volatile: they stay ordered with the mbarrier waits around them.
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_v4_f32(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_v4_f32(uint32_t a, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_v4_u32(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory");
+}
+
 // Streaming (read-once / write-once) global accesses: keep them out of L1.
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
     float4 r;

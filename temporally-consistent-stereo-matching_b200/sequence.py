@@ -106,9 +106,9 @@ def hot_path_frame(fmap1, fmap2, coords_seq, state=None, disp_init=None, rel_T=N
             "corr_fn": corr_fn}
 
 
-def launches_per_frame(iters, first_frame, hidden_levels=3, mode="pyramid", num_levels=4):
+def launches_per_frame(iters, first_frame, hidden_levels=3, mode="pyramid", num_levels=4, fused_build=True):
     """Number of libtcs_b200 kernel launches hot_path_frame issues (memset nodes not counted)."""
-    n = 2 + 1 if mode == "pyramid" else 2 + (num_levels - 1)      # prepass x2 + build | prepass x2 + pools
+    n = (1 if fused_build else 3) if mode == "pyramid" else 2 + (num_levels - 1)   # fused build | prepass x2 + build | prepass x2 + pools
     if first_frame:
         n += 1 if mode == "pyramid" else 2                         # argmax (+ an on-demand level-0 build)
         if mode != "pyramid":

@@ -92,7 +92,7 @@ def test_build_full_size(tcs, B, H, W, precision, rtol, atol):
         assert_exact(lv[l], pooled[l], what="%s level %d is not the exact pool of level %d" % (precision, l, l - 1))
 
 
-@pytest.mark.parametrize("B,H,W1,W2", [(1, 136, 240, 240), (2, 120, 160, 160), (1, 9, 200, 72), (1, 5, 300, 240), (3, 2, 17, 40)])
+@pytest.mark.parametrize("B,H,W1,W2", [(1, 136, 240, 240), (2, 120, 160, 160), (1, 9, 200, 72), (1, 5, 256, 240), (3, 2, 20, 40), (1, 150, 128, 100)])
 @pytest.mark.parametrize("precision", ["fp16x3", "bf16x3", "fp16", "bf16"])
 def test_build_fused_matches_two_step(tcs, B, H, W1, W2, precision):
     """The single fused kernel (normalise + split + UMMA + pyramid) against the pre-pass + build pair: same
