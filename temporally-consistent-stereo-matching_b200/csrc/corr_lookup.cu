@@ -44,7 +44,7 @@ __device__ __forceinline__ float sample_pos_fast(float xk, float wm1, float rc, 
 // thread's own column of a transposed shared-memory tile (conflict-free, private, so no barrier) and the
 // 2 x 9 taps are interpolated from there.  Lanes are consecutive pixels: every store is a full 128-byte
 // line of one tap plane.
-constexpr int kLookThreads = 256;
+constexpr int kLookThreads = 128;
 constexpr int kLookQuads = 7;
 
 // One tap, branch-free: position -> (x0, weights); taps that fall outside the level get weight 0 on both
@@ -68,54 +68,64 @@ __device__ __forceinline__ TapPos tap_position(float xk, float wm1, float rc, fl
     return t;
 }
 
-__global__ void __launch_bounds__(kLookThreads)
-corr_lookup_r4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
-                      float* __restrict__ out, int HW, int W2, int num_levels) {
-    __shared__ float win[4 * kLookQuads][kLookThreads];
-    const int tid = threadIdx.x;
-    const int lb = 2 * blockIdx.y;                              // the level that is read
-    const bool upper = lb + 1 < num_levels;                     // whether level lb + 1 is produced as well
-    const int b = blockIdx.z;
-    const int hw = blockIdx.x * kLookThreads + tid;
-    if (hw >= HW) return;
-    const int Wb = W2 >> lb, Wu = Wb >> 1;
-    const float* __restrict__ base = level_ptr(lv, lb);
-    const long long p = (long long)b * HW + hw;
-    const long long row_start = p * Wb;
-    const long long readable = (((long long)gridDim.z * HW * Wb + 3) >> 2) << 2;   // caller pads each level to 16 B
+#ifndef LOOKUP_LD
+#define LOOKUP_LD ldg_stream_f4
+#endif
+// The span of one (pixel, level pair): where it starts in the row and its 16-byte quads.
+struct Span {
+    float4 q[kLookQuads];
+    int win_first;     // in-row index (level 2g) of q[0].x
+    float cb;          // coords / 2^(2g)
+};
 
-    const float cb = __ldg(coords + b * coords_bstride + hw) * (1.0f / (float)(1 << lb));   // coords / 2**lb (exact)
-    const float cu = cb * 0.5f;
+// Issue the loads of a span (no use of the data: the caller overlaps them with other work).
+__device__ __forceinline__ void span_load(Span& sp, const float* __restrict__ base, long long p, long long npix, float c0,
+                                          int lb, int Wb, bool upper) {
+    const int Wu = Wb >> 1;
+    const long long row_start = p * Wb;
+    const long long readable = ((npix * Wb + 3) >> 2) << 2;     // caller pads each level to 16 B
+    sp.cb = c0 * (1.0f / (float)(1 << lb));                     // coords / 2**lb (exact)
     int span_first, span_last;                                  // in-row indices of level lb that may be needed
     if (upper) {
-        const int fu = (int)fminf(fmaxf(floorf(cu), -16.0f), (float)(Wu + 16));
+        const int fu = (int)fminf(fmaxf(floorf(sp.cb * 0.5f), -16.0f), (float)(Wu + 16));
         span_first = 2 * (fu - 5);
         span_last = 2 * (fu + 6) + 1;
     } else {
-        const int fb = (int)fminf(fmaxf(floorf(cb), -16.0f), (float)(Wb + 16));
+        const int fb = (int)fminf(fmaxf(floorf(sp.cb), -16.0f), (float)(Wb + 16));
         span_first = fb - 5;
         span_last = fb + 6;
     }
     const long long a_abs = ((row_start + span_first) >> 2) << 2;   // floor to a multiple of 4 floats (16 B)
-    const int win_first = (int)(a_abs - row_start);                  // in-row index of win[0]
+    sp.win_first = (int)(a_abs - row_start);
     const int need_lo = max(span_first, 0), need_hi = min(span_last, Wb - 1);
 #pragma unroll
     for (int k = 0; k < kLookQuads; ++k) {
-        const int q_lo = win_first + 4 * k;                     // in-row index of this quad's first float
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int q_lo = sp.win_first + 4 * k;                  // in-row index of this quad's first float
         const long long idx = a_abs + 4 * k;
+        sp.q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q_lo + 3 >= need_lo && q_lo <= need_hi && idx >= 0 && idx + 3 < readable)
-            v = ldg_stream_f4(reinterpret_cast<const float4*>(base + idx));
-        win[4 * k + 0][tid] = v.x;
-        win[4 * k + 1][tid] = v.y;
-        win[4 * k + 2][tid] = v.z;
-        win[4 * k + 3][tid] = v.w;
+            sp.q[k] = LOOKUP_LD(reinterpret_cast<const float4*>(base + idx));
+    }
+}
+
+// Park the span in the thread's own shared-memory column and interpolate the 9 (+9) taps from there.
+__device__ __forceinline__ void span_taps(const Span& sp, float (*win)[kLookThreads], int tid, float* __restrict__ out,
+                                          long long out_px, int HW, int num_levels, int b, int lb, int Wb, bool upper) {
+    const int Wu = Wb >> 1;
+#pragma unroll
+    for (int k = 0; k < kLookQuads; ++k) {
+        win[4 * k + 0][tid] = sp.q[k].x;
+        win[4 * k + 1][tid] = sp.q[k].y;
+        win[4 * k + 2][tid] = sp.q[k].z;
+        win[4 * k + 3][tid] = sp.q[k].w;
     }
     constexpr int kWin = 4 * kLookQuads;
     const float* col = &win[0][tid];                            // entry i of this thread's span: col[i * kLookThreads]
+    const int win_first = sp.win_first;
+    const float cb = sp.cb, cu = sp.cb * 0.5f;
     {   // ---- level lb: taps straight from the span
         const float wm1 = (float)(Wb - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
-        float* o = out + (((long long)b * num_levels + lb) * 9) * HW + hw;
+        float* o = out + (((long long)b * num_levels + lb) * 9) * HW + out_px;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const TapPos tp = tap_position(__fadd_rn((float)(t - 4), cb), wm1, rc, hwm1, Wb);   // corr.py:43
@@ -131,7 +141,7 @@ corr_lookup_r4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long
     }
     if (upper) {   // ---- level lb + 1: entries re-pooled from pairs of the span
         const float wm1 = (float)(Wu - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
-        float* o = out + (((long long)b * num_levels + lb + 1) * 9) * HW + hw;
+        float* o = out + (((long long)b * num_levels + lb + 1) * 9) * HW + out_px;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const TapPos tp = tap_position(__fadd_rn((float)(t - 4), cu), wm1, rc, hwm1, Wu);
@@ -144,6 +154,27 @@ corr_lookup_r4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long
             o += HW;
         }
     }
+}
+
+// One thread per pixel, both level pairs: the loads of pair 1 (levels 2,3) are issued before the taps of pair 0
+// (levels 0,1) are evaluated, so their latency hides behind ~600 instructions of interpolation.
+__global__ void __launch_bounds__(kLookThreads)
+corr_lookup_r4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
+                      float* __restrict__ out, int HW, int W2, int num_levels) {
+    __shared__ float win[4 * kLookQuads][kLookThreads];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z;
+    const int hw = blockIdx.x * kLookThreads + tid;
+    if (hw >= HW) return;
+    const long long npix = (long long)gridDim.z * HW;
+    const long long p = (long long)b * HW + hw;
+    const float c0 = __ldg(coords + b * coords_bstride + hw);
+    const bool two = num_levels > 2;
+    Span s0, s1;
+    span_load(s0, lv.p[0], p, npix, c0, 0, W2, num_levels > 1);
+    if (two) span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, num_levels > 3);
+    span_taps(s0, win, tid, out, hw, HW, num_levels, b, 0, W2, num_levels > 1);
+    if (two) span_taps(s1, win, tid, out, hw, HW, num_levels, b, 2, W2 >> 2, num_levels > 3);
 }
 
 // ---- generic lookup (any radius <= 8): one thread per (pixel, level), scalar loads ---------------------
@@ -406,10 +437,10 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (radius == 4) {
         TCS_REQUIRE(B <= 65535, TCS_E_SHAPE, "tcs_corr_lookup: B must be <= 65535");
-        dim3 grid((unsigned)ceil_div(H * W1, kLookThreads), (num_levels + 1) / 2, B);
+        dim3 grid((unsigned)ceil_div(H * W1, kLookThreads), 1, B);
         static bool attr_done = false;
-        if (!attr_done) {   // leave most of the unified array to L1: the loads stream through it (31 vs 68 us)
-            const int carve = carveout_percent("TCS_CARVE_LOOKUP", 40);
+        if (!attr_done) {   // leave most of the unified array to L1: the loads stream through it (27 vs 68 us)
+            const int carve = carveout_percent("TCS_CARVE_LOOKUP", 25);
             if (carve >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_r4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             attr_done = true;
         }
