@@ -51,7 +51,7 @@ constexpr int kConvWarps = 10;
 constexpr int kConvThreads = kConvWarps * 32;       // 320
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 32 * (2 + kConvWarps + kEpiWarps);   // 512
-constexpr int kEpiStageBytes = 4096 + 2048;         // per epilogue warp: level-0 box [32][32] fp32 + level-1 box [32][16]
+constexpr int kEpiStageBytes = 4096;                // per epilogue warp: [32][32] fp32 (the TMA-store variant needs 6144)
 constexpr int kInvBytes = (kMaxW1 + 256) * 4;       // 1/norm of the A pixels, then of the B pixels
 constexpr int kBarrierBytes = 256;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kSlots * kSlotBytes + kEpiWarps * kEpiStageBytes + kInvBytes + kBarrierBytes;
@@ -493,7 +493,7 @@ extern "C" int tcs_corr_build_fused(const float* fmap1, const float* fmap2,
     // TMA stores need 16-byte row strides on both levels; otherwise the epilogue falls back to ordinary stores
     // (measured 373 us vs 354 us for the ordinary stores at 540p x 8: each warp has a single staging box, so the
     // bulk store serialises with the next chunk; opt in with TCS_FUSED_TMA_STORE=1)
-    { const char* e = getenv("TCS_FUSED_TMA_STORE"); p.tma_store = (W2 % 8 == 0) && e != nullptr && atoi(e) != 0; }
+    { const char* e = getenv("TCS_FUSED_TMA_STORE"); p.tma_store = (kEpiStageBytes >= 6144) && (W2 % 8 == 0) && e != nullptr && atoi(e) != 0; }
     CUtensorMap tml0 = tma, tml1 = tma;
     if (p.tma_store) {
         if ((rc = make_level_map(&tml0, lv[0], B * H, W1, W2, 32, CU_TENSOR_MAP_SWIZZLE_128B)) != 0) return rc;
