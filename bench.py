@@ -371,7 +371,7 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": frames / tt.item(), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "note": "pinned host fmaps -> H2D (copy stream, double-buffered) -> hot_path_frame (eager public API) -> D2H of lookup+init"}
+               "note": "pinned host fmaps -> H2D (two copy streams, triple-buffered staging) -> hot_path_frame (eager public API) -> D2H of lookup + init; PCIe-bound"}
 
     # ---- rooflines
     npix = B * H * W

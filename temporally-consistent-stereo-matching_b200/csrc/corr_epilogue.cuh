@@ -16,7 +16,8 @@ struct EpilogueArgs {
 
 __device__ __forceinline__ void store4(float* __restrict__ row, int col, int limit, bool vec_ok, const float4& v) {
     if (vec_ok && col + 3 < limit) {
-        *reinterpret_cast<float4*>(row + col) = v;
+        // write-once data: cache-streaming so the levels do not push the (re-read) feature maps out of L2
+        asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(row + col), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
     } else {
         if (col < limit) row[col] = v.x;
         if (col + 1 < limit) row[col + 1] = v.y;

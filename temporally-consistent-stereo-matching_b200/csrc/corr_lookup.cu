@@ -332,9 +332,11 @@ corr_lookup_alt_kernel(const float* __restrict__ a, const LevelPtrs bl, const fl
 // ---- argmax_disp ---------------------------------------------------------------------------------------
 // One warp per (b,h,w1) row of level 0.  Pass 1: max over the masked row (w2 > w1 -> 0), first index on
 // ties (torch.max semantics).  Pass 2: max with w2 in {idx-1, idx, idx+1} zeroed.  Values stay in
-// registers between the passes (W2 <= 1024).
+// registers between the passes (W2 <= 1024); the per-lane count is a template parameter so that a 240-wide row
+// costs 8 loads and 8 registers, not 32 predicated ones.
 constexpr int kArgMaxPerLane = 32;
 
+template <int kPer>
 __global__ void __launch_bounds__(256)
 corr_argmax_kernel(const float* __restrict__ lvl0, float* __restrict__ sparse_disp, float* __restrict__ main_cost,
                    float* __restrict__ mask_out, int W1, int W2, float thres, long long nrows) {
@@ -343,11 +345,11 @@ corr_argmax_kernel(const float* __restrict__ lvl0, float* __restrict__ sparse_di
     if (row >= nrows) return;
     const int w1 = (int)(row % W1);
     const float* __restrict__ r = lvl0 + row * W2;
-    float vals[kArgMaxPerLane];
+    float vals[kPer];
     float best = -INFINITY;
     int best_i = 0x7fffffff;
 #pragma unroll
-    for (int k = 0; k < kArgMaxPerLane; ++k) {
+    for (int k = 0; k < kPer; ++k) {
         const int w2 = lane + 32 * k;
         float v = -INFINITY;
         if (w2 < W2) {
@@ -366,7 +368,7 @@ corr_argmax_kernel(const float* __restrict__ lvl0, float* __restrict__ sparse_di
     }
     float sub = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < kArgMaxPerLane; ++k) {
+    for (int k = 0; k < kPer; ++k) {
         const int w2 = lane + 32 * k;
         if (w2 < W2) {
             float v = vals[k];
@@ -484,8 +486,11 @@ extern "C" int tcs_corr_argmax(const float* lvl0, float* sparse_disp, float* mai
     TCS_REQUIRE(B > 0 && H > 0 && W1 > 0 && W2 > 0, TCS_E_BADARG, "tcs_corr_argmax: non-positive size");
     TCS_REQUIRE(W2 <= 32 * kArgMaxPerLane, TCS_E_SHAPE, "tcs_corr_argmax: W2=%d exceeds %d", W2, 32 * kArgMaxPerLane);
     const long long nrows = (long long)B * H * W1;
-    corr_argmax_kernel<<<(unsigned)ceil_div_ll(nrows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        lvl0, sparse_disp, main_cost, mask, W1, W2, thres, nrows);
+    const unsigned grid = (unsigned)ceil_div_ll(nrows, 8);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (W2 <= 256) corr_argmax_kernel<8><<<grid, 256, 0, s>>>(lvl0, sparse_disp, main_cost, mask, W1, W2, thres, nrows);
+    else if (W2 <= 512) corr_argmax_kernel<16><<<grid, 256, 0, s>>>(lvl0, sparse_disp, main_cost, mask, W1, W2, thres, nrows);
+    else corr_argmax_kernel<32><<<grid, 256, 0, s>>>(lvl0, sparse_disp, main_cost, mask, W1, W2, thres, nrows);
     TCS_CHECK_LAUNCH("tcs_corr_argmax");
     return 0;
 }
