@@ -247,7 +247,7 @@ def run_b200(args):
     def phase_warp(s):
         o = slots[1 - s]
         d, _, m, c = tcs_b200.warp_with_cost(o["last_disp"], o["f1"], cam["rel_T"], cam["K"], cam["K_inv"], cam["baseline"],
-                                             cur_fmap=slots[s]["f1"], per_sample_mean=True)
+                                             cur_fmap=slots[s]["f1"], per_sample_mean=True, want_fmap=False)
         grid = tcs_b200.get_backward_grid(d, cam["rel_T_inv"], cam["K"], cam["K_inv"], cam["baseline"])
         live[s]["init"] = (d, c, m)
         live[s]["nets"] = tcs_b200.warp_hidden_states(o["nets"], grid)
@@ -387,7 +387,7 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": lookup_bytes}
     build_flops = 2.0 * npix * W * C
     build_bytes = 2 * npix * C * 4 + npix * W * 4 * (1 + 0.5 + 0.25 + 0.125)
-    warp_bytes = npix * (4 + 1024 + 1024 + 4 + 1024 + 4 + 4 + 1344)
+    warp_bytes = npix * (4 + 1024 + 1024 + 4 + 4 + 4 + 1344)   # disp + prev fmap + cur fmap in; disp', mask, cost out; hidden gather
     phases_out = {
         "build_ms": phase_ms[0], "warp_ms": phase_ms[1], "lookups_ms": phase_ms[2],
         "build": {"note": ("fused normalise + split + tcgen05 build" if fused_build else "2 pre-passes + tcgen05 build") + ", fp32 fmaps in, fp32 levels out", "algorithmic_bytes": build_bytes,

@@ -139,7 +139,9 @@ long long tcs_warp_scratch_bytes(int B, int C, int H, int W);
  *   fmap      [B,C,H,W]  previous left features
  *   rel_T     [B,4,4]    previous->current camera transform;  K, K_inv [B,3,3];  baseline [B]
  *   cur_fmap  [B,C,H,W]  current left features (nullable: then cost is not computed)
- *   out_disp  [B,1,H,W], out_fmap [B,C,H,W], out_mask [B,1,H,W], out_cost [B,1,H,W] (nullable)
+ *   out_disp  [B,1,H,W], out_fmap [B,C,H,W] (nullable: the model reads only the cost of the warped features,
+ *             core/tc_stereo.py:139, so a caller that wants just the cost saves the 1 KB/pixel store),
+ *             out_mask [B,1,H,W], out_cost [B,1,H,W] (nullable)
  *   out_cost = sum_c normalize(cur_fmap)*normalize(out_fmap) * out_mask   (ref: core/tc_stereo.py:139-140)
  *   per_sample_mean != 0 uses each sample's own mean disparity for the soft-splat metric instead of
  *   the reference's batch-global mean (geo_utils.py:193) — for batching independent sequences.

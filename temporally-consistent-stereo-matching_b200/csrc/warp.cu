@@ -281,7 +281,7 @@ warp_finalize_kernel(const float* __restrict__ accum, const float* __restrict__ 
     for (int k = 0; k < kPerWarp; ++k) {
         const int c = warp + 8 * k;
         const float v = tile[c * 33 + lane];
-        if (in_w) stg_stream_f1(out_fmap + base + (size_t)c * plane, v);
+        if (in_w && out_fmap != nullptr) stg_stream_f1(out_fmap + base + (size_t)c * plane, v);
         dot = fmaf(f[k], v, dot);
         s1 = fmaf(f[k], f[k], s1);
         sw = fmaf(v, v, sw);
@@ -443,8 +443,9 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
                                 float* out_disp, float* out_fmap, float* out_mask, float* out_cost,
                                 void* scratch, int B, int C, int H, int W, int per_sample_mean, void* stream) {
     using namespace tcs;
-    TCS_REQUIRE(disp && fmap && rel_T && K && K_inv && baseline && out_disp && out_fmap && out_mask && scratch,
+    TCS_REQUIRE(disp && fmap && rel_T && K && K_inv && baseline && out_disp && out_mask && scratch,
                 TCS_E_BADARG, "tcs_warp_forward: null pointer");
+    TCS_REQUIRE(out_fmap != nullptr || out_cost != nullptr, TCS_E_BADARG, "tcs_warp_forward: neither out_fmap nor out_cost requested");
     TCS_REQUIRE(out_cost == nullptr || cur_fmap != nullptr, TCS_E_BADARG, "tcs_warp_forward: out_cost needs cur_fmap");
     TCS_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, TCS_E_BADARG, "tcs_warp_forward: non-positive size");
     TCS_REQUIRE(C == 128 || C == 256 || C == 384 || C == 512, TCS_E_SHAPE, "tcs_warp_forward: C=%d must be 128, 256, 384 or 512", C);

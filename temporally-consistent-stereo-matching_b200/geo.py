@@ -50,10 +50,11 @@ def _camera_args(relative_T, K, K_inv, baseline, B):
     return relative_T, K, K_inv, baseline
 
 
-def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, per_sample_mean=False):
+def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, per_sample_mean=False, want_fmap=True):
     """warp() plus the matching cost of core/tc_stereo.py:139-140 fused into the normalise kernel.
 
-    -> (disp', fmap', mask, cost)  with cost None when cur_fmap is None."""
+    -> (disp', fmap', mask, cost)  with cost None when cur_fmap is None.  want_fmap=False skips materialising
+    fmap' (TCStereo.forward only ever reads its cost, tc_stereo.py:139-140) and returns None in its place."""
     disp = _f32c("disp", disp)
     fmap = _f32c("fmap", fmap)
     if disp.dim() != 4 or disp.shape[1] != 1:
@@ -67,14 +68,16 @@ def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, pe
         cur_fmap = _f32c("cur_fmap", cur_fmap, fmap.shape)
     dev = disp.device
     out_disp = torch.empty_like(disp)
-    out_fmap = torch.empty_like(fmap)
+    if not want_fmap and cur_fmap is None:
+        raise ValueError("want_fmap=False needs cur_fmap (otherwise nothing of the warped features is returned)")
+    out_fmap = torch.empty_like(fmap) if want_fmap else None
     out_mask = torch.empty_like(disp)
     out_cost = torch.empty_like(disp) if cur_fmap is not None else None
     with torch.cuda.device(dev):
         scratch = _warp_scratch(B, C, H, W, dev)
         _lib.call("tcs_warp_forward", disp.data_ptr(), fmap.data_ptr(), relative_T.data_ptr(), K.data_ptr(),
                   K_inv.data_ptr(), baseline.data_ptr(), cur_fmap.data_ptr() if cur_fmap is not None else None,
-                  out_disp.data_ptr(), out_fmap.data_ptr(), out_mask.data_ptr(),
+                  out_disp.data_ptr(), out_fmap.data_ptr() if out_fmap is not None else None, out_mask.data_ptr(),
                   out_cost.data_ptr() if out_cost is not None else None, scratch.data_ptr(),
                   B, C, H, W, 1 if per_sample_mean else 0, _stream())
     return out_disp, out_fmap, out_mask, out_cost

@@ -256,6 +256,9 @@ def test_warp_golden(tcs):
     assert_close(host(c), g["cost"], rtol=1e-5, atol=2e-6, what="matching cost vs reference")
     d2, f2, m2 = tcs.warp(*args)
     assert torch.equal(m2, m)
+    d3, f3, m3, c3 = tcs.warp_with_cost(*args, cur_fmap=cuda(g["cur_fmap"]), want_fmap=False)   # cost without materialising fmap'
+    assert f3 is None and torch.equal(m3, m)
+    assert_close(host(c3), g["cost"], rtol=1e-5, atol=2e-6, what="matching cost (no fmap output) vs reference")
 
 
 def camera(B, H, W, seed):
