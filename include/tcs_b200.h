@@ -40,6 +40,9 @@ extern "C" {
 #define TCS_PREC_FP16    2    /* one fp16 pass on 2^8-scaled unit vectors                     */
 #define TCS_PREC_FP16X3  3    /* fp16 hi/lo split                                             */
 
+#define TCS_WARP_PER_SAMPLE_MEAN 1
+#define TCS_WARP_DETERMINISTIC   2
+
 #define TCS_MAX_LEVELS   4
 #define TCS_MAX_RADIUS   8
 
@@ -143,13 +146,15 @@ long long tcs_warp_scratch_bytes(int B, int C, int H, int W);
  *             core/tc_stereo.py:139, so a caller that wants just the cost saves the 1 KB/pixel store),
  *             out_mask [B,1,H,W], out_cost [B,1,H,W] (nullable)
  *   out_cost = sum_c normalize(cur_fmap)*normalize(out_fmap) * out_mask   (ref: core/tc_stereo.py:139-140)
- *   per_sample_mean != 0 uses each sample's own mean disparity for the soft-splat metric instead of
- *   the reference's batch-global mean (geo_utils.py:193) — for batching independent sequences.
+ *   flags     TCS_WARP_PER_SAMPLE_MEAN: each sample's own mean disparity for the soft-splat metric instead of the
+ *             reference's batch-global mean (geo_utils.py:193) — for batching independent sequences.
+ *             TCS_WARP_DETERMINISTIC: collect the splat from the target's side (fixed summation order, no global
+ *             accumulator); falls back to the atomic scatter on the device when the flow is too large or irregular.
  *   scratch   tcs_warp_scratch_bytes() bytes, 16-byte aligned. */
 int tcs_warp_forward(const float* disp, const float* fmap, const float* rel_T, const float* K,
                      const float* K_inv, const float* baseline, const float* cur_fmap,
                      float* out_disp, float* out_fmap, float* out_mask, float* out_cost,
-                     void* scratch, int B, int C, int H, int W, int per_sample_mean, void* stream);
+                     void* scratch, int B, int C, int H, int W, int flags, void* stream);
 
 /* ref: core/utils/geo_utils.py:201-236 (get_backward_grid).  disp [B,1,H,W] -> grid [B,2,H,W] (x,y). */
 int tcs_backward_grid(const float* disp, const float* rel_T, const float* K, const float* K_inv,

@@ -50,11 +50,13 @@ def _camera_args(relative_T, K, K_inv, baseline, B):
     return relative_T, K, K_inv, baseline
 
 
-def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, per_sample_mean=False, want_fmap=True):
+def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, per_sample_mean=False, want_fmap=True,
+                   deterministic=False):
     """warp() plus the matching cost of core/tc_stereo.py:139-140 fused into the normalise kernel.
 
     -> (disp', fmap', mask, cost)  with cost None when cur_fmap is None.  want_fmap=False skips materialising
-    fmap' (TCStereo.forward only ever reads its cost, tc_stereo.py:139-140) and returns None in its place."""
+    fmap' (TCStereo.forward only ever reads its cost, tc_stereo.py:139-140) and returns None in its place.
+    deterministic=True collects the splat from the target's side in a fixed order (bitwise repeatable, slower)."""
     disp = _f32c("disp", disp)
     fmap = _f32c("fmap", fmap)
     if disp.dim() != 4 or disp.shape[1] != 1:
@@ -79,7 +81,7 @@ def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, pe
                   K_inv.data_ptr(), baseline.data_ptr(), cur_fmap.data_ptr() if cur_fmap is not None else None,
                   out_disp.data_ptr(), out_fmap.data_ptr() if out_fmap is not None else None, out_mask.data_ptr(),
                   out_cost.data_ptr() if out_cost is not None else None, scratch.data_ptr(),
-                  B, C, H, W, 1 if per_sample_mean else 0, _stream())
+                  B, C, H, W, (1 if per_sample_mean else 0) | (2 if deterministic else 0), _stream())
     return out_disp, out_fmap, out_mask, out_cost
 
 

@@ -277,8 +277,9 @@ def camera(B, H, W, seed):
     return f32(K), f32(np.linalg.inv(K)), f32(T), f32(np.linalg.inv(T)), f32(np.full((B, 1), 0.25))
 
 
+@pytest.mark.parametrize("deterministic", [False, True])
 @pytest.mark.parametrize("B,H,W,per_sample", [(1, 120, 160, False), (2, 136, 240, False), (2, 30, 75, True)])
-def test_warp_full_size(tcs, B, H, W, per_sample):
+def test_warp_full_size(tcs, B, H, W, per_sample, deterministic):
     K, Kinv, T, Tinv, base = camera(B, H, W, 3)
     g = torch.Generator().manual_seed(17)
     disp = 0.5 + torch.rand(B, 1, H, W, generator=g) * (W / 16)
@@ -286,7 +287,7 @@ def test_warp_full_size(tcs, B, H, W, per_sample):
     fmap = torch.randn(B, 256, H, W, generator=g)
     cur = torch.randn(B, 256, H, W, generator=g)
     d, f, m, c = tcs.warp_with_cost(disp.cuda(), fmap.cuda(), cuda(T), cuda(K), cuda(Kinv), cuda(base),
-                                    cur_fmap=cur.cuda(), per_sample_mean=per_sample)
+                                    cur_fmap=cur.cuda(), per_sample_mean=per_sample, deterministic=deterministic)
     rd, rf, rm = orc.warp(disp.numpy(), fmap.numpy(), T, K, Kinv, base, per_sample_mean=per_sample)
     assert_exact(host(m), rm, what="splat mask")
     assert 0.5 < rm.mean() < 1.0
@@ -294,6 +295,47 @@ def test_warp_full_size(tcs, B, H, W, per_sample):
     assert_close(host(f), rf, rtol=1e-4, atol=1e-4, what="warped features")
     rc = orc.matching_cost(cur.numpy(), host(f), host(m))
     assert_close(host(c), rc, rtol=1e-5, atol=2e-6, what="matching cost")
+
+
+@pytest.mark.parametrize("kind", ["large_flow", "irregular_flow"])
+def test_warp_scatter_fallback(tcs, kind):
+    """Deterministic mode: frames the gather kernel cannot take (flow beyond its search radius, or too many distinct source offsets
+    per target segment) fall back to the scatter kernels on the device; the result must be the same splat."""
+    B, H, W = 1, 40, 96
+    K, Kinv, T, _, base = camera(B, H, W, 5)
+    g = torch.Generator().manual_seed(23)
+    if kind == "large_flow":
+        yaw = np.deg2rad(25.0)                       # ~ 0.5 * W * tan(25 deg) = 22 px of flow and more
+        c, s_ = np.cos(yaw), np.sin(yaw)
+        T[0] = np.linalg.inv(np.array([[c, 0, s_, 0.0], [0, 1, 0, 0], [-s_, 0, c, 0.3], [0, 0, 0, 1.0]])).astype(np.float32)
+        disp = 1.0 + torch.rand(B, 1, H, W, generator=g) * 3
+    else:
+        T[0] = np.linalg.inv(np.array([[1, 0, 0, 0.0], [0, 1, 0, 0], [0, 0, 1, 2.5], [0, 0, 0, 1.0]])).astype(np.float32)
+        disp = 0.5 + torch.rand(B, 1, H, W, generator=g) * 6     # i.i.d. depths + a big forward step: flow jumps pixel to pixel
+    fmap = torch.randn(B, 128, H, W, generator=g)
+    cur = torch.randn(B, 128, H, W, generator=g)
+    d, f, m, c = tcs.warp_with_cost(disp.cuda(), fmap.cuda(), cuda(T), cuda(K), cuda(Kinv), cuda(base), cur_fmap=cur.cuda(),
+                                    deterministic=True)
+    rd, rf, rm = orc.warp(disp.numpy(), fmap.numpy(), T, K, Kinv, base)
+    assert_exact(host(m), rm, what="splat mask (%s)" % kind)
+    assert 0.05 < rm.mean() < 1.0
+    assert_close(host(d), rd, rtol=1e-4, atol=1e-4, what="warped disparity (%s)" % kind)
+    assert_close(host(f), rf, rtol=1e-4, atol=1e-4, what="warped features (%s)" % kind)
+
+
+def test_warp_is_deterministic(tcs):
+    """The gather formulation adds a target's contributions in a fixed order: bitwise repeatable (the reference's
+    atomic scatter is not)."""
+    g = load_golden("warp_small")
+    args = [cuda(g[k]) for k in ("disp", "fmap", "rel_T", "K", "K_inv", "baseline")]
+    a = tcs.warp_with_cost(*args, cur_fmap=cuda(g["cur_fmap"]), deterministic=True)
+    b = tcs.warp_with_cost(*args, cur_fmap=cuda(g["cur_fmap"]), deterministic=True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert_exact(host(a[2]), g["warped_mask"], what="gather splat mask vs reference")
+    assert_close(host(a[0]), g["warped_disp"], rtol=1e-5, atol=1e-5, what="gather warped disparity vs reference")
+    assert_close(host(a[1]), g["warped_fmap"], rtol=1e-5, atol=1e-5, what="gather warped features vs reference")
+    assert_close(host(a[3]), g["cost"], rtol=1e-5, atol=2e-6, what="gather matching cost vs reference")
 
 
 def test_warp_identity_pose_keeps_everything(tcs):
