@@ -104,6 +104,16 @@ int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float* lvl2, con
                     const float* coords, long long coords_bstride, float* out,
                     int B, int H, int W1, int W2, int num_levels, int radius, void* stream);
 
+/* Lookup fused with the motion encoder's first layer: out = [relu](W . taps + bias), the 36 taps never leave
+ * the registers.  ref: core/update.py:97,104 (BasicMotionEncoder.convc1, a 1x1 Conv2d(36, 64), then F.relu)
+ * applied to core/corr.py:33-52.  (the first "next" row after the path itself.)
+ *   weight [Cout, 36] fp32 (the conv weight viewed 2-D), bias [Cout] (nullable), out [B, Cout, H, W1] fp32.
+ * Requires num_levels == 4, radius == 4, Cout % 4 == 0, Cout <= 128. */
+int tcs_corr_lookup_encode(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                           const float* coords, long long coords_bstride, const float* weight, const float* bias,
+                           float* out, int B, int H, int W1, int W2, int num_levels, int radius, int Cout, int relu,
+                           void* stream);
+
 /* ---- (3) alternate (on-the-fly) lookup ---------------------------------------------------------- */
 
 /* Average-pool the fp32 normalised right features along W (channels last): out[b,h,j,:] =

@@ -103,6 +103,19 @@ def corr_lookup(levels, coords, radius=4):
     return np.ascontiguousarray(out.transpose(0, 3, 1, 2))
 
 
+def corr_lookup_encoded(levels, coords, weight, bias=None, relu=True, radius=4):
+    """relu(conv1x1(lookup)): the first layer of the motion encoder on the lookup result.
+    ref: core/update.py:97,104 (BasicMotionEncoder.convc1 = Conv2d(36, 64, 1); cor = F.relu(convc1(corr)))."""
+    taps = corr_lookup(levels, coords, radius).astype(np.float64)          # [B,36,H,W]
+    w = np.asarray(weight, np.float64).reshape(weight.shape[0], -1)
+    out = np.einsum("ok,bkhw->bohw", w, taps)
+    if bias is not None:
+        out = out + np.asarray(bias, np.float64)[None, :, None, None]
+    if relu:
+        out = np.maximum(out, 0.0)
+    return out.astype(F32)
+
+
 def corr_lookup_alternate(fmap1, fmap2, coords, num_levels=4, radius=4):
     """The on-the-fly path's contract: same result as corr_lookup without a volume, using
     pool(volume) == <n1, pool(n2)> (pooling happens after normalisation).  Not in the reference."""

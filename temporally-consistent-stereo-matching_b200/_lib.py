@@ -30,6 +30,7 @@ SIGNATURES = {
     "tcs_corr_build_fused": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_build_fp32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_lookup": (_i, [_p, _p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "tcs_corr_lookup_encode": (_i, [_p, _p, _p, _p, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_fmap_pool_w": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tcs_corr_lookup_alt": (_i, [_p, _p, _p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_argmax": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),

@@ -127,6 +127,35 @@ def _coords_plane(coords, B, H, W1):
     return c, c.data_ptr(), (c.stride(0) if B > 1 else H * W1)
 
 
+class LazyLookup:
+    """corr_fn(coords) not yet evaluated.  BasicMotionEncoder's patched forward calls .encode(convc1) and never
+    materialises the 36 tap planes; every other use (torch functions, the reference's isnan asserts) goes through
+    __torch_function__ and sees the ordinary lookup result."""
+
+    def __init__(self, block, coords):
+        self.block, self.coords, self._value = block, coords, None
+
+    def materialize(self):
+        if self._value is None:
+            self._value = self.block(self.coords)
+        return self._value
+
+    def encode(self, conv, relu=True):
+        return self.block.lookup_encoded(self.coords, conv.weight, conv.bias, relu=relu)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        unwrap = lambda a: a.materialize() if isinstance(a, LazyLookup) else a
+        args = tuple(unwrap(a) for a in args)
+        kwargs = {k: unwrap(v) for k, v in (kwargs or {}).items()}
+        return func(*args, **kwargs)
+
+    @property
+    def shape(self):
+        b = self.block
+        return torch.Size((b.B, b.num_levels * (2 * b.radius + 1), b.H, b.W1))
+
+
 class CorrBlock1D:
     """ref: core/corr.py:7-79.  `mode='alternate'` never materialises the volume (subsystem 3)."""
 
@@ -214,6 +243,33 @@ class CorrBlock1D:
                 _lib.call("tcs_corr_lookup_alt", self._a32.data_ptr(), *ptrs, cptr, cstride, out.data_ptr(),
                           self.B, self.H, self.W1, self.W2, self.C, self.num_levels, self.radius, _stream())
         return out
+
+    def lookup_encoded(self, coords, weight, bias=None, relu=True):
+        """relu(conv1x1(self(coords))) in one kernel: the lookup fused with the motion encoder's first layer
+        (ref: core/update.py:97,104, BasicMotionEncoder.convc1 + F.relu).  weight [Cout, L*(2r+1)] or the conv's
+        [Cout, L*(2r+1), 1, 1]; -> [B, Cout, H, W] fp32.  Pyramid mode, 4 levels, radius 4."""
+        if self.mode != "pyramid" or self.num_levels != 4 or self.radius != 4:
+            raise NotImplementedError("lookup_encoded needs mode='pyramid', num_levels=4, radius=4")
+        c, cptr, cstride = _coords_plane(coords, self.B, self.H, self.W1)
+        w = weight.detach()
+        if w.dim() == 4:
+            w = w.reshape(w.shape[0], -1)
+        if not w.is_cuda or w.dim() != 2 or w.shape[1] != 36:
+            raise ValueError("weight must be a CUDA tensor [Cout, 36] (or [Cout, 36, 1, 1]), got %s" % (tuple(weight.shape),))
+        w = w.float().contiguous()
+        bb = bias.detach().float().contiguous() if bias is not None else None
+        cout = w.shape[0]
+        out = torch.empty((self.B, cout, self.H, self.W1), dtype=torch.float32, device=self.device)
+        ptrs = [self._levels[l].data_ptr() for l in range(4)]
+        with torch.cuda.device(self.device):
+            _lib.call("tcs_corr_lookup_encode", *ptrs, cptr, cstride, w.data_ptr(), bb.data_ptr() if bb is not None else None,
+                      out.data_ptr(), self.B, self.H, self.W1, self.W2, 4, 4, cout, 1 if relu else 0, _stream())
+        return out
+
+    def lazy(self, coords):
+        """A deferred lookup for a consumer that can fuse it (see dropin.install(..., fuse_motion_encoder=...)).
+        Anything else that touches it as a tensor gets the ordinary lookup."""
+        return LazyLookup(self, coords)
 
     def get_cost_volume(self):
         """ref: corr.py:25-31,64-65.  [B, W2, H, W1], zero where w2 > w1.  Built on first use."""

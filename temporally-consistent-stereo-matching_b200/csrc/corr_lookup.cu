@@ -108,9 +108,12 @@ __device__ __forceinline__ void span_load(Span& sp, const float* __restrict__ ba
     }
 }
 
-// Park the span in the thread's own shared-memory column and interpolate the 9 (+9) taps from there.
+// Park the span in the thread's own shared-memory column and interpolate the 9 (+9) taps from there.  kKeep: the
+// taps stay in registers (keep[0..17]) for a fused consumer instead of going to global memory.
+template <bool kKeep>
 __device__ __forceinline__ void span_taps(const Span& sp, float (*win)[kLookThreads], int tid, float* __restrict__ out,
-                                          long long out_px, int HW, int num_levels, int b, int lb, int Wb, bool upper) {
+                                          long long out_px, int HW, int num_levels, int b, int lb, int Wb, bool upper,
+                                          float* keep) {
     const int Wu = Wb >> 1;
 #pragma unroll
     for (int k = 0; k < kLookQuads; ++k) {
@@ -135,9 +138,13 @@ __device__ __forceinline__ void span_taps(const Span& sp, float (*win)[kLookThre
             // clamped slot holds a non-finite value
             const float a0 = (tp.w_lo != 0.0f) ? __fmul_rn(v0, tp.w_lo) : 0.0f;
             const float r = (tp.w_hi != 0.0f) ? fmaf(v1, tp.w_hi, a0) : a0;
-            stg_stream_f1(o, r);
+            if (kKeep) keep[t] = r; else stg_stream_f1(o, r);
             o += HW;
         }
+    }
+    if (kKeep && !upper) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) keep[9 + t] = 0.0f;
     }
     if (upper) {   // ---- level lb + 1: entries re-pooled from pairs of the span
         const float wm1 = (float)(Wu - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
@@ -150,7 +157,7 @@ __device__ __forceinline__ void span_taps(const Span& sp, float (*win)[kLookThre
             const float v1 = __fmul_rn(__fadd_rn(col[(i0 + 2) * kLookThreads], col[(i0 + 3) * kLookThreads]), 0.5f);
             const float a0 = (tp.w_lo != 0.0f) ? __fmul_rn(v0, tp.w_lo) : 0.0f;
             const float r = (tp.w_hi != 0.0f) ? fmaf(v1, tp.w_hi, a0) : a0;
-            stg_stream_f1(o, r);
+            if (kKeep) keep[9 + t] = r; else stg_stream_f1(o, r);
             o += HW;
         }
     }
@@ -173,8 +180,58 @@ corr_lookup_r4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long
     Span s0, s1;
     span_load(s0, lv.p[0], p, npix, c0, 0, W2, num_levels > 1);
     if (two) span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, num_levels > 3);
-    span_taps(s0, win, tid, out, hw, HW, num_levels, b, 0, W2, num_levels > 1);
-    if (two) span_taps(s1, win, tid, out, hw, HW, num_levels, b, 2, W2 >> 2, num_levels > 3);
+    span_taps<false>(s0, win, tid, out, hw, HW, num_levels, b, 0, W2, num_levels > 1, nullptr);
+    if (two) span_taps<false>(s1, win, tid, out, hw, HW, num_levels, b, 2, W2 >> 2, num_levels > 3, nullptr);
+}
+
+// ---- lookup fused with the motion encoder's first layer ------------------------------------------------------
+// ref: core/update.py:97,104 (BasicMotionEncoder: cor = relu(convc1(corr)), convc1 = Conv2d(36, 64, 1)) applied to
+// the result of core/corr.py:33-52.  The 36 taps never go to global memory: they stay in the thread's registers and
+// the per-pixel 36 -> Cout product runs against weights broadcast from shared memory (SURVEY.md section 8f, rank 1:
+// saves the 144 B/pixel store and its re-read every GRU iteration, and one launch).
+constexpr int kEncTaps = 36;
+constexpr int kEncMaxOut = 128;
+
+__global__ void __launch_bounds__(kLookThreads)
+corr_lookup_encode_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
+                          const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ out,
+                          int HW, int W2, int Cout, int relu) {
+    __shared__ float win[4 * kLookQuads][kLookThreads];
+    __shared__ __align__(16) float s_w[kEncMaxOut * kEncTaps];
+    __shared__ float s_b[kEncMaxOut];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < Cout * kEncTaps; i += kLookThreads) s_w[i] = __ldg(weight + i);
+    for (int i = tid; i < Cout; i += kLookThreads) s_b[i] = (bias != nullptr) ? __ldg(bias + i) : 0.0f;
+    __syncthreads();
+    const int b = blockIdx.z;
+    const int hw = blockIdx.x * kLookThreads + tid;
+    if (hw >= HW) return;
+    const long long npix = (long long)gridDim.z * HW;
+    const long long p = (long long)b * HW + hw;
+    const float c0 = __ldg(coords + b * coords_bstride + hw);
+    Span s0, s1;
+    span_load(s0, lv.p[0], p, npix, c0, 0, W2, true);
+    span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
+    float tp[kEncTaps];
+    span_taps<true>(s0, win, tid, nullptr, 0, HW, 4, b, 0, W2, true, tp);
+    span_taps<true>(s1, win, tid, nullptr, 0, HW, 4, b, 2, W2 >> 2, true, tp + 18);
+    float* o = out + (long long)b * Cout * HW + hw;
+    for (int oc = 0; oc < Cout; oc += 4) {
+        float acc[4] = {s_b[oc], s_b[oc + 1], s_b[oc + 2], s_b[oc + 3]};
+#pragma unroll
+        for (int k = 0; k < kEncTaps; k += 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 w = *reinterpret_cast<const float4*>(s_w + (oc + j) * kEncTaps + k);   // broadcast
+                acc[j] = fmaf(w.x, tp[k], acc[j]);
+                acc[j] = fmaf(w.y, tp[k + 1], acc[j]);
+                acc[j] = fmaf(w.z, tp[k + 2], acc[j]);
+                acc[j] = fmaf(w.w, tp[k + 3], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) stg_stream_f1(o + (long long)(oc + j) * HW, relu ? fmaxf(acc[j], 0.0f) : acc[j]);
+    }
 }
 
 // ---- generic lookup (any radius <= 8): one thread per (pixel, level), scalar loads ---------------------
@@ -452,6 +509,33 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
         corr_lookup_generic_kernel<<<grid, 256, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels, radius, npix);
     }
     TCS_CHECK_LAUNCH("tcs_corr_lookup");
+    return 0;
+}
+
+extern "C" int tcs_corr_lookup_encode(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                      const float* coords, long long coords_bstride, const float* weight,
+                                      const float* bias, float* out, int B, int H, int W1, int W2, int num_levels,
+                                      int radius, int Cout, int relu, void* stream) {
+    using namespace tcs;
+    const float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
+    int rc = check_lookup_args("tcs_corr_lookup_encode", lv, coords, out, B, H, W1, W2, num_levels, radius);
+    if (rc != 0) return rc;
+    TCS_REQUIRE(num_levels == 4 && radius == 4, TCS_E_SHAPE, "tcs_corr_lookup_encode: implemented for num_levels=4, radius=4 (36 taps)");
+    TCS_REQUIRE(weight != nullptr, TCS_E_BADARG, "tcs_corr_lookup_encode: null weight");
+    TCS_REQUIRE(Cout > 0 && Cout <= kEncMaxOut && Cout % 4 == 0, TCS_E_SHAPE, "tcs_corr_lookup_encode: Cout=%d must be a multiple of 4, <= %d", Cout, kEncMaxOut);
+    TCS_REQUIRE(B <= 65535, TCS_E_SHAPE, "tcs_corr_lookup_encode: B must be <= 65535");
+    LevelPtrs lp;
+    for (int l = 0; l < 4; ++l) lp.p[l] = lv[l];
+    dim3 grid((unsigned)ceil_div(H * W1, kLookThreads), 1, B);
+    static bool attr_done = false;
+    if (!attr_done) {
+        const int carve = carveout_percent("TCS_CARVE_LOOKUP_ENC", 35);
+        if (carve >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        attr_done = true;
+    }
+    corr_lookup_encode_kernel<<<grid, kLookThreads, 0, static_cast<cudaStream_t>(stream)>>>(lp, coords, coords_bstride, weight, bias, out,
+                                                                                            H * W1, W2, Cout, relu);
+    TCS_CHECK_LAUNCH("tcs_corr_lookup_encode");
     return 0;
 }
 

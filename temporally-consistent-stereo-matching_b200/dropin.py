@@ -8,17 +8,30 @@ _saved = {}
 _NAMES = ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler")
 
 
-def install(tc_stereo_module, precision=None, mode=None):
-    """tc_stereo_module: the imported `core.tc_stereo`.  Returns the dict of names that were replaced."""
+def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=None):
+    """tc_stereo_module: the imported `core.tc_stereo`.  Returns the dict of names that were replaced.
+
+    fuse_motion_encoder: the imported `core.update`.  When given, corr_fn(coords) returns a deferred lookup and
+    BasicMotionEncoder.forward (update.py:103-112) evaluates `relu(convc1(corr))` with the fused lookup + 1x1
+    kernel; fp32 only — under autocast the reference's conv runs in fp16."""
     from . import corr, geo
 
     block = corr.CorrBlock1D
-    if precision is not None or mode is not None:
+    if precision is not None or mode is not None or fuse_motion_encoder is not None:
+        lazy = fuse_motion_encoder is not None
+
         class _Configured(corr.CorrBlock1D):
             def __init__(self, fmap1, fmap2, num_levels=4, radius=4, thres=0.2):
                 super().__init__(fmap1, fmap2, num_levels, radius, thres, precision=precision, mode=mode)
+
+            def __call__(self, coords):
+                if lazy and self.mode == "pyramid" and self.num_levels == 4 and self.radius == 4:
+                    return self.lazy(coords)
+                return super().__call__(coords)
         _Configured.__name__ = "CorrBlock1D"
         block = _Configured
+    if fuse_motion_encoder is not None:
+        _patch_motion_encoder(fuse_motion_encoder)
     new = {"CorrBlock1D": block, "warp": geo.warp, "get_backward_grid": geo.get_backward_grid,
            "bilinear_sampler": geo.bilinear_sampler}
     for name in _NAMES:
@@ -29,7 +42,33 @@ def install(tc_stereo_module, precision=None, mode=None):
     return new
 
 
-def uninstall(tc_stereo_module):
+def _patch_motion_encoder(update_module):
+    import torch
+    import torch.nn.functional as F
+    from .corr import LazyLookup
+
+    enc = update_module.BasicMotionEncoder
+    _saved.setdefault((id(update_module), "BasicMotionEncoder.forward"), enc.forward)
+
+    def forward(self, flow, corr):                      # update.py:103-112 with the first layer fused
+        if isinstance(corr, LazyLookup):
+            cor = corr.encode(self.convc1)              # relu(convc1(lookup)) in one kernel
+        else:
+            cor = F.relu(self.convc1(corr))
+        cor = F.relu(self.convc2(cor))
+        flo = F.relu(self.convf1(flow))
+        flo = F.relu(self.convf2(flo))
+        out = F.relu(self.conv(torch.cat([cor, flo], dim=1)))
+        return torch.cat([out, flow], dim=1)
+
+    enc.forward = forward
+
+
+def uninstall(tc_stereo_module, update_module=None):
+    if update_module is not None:
+        old = _saved.pop((id(update_module), "BasicMotionEncoder.forward"), None)
+        if old is not None:
+            update_module.BasicMotionEncoder.forward = old
     for name in _NAMES:
         old = _saved.pop((id(tc_stereo_module), name), None)
         if old is not None:

@@ -116,6 +116,25 @@ def test_dropin_rebinds_and_restores_names():
         tcs_b200.install(types.ModuleType("empty"))
 
 
+def test_dropin_patches_motion_encoder():
+    import tcs_b200
+    tcs_mod = types.ModuleType("core.tc_stereo")
+    for n in ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler"):
+        setattr(tcs_mod, n, object())
+    upd = types.ModuleType("core.update")
+
+    class BasicMotionEncoder(torch.nn.Module):
+        def forward(self, flow, corr):
+            return "original"
+    upd.BasicMotionEncoder = BasicMotionEncoder
+    original = BasicMotionEncoder.forward
+    tcs_b200.install(tcs_mod, fuse_motion_encoder=upd)
+    assert BasicMotionEncoder.forward is not original
+    assert tcs_mod.CorrBlock1D.__call__ is not tcs_b200.CorrBlock1D.__call__     # returns deferred lookups
+    tcs_b200.uninstall(tcs_mod, upd)
+    assert BasicMotionEncoder.forward is original
+
+
 GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, %r)

@@ -196,6 +196,46 @@ def test_lookup_coords_view_and_nan(tcs):
     assert torch.equal(out[1], blk(one)[1])
 
 
+# ---------------------------------------------------------------------------------------------------------
+# "next" row: lookup fused with BasicMotionEncoder.convc1 + relu
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth"])
+def test_lookup_encoded_golden(tcs, case):
+    """Against the reference's own lookup output pushed through torch's conv2d + relu (what update.py:104 does)."""
+    g = load_golden(case)
+    gen = torch.Generator().manual_seed(3)
+    conv = torch.nn.Conv2d(36, 64, 1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(64, 36, 1, 1, generator=gen) * 0.3)
+        conv.bias.copy_(torch.randn(64, generator=gen) * 0.1)
+        ref = torch.relu(conv(torch.from_numpy(g["lookup"]))).numpy()
+    blk = tcs.CorrBlock1D.from_levels([cuda(g["level%d" % l]) for l in range(4)])
+    out = blk.lookup_encoded(cuda(g["coords"]), conv.weight.cuda(), conv.bias.cuda())
+    assert_close(host(out), ref, rtol=1e-5, atol=2e-6, what=case + " fused lookup + convc1 + relu vs reference ops")
+    lazy = blk.lazy(cuda(g["coords"]))
+    assert torch.equal(lazy.encode(conv.cuda()), out)
+    assert not torch.isnan(lazy).any()                       # any other torch use sees the plain lookup
+    assert_close(host(lazy.materialize()), g["lookup"], what="lazy lookup materialised")
+
+
+@pytest.mark.parametrize("B,H,W,cout,relu", [(1, 136, 240, 64, True), (2, 30, 160, 64, False), (1, 9, 67, 8, True)])
+def test_lookup_encoded_full_size(tcs, B, H, W, cout, relu):
+    f1, f2 = make_fmaps(B, 128, H, W, 13 + W)
+    blk = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), precision="fp32")
+    coords = make_coords(B, H, W, 5)
+    gen = torch.Generator().manual_seed(9)
+    w = torch.randn(cout, 36, generator=gen) * 0.3
+    bias = torch.randn(cout, generator=gen) * 0.1 if relu else None
+    out = blk.lookup_encoded(coords.cuda(), w.cuda(), bias.cuda() if bias is not None else None, relu=relu)
+    ref = orc.corr_lookup_encoded([host(x) for x in blk._levels], coords.numpy(), w.numpy(), None if bias is None else bias.numpy(), relu)
+    assert_close(host(out), ref, rtol=1e-5, atol=2e-6, what="fused lookup + 1x1")
+    torch.backends.cudnn.allow_tf32 = False          # cuDNN convolutions default to TF32 (1e-3): compare in true fp32
+    assert_close(host(out), host(torch.relu(torch.nn.functional.conv2d(blk(coords.cuda()), w.cuda()[:, :, None, None], bias.cuda())) if relu
+                                 else torch.nn.functional.conv2d(blk(coords.cuda()), w.cuda()[:, :, None, None])),
+                 rtol=1e-4, atol=1e-5, what="fused vs lookup + torch conv2d on the GPU")
+
+
 @pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth"])
 def test_alternate_golden(tcs, case):
     g = load_golden(case)

@@ -97,6 +97,10 @@ for prec in ("fp16", "fp16x3"):
     del flat, levels
 blk = tcs_b200.CorrBlock1D(f1, f2, precision="fp16x3")
 timeit("lookup", lambda: blk(coords), 308 * npix)
+wenc = torch.randn(64, 36, device=dev) * 0.3
+benc = torch.randn(64, device=dev) * 0.1
+timeit("lookup+conv1x1[fused]", lambda: blk.lookup_encoded(coords, wenc, benc), (4 + 160 + 256) * npix)
+timeit("lookup+conv1x1[torch]", lambda: torch.relu(torch.nn.functional.conv2d(blk(coords), wenc[:, :, None, None], benc)), (4 + 160 + 256) * npix)
 timeit("argmax", lambda: blk.argmax_disp(), npix * W * 4)
 alt = tcs_b200.CorrBlock1D(f1, f2, mode="alternate")
 timeit("lookup_alt", lambda: alt(coords), npix * (1024 + 144 + 4), reps=5)
