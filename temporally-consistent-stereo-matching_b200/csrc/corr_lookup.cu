@@ -69,7 +69,7 @@ __device__ __forceinline__ TapPos tap_position(float xk, float wm1, float rc, fl
 }
 
 #ifndef LOOKUP_LD
-#define LOOKUP_LD ldg_stream_f4
+#define LOOKUP_LD ldg_stream64_f4
 #endif
 // The span of one (pixel, level pair): where it starts in the row and its 16-byte quads.
 struct Span {
