@@ -68,9 +68,6 @@ __device__ __forceinline__ TapPos tap_position(float xk, float wm1, float rc, fl
     return t;
 }
 
-#ifndef LOOKUP_LD
-#define LOOKUP_LD ldg_stream64_f4
-#endif
 // The span of one (pixel, level pair): where it starts in the row and its 16-byte quads.
 struct Span {
     float4 q[kLookQuads];
@@ -104,7 +101,7 @@ __device__ __forceinline__ void span_load(Span& sp, const float* __restrict__ ba
         const long long idx = a_abs + 4 * k;
         sp.q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q_lo + 3 >= need_lo && q_lo <= need_hi && idx >= 0 && idx + 3 < readable)
-            sp.q[k] = LOOKUP_LD(reinterpret_cast<const float4*>(base + idx));
+            sp.q[k] = ldg_stream64_f4(reinterpret_cast<const float4*>(base + idx));
     }
 }
 
@@ -391,7 +388,7 @@ corr_lookup_alt_kernel(const float* __restrict__ a, const LevelPtrs bl, const fl
 // ties (torch.max semantics).  Pass 2: max with w2 in {idx-1, idx, idx+1} zeroed.  Values stay in
 // registers between the passes (W2 <= 1024); the per-lane count is a template parameter so that a 240-wide row
 // costs 8 loads and 8 registers, not 32 predicated ones.
-constexpr int kArgMaxPerLane = 32;
+constexpr int kArgMaxPerLane = 32;   // upper bound: rows of up to 1024 columns
 
 template <int kPer>
 __global__ void __launch_bounds__(256)

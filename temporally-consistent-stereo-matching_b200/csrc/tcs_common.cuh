@@ -92,9 +92,6 @@ __device__ __forceinline__ void sts_v4_f32(uint32_t a, const float4& v) {
 __device__ __forceinline__ void sts_v4_u32(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory");
-}
 
 // Streaming (read-once / write-once) global accesses: keep them out of L1.
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
@@ -115,11 +112,6 @@ __device__ __forceinline__ float ldg_ordered_f1(const float* p) {
     asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
-__device__ __forceinline__ float4 ldg_ordered_f4(const float4* p) {   // read-only, allocates in L1, keeps program order
-    float4 r;
-    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
 // Streaming 16-byte load that asks L2 for a 64-byte granule instead of the default 128-byte line: for scattered
 // sub-line reads (the lookup's tap windows) it cuts the DRAM traffic by a third (109 -> 76 MB per launch).
 __device__ __forceinline__ float4 ldg_stream64_f4(const float4* p) {
@@ -127,10 +119,6 @@ __device__ __forceinline__ float4 ldg_stream64_f4(const float4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
-}
-__device__ __forceinline__ void stg_stream_f4(float4* p, const float4& v) {
-    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void stg_stream_f1(float* p, float v) {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
