@@ -8,6 +8,7 @@
 // rounding: x = k + coords/2^l ; xg = 2x/(W-1) - 1 ; ix = ((xg+1)/2)*(W-1) ; x0 = floor(ix) ;
 // out = v[x0]*(x0+1-ix) + v[x0+1]*(ix-x0), out-of-range taps contributing 0 (zeros padding).
 #include "tcs_common.cuh"
+#include <cstdlib>
 
 namespace tcs {
 
@@ -72,6 +73,7 @@ __device__ __forceinline__ TapPos tap_position(float xk, float wm1, float rc, fl
 struct Span {
     float4 q[kLookQuads];
     int win_first;     // in-row index (level 2g) of q[0].x
+    int span_first;    // in-row index of the first float that may be needed (>= win_first, < win_first + 4)
     float cb;          // coords / 2^(2g)
 };
 
@@ -94,6 +96,7 @@ __device__ __forceinline__ void span_load(Span& sp, const float* __restrict__ ba
     }
     const long long a_abs = ((row_start + span_first) >> 2) << 2;   // floor to a multiple of 4 floats (16 B)
     sp.win_first = (int)(a_abs - row_start);
+    sp.span_first = span_first;
     const int need_lo = max(span_first, 0), need_hi = min(span_last, Wb - 1);
 #pragma unroll
     for (int k = 0; k < kLookQuads; ++k) {
@@ -160,6 +163,78 @@ __device__ __forceinline__ void span_taps(const Span& sp, float (*win)[kLookThre
     }
 }
 
+// The same taps with the span held in REGISTERS (level pair with both levels present).  Shared memory costs this
+// kernel L1 capacity, and L1 capacity is what bounds its loads in flight; so the run-time indexing is done with
+// selects instead.  After re-aligning the quads to the span start (offset 0..3), the left neighbour of base-level
+// tap t sits at span position t + 6 + s with s in {-1, 0, 1, 2} (floor(coords) is 2*fu or 2*fu + 1, and
+// grid_sample's round trip moves a tap by at most one), and that of upper-level tap t at pooled position
+// t + 1 + e with e in {-1, 0, 1}: a 4-way and a 3-way select per tap.
+template <bool kKeep>
+__device__ __forceinline__ void span_taps_reg(const Span& sp, float* __restrict__ out, long long out_px, int HW,
+                                              int num_levels, int b, int lb, int Wb, float* keep) {
+    const int Wu = Wb >> 1;
+    const float* f = reinterpret_cast<const float*>(sp.q);      // 28 floats, statically indexed below
+    const int off = sp.span_first - sp.win_first;               // 0..3
+    float t1[27], R[24];
+#pragma unroll
+    for (int j = 0; j < 27; ++j) t1[j] = (off & 1) ? f[j + 1] : f[j];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) R[j] = (off & 2) ? t1[j + 2] : t1[j];
+    const float cb = sp.cb, cu = sp.cb * 0.5f;
+    const int fu = (sp.span_first >> 1) + 5;                    // span_first = 2 * (fu - 5)
+    {   // ---- level lb
+        const float wm1 = (float)(Wb - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
+        float* o = out + (((long long)b * num_levels + lb) * 9) * HW + out_px;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const TapPos tp = tap_position(__fadd_rn((float)(t - 4), cb), wm1, rc, hwm1, Wb);   // corr.py:43
+            const int c = min(max(tp.x0 - sp.span_first - (t + 5), 0), 3);     // s + 1
+            const float lo01 = (c & 1) ? R[t + 6] : R[t + 5], lo23 = (c & 1) ? R[t + 8] : R[t + 7];
+            const float hi01 = (c & 1) ? R[t + 7] : R[t + 6], hi23 = (c & 1) ? R[t + 9] : R[t + 8];
+            const float v0 = (c & 2) ? lo23 : lo01, v1 = (c & 2) ? hi23 : hi01;
+            const float a0 = (tp.w_lo != 0.0f) ? __fmul_rn(v0, tp.w_lo) : 0.0f;
+            const float r = (tp.w_hi != 0.0f) ? fmaf(v1, tp.w_hi, a0) : a0;
+            if (kKeep) keep[t] = r; else stg_stream_f1(o, r);
+            o += HW;
+        }
+    }
+    {   // ---- level lb + 1: entries re-pooled from pairs of the span
+        float P[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) P[j] = __fmul_rn(__fadd_rn(R[2 * j], R[2 * j + 1]), 0.5f);
+        const float wm1 = (float)(Wu - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
+        float* o = out + (((long long)b * num_levels + lb + 1) * 9) * HW + out_px;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const TapPos tp = tap_position(__fadd_rn((float)(t - 4), cu), wm1, rc, hwm1, Wu);
+            const int c = min(max(tp.x0 - (fu - 5) - t, 0), 2);                  // e + 1
+            const float v0 = (c == 0) ? P[t] : (c == 1) ? P[t + 1] : P[t + 2];
+            const float v1 = (c == 0) ? P[t + 1] : (c == 1) ? P[t + 2] : P[t + 3];
+            const float a0 = (tp.w_lo != 0.0f) ? __fmul_rn(v0, tp.w_lo) : 0.0f;
+            const float r = (tp.w_hi != 0.0f) ? fmaf(v1, tp.w_hi, a0) : a0;
+            if (kKeep) keep[9 + t] = r; else stg_stream_f1(o, r);
+            o += HW;
+        }
+    }
+}
+
+// The standard configuration (4 levels): no shared memory at all.
+__global__ void __launch_bounds__(kLookThreads)
+corr_lookup_r4x4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
+                        float* __restrict__ out, int HW, int W2) {
+    const int b = blockIdx.z;
+    const int hw = blockIdx.x * kLookThreads + threadIdx.x;
+    if (hw >= HW) return;
+    const long long npix = (long long)gridDim.z * HW;
+    const long long p = (long long)b * HW + hw;
+    const float c0 = __ldg(coords + b * coords_bstride + hw);
+    Span s0, s1;
+    span_load(s0, lv.p[0], p, npix, c0, 0, W2, true);
+    span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
+    span_taps_reg<false>(s0, out, hw, HW, 4, b, 0, W2, nullptr);
+    span_taps_reg<false>(s1, out, hw, HW, 4, b, 2, W2 >> 2, nullptr);
+}
+
 // One thread per pixel, both level pairs: the loads of pair 1 (levels 2,3) are issued before the taps of pair 0
 // (levels 0,1) are evaluated, so their latency hides behind ~600 instructions of interpolation.
 __global__ void __launch_bounds__(kLookThreads)
@@ -193,7 +268,6 @@ __global__ void __launch_bounds__(kLookThreads)
 corr_lookup_encode_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
                           const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ out,
                           int HW, int W2, int Cout, int relu) {
-    __shared__ float win[4 * kLookQuads][kLookThreads];
     __shared__ __align__(16) float s_w[kEncMaxOut * kEncTaps];
     __shared__ float s_b[kEncMaxOut];
     const int tid = threadIdx.x;
@@ -210,8 +284,8 @@ corr_lookup_encode_kernel(const LevelPtrs lv, const float* __restrict__ coords, 
     span_load(s0, lv.p[0], p, npix, c0, 0, W2, true);
     span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
     float tp[kEncTaps];
-    span_taps<true>(s0, win, tid, nullptr, 0, HW, 4, b, 0, W2, true, tp);
-    span_taps<true>(s1, win, tid, nullptr, 0, HW, 4, b, 2, W2 >> 2, true, tp + 18);
+    span_taps_reg<true>(s0, nullptr, 0, HW, 4, b, 0, W2, tp);
+    span_taps_reg<true>(s1, nullptr, 0, HW, 4, b, 2, W2 >> 2, tp + 18);
     float* o = out + (long long)b * Cout * HW + hw;
     for (int oc = 0; oc < Cout; oc += 4) {
         float acc[4] = {s_b[oc], s_b[oc + 1], s_b[oc + 2], s_b[oc + 3]};
@@ -500,7 +574,10 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
             if (carve >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_r4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             attr_done = true;
         }
-        corr_lookup_r4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels);
+        if (num_levels == 4)     // the standard configuration: span in registers, no shared memory (+2 % in the step)
+            corr_lookup_r4x4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
+        else
+            corr_lookup_r4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels);
     } else {
         dim3 grid((unsigned)ceil_div_ll(npix, 256), num_levels);
         corr_lookup_generic_kernel<<<grid, 256, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels, radius, npix);
@@ -526,7 +603,7 @@ extern "C" int tcs_corr_lookup_encode(const float* lvl0, const float* lvl1, cons
     dim3 grid((unsigned)ceil_div(H * W1, kLookThreads), 1, B);
     static bool attr_done = false;
     if (!attr_done) {
-        const int carve = carveout_percent("TCS_CARVE_LOOKUP_ENC", 35);
+        const int carve = carveout_percent("TCS_CARVE_LOOKUP_ENC", 25);
         if (carve >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         attr_done = true;
     }
