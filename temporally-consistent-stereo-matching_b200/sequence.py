@@ -114,7 +114,7 @@ def launches_per_frame(iters, first_frame, hidden_levels=3, mode="pyramid", num_
         if mode != "pyramid":
             n += 2                                                 # its prepasses
     else:
-        n += 3 + 1 + hidden_levels + (hidden_levels - 1)           # geometry, splat, finalize; grid; gathers; halves
+        n += 4 + 1 + hidden_levels + (hidden_levels - 1)           # geometry, weights, splat, finalize; grid; gathers; halves
     return n + iters
 
 

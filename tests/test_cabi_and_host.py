@@ -164,3 +164,26 @@ def test_two_rank_gloo_metric_reduce(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0 and "ok" in out, out
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints ONE JSON line with the contract's keys (CPU port of the path)."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--height", "128", "--width", "192", "--iters", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_launch_count_model():
+    from tcs_b200 import sequence
+    assert sequence.launches_per_frame(32, False) == 1 + 4 + 1 + 3 + 2 + 32   # fused build; geometry, weights, splat, finalize; grid; 3 gathers; 2 halvings; lookups
+    assert sequence.launches_per_frame(32, True) == 1 + 1 + 32
+    assert sequence.launches_per_frame(32, False, fused_build=False) == sequence.launches_per_frame(32, False) + 2
