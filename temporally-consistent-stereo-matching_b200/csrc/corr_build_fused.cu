@@ -37,13 +37,17 @@ constexpr int kMaxN = 240;                          // one N tile
 constexpr int kMaxW1 = 256;
 constexpr int kStages = 2;                          // operand tile stages
 constexpr int kSlotK = 16;                          // channels per staging slot (two slots feed one operand stage)
-constexpr int kSlots = 4;                           // fp32 staging slots: three in flight while one is converted
+#ifndef TCS_FUSED_SLOTS
+#define TCS_FUSED_SLOTS 5
+#endif
+constexpr int kSlots = TCS_FUSED_SLOTS;             // fp32 staging slots: three in flight while one is converted
 constexpr int kATile = kBlockM * kBlockK * 2;       // 8 KB
 constexpr int kBTile = kMaxN * kBlockK * 2;         // 15 KB
 constexpr int kStageBytes = 2 * kATile + 2 * kBTile;    // A_hi, A_lo, B_hi, B_lo = 46 KB
 constexpr int kABox = kSlotK * kBlockM * 4;         // 8 KB of fp32
 constexpr int kBBox = kSlotK * kMaxN * 4;           // 15 KB of fp32 (box width = block_n <= 240)
 constexpr int kSlotBytes = kABox + kBBox;           // 23 KB
+constexpr int kXSlots = 4;                          // norm pass only: the (then idle) operand stages serve as extra staging slots
 constexpr int kAccStages = 2;
 constexpr int kAccCols = 256;
 constexpr int kTmemCols = kAccStages * kAccCols;
@@ -56,6 +60,10 @@ constexpr int kInvBytes = (kMaxW1 + 256) * 4;       // 1/norm of the A pixels, t
 constexpr int kBarrierBytes = 256;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kSlots * kSlotBytes + kEpiWarps * kEpiStageBytes + kInvBytes + kBarrierBytes;
 static_assert(kSmemBytes <= 232448, "fused build: shared memory budget exceeded");
+static_assert(kXSlots * kSlotBytes <= kStages * kStageBytes, "extra norm-pass slots live inside the operand stages");
+constexpr int kRing1 = kSlots + kXSlots;            // staging ring of the norm pass
+static_assert(8 * (2 * kRing1 + 2 * kStages + 2 * kAccStages + 1) + 4 <= kBarrierBytes, "barrier area");
+static_assert(2 * kABox <= kSlotBytes, "a slot must hold two A boxes (norm pass of the later M tiles)");
 static_assert(kStageBytes % 1024 == 0 && kSlotBytes % 512 == 0 && kATile % 512 == 0 && kBTile % 512 == 0, "tile alignment");
 
 struct Params {
@@ -210,6 +218,26 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpilogueArgs& p, const C
     }
 }
 
+// Work list of a CTA: whole image rows (all M tiles, so the row's B norms are computed once), interleaved over the
+// grid; when the last, partial wave has no more tiles than there are CTAs it is dealt out tile by tile instead, so
+// the tail costs one tile rather than one row.
+__device__ __forceinline__ bool work_item(const Params& p, int k, int& row, int& m_lo, int& m_hi) {
+    const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int waves = p.num_rows / grid;
+    m_lo = 0; m_hi = p.num_m;
+    if (k < waves) { row = k * grid + cta; return true; }
+    const int rem = p.num_rows - waves * grid;
+    if (k > waves || rem == 0) return false;
+    if (rem * p.num_m <= grid) {
+        if (cta >= rem * p.num_m) return false;
+        row = waves * grid + cta / p.num_m;
+        m_lo = cta - (cta / p.num_m) * p.num_m; m_hi = m_lo + 1;
+        return true;
+    }
+    row = waves * grid + cta;
+    return cta < rem;
+}
+
 template <bool kFp16>
 __global__ void __launch_bounds__(kThreads, 1)
 corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -222,22 +250,29 @@ corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     float* inv_b = inv_a + kMaxW1;                                                     // [256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(inv_a) + kInvBytes);
     const uint32_t bar_sfull = smem_u32(bars);                    // staging slot filled by TMA
-    const uint32_t bar_sempty = bar_sfull + 8 * kSlots;           // staging slot drained by the converters
-    const uint32_t bar_full = bar_sempty + 8 * kSlots;            // operand stage written by the converters
+    const uint32_t bar_sempty = bar_sfull + 8 * kRing1;           // staging slot drained by the converters
+    const uint32_t bar_full = bar_sempty + 8 * kRing1;            // operand stage written by the converters
     const uint32_t bar_empty = bar_full + 8 * kStages;            // operand stage consumed by the MMAs
     const uint32_t bar_tfull = bar_empty + 8 * kStages;
     const uint32_t bar_tempty = bar_tfull + 8 * kAccStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 2 * kStages + 2 * kAccStages);
+    const uint32_t bar_rowdone = bar_tempty + 8 * kAccStages;     // every MMA of a row has retired: its operand stages are idle
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRing1 + 2 * kStages + 2 * kAccStages + 1);
+    // staging slot j: the dedicated ring, then (norm pass only) the operand stages cut into slot-sized pieces
+    const uint32_t slot0_addr = smem_u32(slot_base), stage0_addr = smem_u32(smem);
+    auto slot_addr = [&](int j) -> uint32_t {
+        return j < kSlots ? slot0_addr + (uint32_t)j * kSlotBytes : stage0_addr + (uint32_t)(j - kSlots) * kSlotBytes;
+    };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int i = 0; i < kSlots; ++i) {
+            for (int i = 0; i < kRing1; ++i) {
                 ptx::mbar_init(bar_sfull + 8 * i, 1);
                 ptx::mbar_init(bar_sempty + 8 * i, kConvThreads);
             }
+            ptx::mbar_init(bar_rowdone, 1);
             for (int i = 0; i < kStages; ++i) {
                 ptx::mbar_init(bar_full + 8 * i, kConvThreads);
                 ptx::mbar_init(bar_empty + 8 * i, 1);
@@ -267,8 +302,9 @@ corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             int iter = 0;
-            for (int row = blockIdx.x; row < p.num_rows; row += gridDim.x) {
-                for (int m_t = 0; m_t < p.num_m; ++m_t, ++iter) {
+            int row, m_lo, m_hi;
+            for (int k = 0; work_item(p, k, row, m_lo, m_hi); ++k) {
+                for (int m_t = m_lo; m_t < m_hi; ++m_t, ++iter) {
                     const uint32_t acc = iter & 1;
                     const uint32_t acc_phase = (iter >> 1) & 1;
                     ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -289,7 +325,10 @@ corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
                                 ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (kb | pass | k) != 0 ? 1u : 0u);
                         }
                         ptx::umma_commit(bar_empty + 8 * stage);
-                        if (kb == p.kblocks - 1) ptx::umma_commit(bar_tfull + 8 * acc);
+                        if (kb == p.kblocks - 1) {
+                            ptx::umma_commit(bar_tfull + 8 * acc);
+                            if (m_t == m_hi - 1) ptx::umma_commit(bar_rowdone);
+                        }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -299,20 +338,33 @@ corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
         // ================= TMA producer =================
         // Per row: pass 1 (A tile of every M tile, B only with the first), then pass 2 (A tile + B for every M tile).
         if (lane == 0) {
-            uint32_t slot = 0, phase = 0;
-            for (int row = blockIdx.x; row < p.num_rows; row += gridDim.x) {
+            uint32_t bits = 0;                         // per-slot phase parity (the two passes use rings of different length)
+            int rows_done = 0;
+            int row, m_lo, m_hi;
+            for (; work_item(p, rows_done, row, m_lo, m_hi); ++rows_done) {
                 const int b = row / p.H, h = row - b * p.H;
                 for (int pass = 0; pass < 2; ++pass) {
-                    for (int m_t = 0; m_t < p.num_m; ++m_t) {
-                        const bool with_b = (pass == 1) || (m_t == 0);
-                        for (int kb = 0; kb < 2 * p.kblocks; ++kb) {      // 16-channel boxes
-                            ptx::mbar_wait(bar_sempty + 8 * slot, phase ^ 1);
-                            const uint32_t dst = smem_u32(slot_base + slot * kSlotBytes);
-                            const uint32_t full = bar_sfull + 8 * slot;
-                            ptx::mbar_arrive_expect_tx(full, a_box_bytes + (with_b ? b_box_bytes : 0));
+                    const int ring = pass == 0 ? kRing1 : kSlots;
+                    int j = 0;
+                    bool stages_idle = rows_done == 0;
+                    for (int m_t = m_lo; m_t < m_hi; ++m_t) {
+                        const bool with_b = (pass == 1) || (m_t == m_lo);
+                        // a slot without a B box has room for two A boxes: fewer, fuller round trips in the norm pass
+                        const int per_slot = with_b ? 1 : 2;
+                        for (int kb = 0; kb < 2 * p.kblocks; kb += per_slot) {      // 16-channel boxes
+                            if (j >= kSlots && !stages_idle) {   // the previous row's MMAs still read the operand stages
+                                ptx::mbar_wait(bar_rowdone, (rows_done - 1) & 1);
+                                stages_idle = true;
+                            }
+                            ptx::mbar_wait(bar_sempty + 8 * j, ((bits >> j) & 1) ^ 1);
+                            const uint32_t dst = slot_addr(j);
+                            const uint32_t full = bar_sfull + 8 * j;
+                            ptx::mbar_arrive_expect_tx(full, with_b ? a_box_bytes + b_box_bytes : 2 * a_box_bytes);
                             ptx::tma_load_4d(dst, &tm_a, full, m_t * kBlockM, h, kb * kSlotK, b);
                             if (with_b) ptx::tma_load_4d(dst + kABox, &tm_b, full, 0, h, kb * kSlotK, b);
-                            if (++slot == kSlots) { slot = 0; phase ^= 1; }
+                            else ptx::tma_load_4d(dst + kABox, &tm_a, full, m_t * kBlockM, h, (kb + 1) * kSlotK, b);
+                            bits ^= 1u << j;
+                            if (++j == ring) j = 0;
                         }
                     }
                 }
@@ -324,22 +376,29 @@ corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
         const int ct = cw * 32 + lane;                // 0..319
         const bool want_lo = p.passes == 3;
         const int bw = p.block_n;                     // B box width (pixels)
-        uint32_t slot = 0, sphase = 0;                // staging ring
+        uint32_t bits = 0;                            // per-slot phase parity of the staging slots (as in the producer)
         uint32_t stage = 0, phase = 0;                // operand stages
-        for (int row = blockIdx.x; row < p.num_rows; row += gridDim.x) {
+        int row, m_lo, m_hi;
+        for (int k = 0; work_item(p, k, row, m_lo, m_hi); ++k) {
             // ---- pass 1: sum of squares per pixel; a thread owns fixed pixels and adds channels in order
             float ss_b0 = 0.0f, ss_b1 = 0.0f;
-            for (int m_t = 0; m_t < p.num_m; ++m_t) {
+            int j = 0;
+            for (int m_t = m_lo; m_t < m_hi; ++m_t) {
                 float ss_a = 0.0f;
-                for (int kb = 0; kb < 2 * p.kblocks; ++kb) {
-                    ptx::mbar_wait(bar_sfull + 8 * slot, sphase);
-                    const uint32_t abox = smem_u32(slot_base + slot * kSlotBytes);
+                const int per_slot = m_t == m_lo ? 1 : 2;    // M tiles after the first come two A boxes to a slot
+                for (int kb = 0; kb < 2 * p.kblocks; kb += per_slot) {
+                    ptx::mbar_wait(bar_sfull + 8 * j, (bits >> j) & 1);
+                    const uint32_t abox = slot_addr(j);
                     const uint32_t bbox = abox + kABox;
                     if (ct < kBlockM) {
 #pragma unroll
                         for (int c = 0; c < kSlotK; ++c) { const float v = lds_f32(abox + 4u * (c * kBlockM + ct)); ss_a = fmaf(v, v, ss_a); }
+                        if (m_t != m_lo) {
+#pragma unroll
+                            for (int c = kSlotK; c < 2 * kSlotK; ++c) { const float v = lds_f32(abox + 4u * (c * kBlockM + ct)); ss_a = fmaf(v, v, ss_a); }
+                        }
                     }
-                    if (m_t == 0) {
+                    if (m_t == m_lo) {
                         if (ct < bw) {
 #pragma unroll
                             for (int c = 0; c < kSlotK; ++c) { const float v = lds_f32(bbox + 4u * (c * bw + ct)); ss_b0 = fmaf(v, v, ss_b0); }
@@ -349,16 +408,18 @@ corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
                             for (int c = 0; c < kSlotK; ++c) { const float v = lds_f32(bbox + 4u * (c * bw + ct + kConvThreads)); ss_b1 = fmaf(v, v, ss_b1); }
                         }
                     }
-                    ptx::mbar_arrive(bar_sempty + 8 * slot);
-                    if (++slot == kSlots) { slot = 0; sphase ^= 1; }
+                    ptx::mbar_arrive(bar_sempty + 8 * j);
+                    bits ^= 1u << j;
+                    if (++j == kRing1) j = 0;
                 }
                 if (ct < kBlockM) inv_a[m_t * kBlockM + ct] = __frcp_rn(fmaxf(sqrtf(ss_a), 1e-12f));   // corr.py:58-59
             }
             if (ct < bw) inv_b[ct] = __frcp_rn(fmaxf(sqrtf(ss_b0), 1e-12f));
             if (ct + kConvThreads < bw) inv_b[ct + kConvThreads] = __frcp_rn(fmaxf(sqrtf(ss_b1), 1e-12f));
-            conv_barrier();
+            conv_barrier();   // also: every converter is done reading the norm-pass slots that live in the operand stages
+            j = 0;
             // ---- pass 2: one 32-channel K block per stage: the A tile of this M tile and the whole B row
-            for (int m_t = 0; m_t < p.num_m; ++m_t) {
+            for (int m_t = m_lo; m_t < m_hi; ++m_t) {
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t sa_hi = smem_u32(smem + stage * kStageBytes);
@@ -366,16 +427,17 @@ corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
                     const uint32_t sb_hi = sa_lo + kATile;
                     const uint32_t sb_lo = sb_hi + kBTile;
                     for (int half = 0; half < 2; ++half) {       // two 16-channel slots fill one 32-channel stage
-                        ptx::mbar_wait(bar_sfull + 8 * slot, sphase);
-                        const uint32_t abox = smem_u32(slot_base + slot * kSlotBytes);
+                        ptx::mbar_wait(bar_sfull + 8 * j, (bits >> j) & 1);
+                        const uint32_t abox = slot_addr(j);
                         const uint32_t bbox = abox + kABox;
                         {
                             // A: 4 row groups x 2 octets = 8 items; B: up to 8 x 2 = 16 items; 24 items over 6 warps
                             convert_box<kFp16>(abox, kBlockM, kBlockM, smem_u32(inv_a + m_t * kBlockM), p.in_scale, sa_hi, sa_lo, want_lo, half, cw, kConvWarps, lane);
                             convert_box<kFp16>(bbox, bw, bw, smem_u32(inv_b), p.in_scale, sb_hi, sb_lo, want_lo, half, (cw + 8) % kConvWarps, kConvWarps, lane);
                         }
-                        ptx::mbar_arrive(bar_sempty + 8 * slot);
-                        if (++slot == kSlots) { slot = 0; sphase ^= 1; }
+                        ptx::mbar_arrive(bar_sempty + 8 * j);
+                        bits ^= 1u << j;
+                        if (++j == kSlots) j = 0;
                     }
                     fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
                     ptx::mbar_arrive(bar_full + 8 * stage);
@@ -394,8 +456,9 @@ corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
         for (int l = 0; l < TCS_MAX_LEVELS; ++l) ea.lvl[l] = p.lvl[l];
         ea.W1 = p.W1; ea.W2 = p.W2; ea.num_levels = p.num_levels; ea.scale = p.out_scale;
         int iter = 0;
-        for (int row = blockIdx.x; row < p.num_rows; row += gridDim.x) {
-            for (int m_t = 0; m_t < p.num_m; ++m_t, ++iter) {
+        int row, m_lo, m_hi;
+        for (int k = 0; work_item(p, k, row, m_lo, m_hi); ++k) {
+            for (int m_t = m_lo; m_t < m_hi; ++m_t, ++iter) {
                 const uint32_t acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
                 ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
