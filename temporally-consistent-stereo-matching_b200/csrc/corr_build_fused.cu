@@ -569,7 +569,8 @@ extern "C" int tcs_corr_build_fused(const float* fmap1, const float* fmap2,
         else TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_build_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_done[fp16 ? 1 : 0] = true;
     }
-    const int grid = p.num_rows < num_sms() ? p.num_rows : num_sms();
+    const int units = p.num_rows * p.num_m;
+    const int grid = units < num_sms() ? units : num_sms();
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (fp16) corr_build_fused_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(tma, tmb, tml0, tml1, p);
     else corr_build_fused_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(tma, tmb, tml0, tml1, p);
