@@ -381,7 +381,7 @@ def run_b200(args):
     tp_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp_path):
         traffic = json.load(open(tp_path)).get("corr_lookup_bytes_per_launch_B%d" % B)
-    roofline = {"kernel": "corr_lookup_r4x4_kernel", "bound": "hbm", "achieved": lookup_bytes / (lookup_ms * 1e-3) / 1e9,
+    roofline = {"kernel": "corr_lookup_r4x4o_kernel", "bound": "hbm", "achieved": lookup_bytes / (lookup_ms * 1e-3) / 1e9,
                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": lookup_bytes / (lookup_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                 "traffic": traffic, "peak_source": pk["source"], "launches_per_step": iters,
                 "algorithmic_bytes_per_launch": lookup_bytes}

@@ -57,13 +57,13 @@ def normalized_operands(fmap, precision="bf16x3", want_hi=True, want_lo=None, wa
 
 
 def alloc_pyramid(B, H, W1, W2, num_levels, device):
-    """One flat fp32 buffer holding every level [B,H,W1,W2>>l], each 16-byte aligned and padded so the
-    lookup may read up to the next 16-byte boundary past a level's end."""
+    """One flat fp32 buffer holding every level [B,H,W1,W2>>l], each 128-byte aligned (the lookup's 32-byte
+    loads need 32) and padded so the lookup may read up to the next 16-byte boundary past a level's end."""
     sizes = [B * H * W1 * (W2 >> l) for l in range(num_levels)]
     offs, total = [], 0
     for s in sizes:
         offs.append(total)
-        total += _pad16(s) + 4
+        total += (_pad16(s) + 4 + 31) & ~31
     flat = torch.empty(total, dtype=torch.float32, device=device)
     levels = [flat[o:o + s].view(B, H, W1, W2 >> l) for l, (o, s) in enumerate(zip(offs, sizes))]
     return flat, levels

@@ -69,6 +69,24 @@ __device__ __forceinline__ TapPos tap_position(float xk, float wm1, float rc, fl
     return t;
 }
 
+// The same when the span registers already hold exact zeros wherever the level ends (rows that start and end on
+// 16-byte boundaries: a quad is then entirely inside or entirely outside its row, and span_load() leaves the
+// outside ones at zero).  Zero padding then needs no predicate at all: 0 * w is the reference's "skip this corner".
+// The caller keeps coords finite (sane_coord), so w is finite.
+__device__ __forceinline__ TapPos tap_position_padded(float xk, float wm1, float rc, float hwm1) {
+    TapPos t;
+    const float ix = sample_pos_fast(xk, wm1, rc, hwm1);
+    const float x0f = floorf(ix);
+    t.x0 = (int)x0f;                                                // saturating; only its clamped offset is used
+    t.w_hi = __fsub_rn(ix, x0f);
+    t.w_lo = __fsub_rn(__fadd_rn(x0f, 1.0f), ix);
+    return t;
+}
+
+// NaN / infinite / absurd coordinates -> a finite one far outside every level (all taps are then zero padding,
+// which is also what the reference's grid_sample returns for them).
+__device__ __forceinline__ float sane_coord(float c) { return (fabsf(c) <= 1.0e9f) ? c : 1.0e9f; }
+
 // The span of one (pixel, level pair): where it starts in the row and its 16-byte quads.
 struct Span {
     float4 q[kLookQuads];
@@ -169,10 +187,14 @@ __device__ __forceinline__ void span_taps(const Span& sp, float (*win)[kLookThre
 // tap t sits at span position t + 6 + s with s in {-1, 0, 1, 2} (floor(coords) is 2*fu or 2*fu + 1, and
 // grid_sample's round trip moves a tap by at most one), and that of upper-level tap t at pooled position
 // t + 1 + e with e in {-1, 0, 1}: a 4-way and a 3-way select per tap.
-template <bool kKeep>
+template <bool kKeep, bool kPadded>
+__device__ __forceinline__ void span_taps_R(const float* R, int span_first, float cb_, float* __restrict__ out, long long out_px,
+                                            int HW, int num_levels, int b, int lb, int Wb, float* keep);
+
+// kPadded: the rows of this level start on 16-byte boundaries (Wb % 4 == 0), see tap_position_padded().
+template <bool kKeep, bool kPadded>
 __device__ __forceinline__ void span_taps_reg(const Span& sp, float* __restrict__ out, long long out_px, int HW,
                                               int num_levels, int b, int lb, int Wb, float* keep) {
-    const int Wu = Wb >> 1;
     const float* f = reinterpret_cast<const float*>(sp.q);      // 28 floats, statically indexed below
     const int off = sp.span_first - sp.win_first;               // 0..3
     float t1[27], R[24];
@@ -180,20 +202,34 @@ __device__ __forceinline__ void span_taps_reg(const Span& sp, float* __restrict_
     for (int j = 0; j < 27; ++j) t1[j] = (off & 1) ? f[j + 1] : f[j];
 #pragma unroll
     for (int j = 0; j < 24; ++j) R[j] = (off & 2) ? t1[j + 2] : t1[j];
-    const float cb = sp.cb, cu = sp.cb * 0.5f;
-    const int fu = (sp.span_first >> 1) + 5;                    // span_first = 2 * (fu - 5)
+    span_taps_R<kKeep, kPadded>(R, sp.span_first, sp.cb, out, out_px, HW, num_levels, b, lb, Wb, keep);
+}
+
+// R[0..23]: the span itself (entry j = in-row index span_first + j of level lb, zero outside the row when kPadded).
+template <bool kKeep, bool kPadded>
+__device__ __forceinline__ void span_taps_R(const float* R, int span_first, float cb_, float* __restrict__ out, long long out_px,
+                                            int HW, int num_levels, int b, int lb, int Wb, float* keep) {
+    const int Wu = Wb >> 1;
+    const float cb = cb_, cu = cb_ * 0.5f;
+    const int fu = (span_first >> 1) + 5;                       // span_first = 2 * (fu - 5)
     {   // ---- level lb
         const float wm1 = (float)(Wb - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
         float* o = out + (((long long)b * num_levels + lb) * 9) * HW + out_px;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-            const TapPos tp = tap_position(__fadd_rn((float)(t - 4), cb), wm1, rc, hwm1, Wb);   // corr.py:43
-            const int c = min(max(tp.x0 - sp.span_first - (t + 5), 0), 3);     // s + 1
+            const float xk = __fadd_rn((float)(t - 4), cb);                    // corr.py:43
+            const TapPos tp = kPadded ? tap_position_padded(xk, wm1, rc, hwm1) : tap_position(xk, wm1, rc, hwm1, Wb);
+            const int c = min(max(tp.x0 - span_first - (t + 5), 0), 3);     // s + 1
             const float lo01 = (c & 1) ? R[t + 6] : R[t + 5], lo23 = (c & 1) ? R[t + 8] : R[t + 7];
             const float hi01 = (c & 1) ? R[t + 7] : R[t + 6], hi23 = (c & 1) ? R[t + 9] : R[t + 8];
             const float v0 = (c & 2) ? lo23 : lo01, v1 = (c & 2) ? hi23 : hi01;
-            const float a0 = (tp.w_lo != 0.0f) ? __fmul_rn(v0, tp.w_lo) : 0.0f;
-            const float r = (tp.w_hi != 0.0f) ? fmaf(v1, tp.w_hi, a0) : a0;
+            float r;
+            if (kPadded) {
+                r = fmaf(v1, tp.w_hi, __fmul_rn(v0, tp.w_lo));
+            } else {
+                const float a0 = (tp.w_lo != 0.0f) ? __fmul_rn(v0, tp.w_lo) : 0.0f;
+                r = (tp.w_hi != 0.0f) ? fmaf(v1, tp.w_hi, a0) : a0;
+            }
             if (kKeep) keep[t] = r; else stg_stream_f1(o, r);
             o += HW;
         }
@@ -206,19 +242,90 @@ __device__ __forceinline__ void span_taps_reg(const Span& sp, float* __restrict_
         float* o = out + (((long long)b * num_levels + lb + 1) * 9) * HW + out_px;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-            const TapPos tp = tap_position(__fadd_rn((float)(t - 4), cu), wm1, rc, hwm1, Wu);
+            const float xk = __fadd_rn((float)(t - 4), cu);
+            const TapPos tp = kPadded ? tap_position_padded(xk, wm1, rc, hwm1) : tap_position(xk, wm1, rc, hwm1, Wu);
             const int c = min(max(tp.x0 - (fu - 5) - t, 0), 2);                  // e + 1
             const float v0 = (c == 0) ? P[t] : (c == 1) ? P[t + 1] : P[t + 2];
             const float v1 = (c == 0) ? P[t + 1] : (c == 1) ? P[t + 2] : P[t + 3];
-            const float a0 = (tp.w_lo != 0.0f) ? __fmul_rn(v0, tp.w_lo) : 0.0f;
-            const float r = (tp.w_hi != 0.0f) ? fmaf(v1, tp.w_hi, a0) : a0;
+            float r;
+            if (kPadded) {
+                r = fmaf(v1, tp.w_hi, __fmul_rn(v0, tp.w_lo));
+            } else {
+                const float a0 = (tp.w_lo != 0.0f) ? __fmul_rn(v0, tp.w_lo) : 0.0f;
+                r = (tp.w_hi != 0.0f) ? fmaf(v1, tp.w_hi, a0) : a0;
+            }
             if (kKeep) keep[9 + t] = r; else stg_stream_f1(o, r);
             o += HW;
         }
     }
 }
 
-// The standard configuration (4 levels): no shared memory at all.
+// Level 0 of a row-aligned pyramid read as four 32-byte loads instead of seven 16-byte ones: what bounds this kernel
+// is the number of load requests the SM keeps in flight, not their bytes (23.0 -> 20.4 us).  Needs W2 % 8 == 0 and a
+// 32-byte aligned base: rows then start on 32-byte boundaries and an oct is entirely inside or outside its row.
+// (The same for level 2, whose 240-byte rows would need half-oct fix-ups, is no faster than quads: 23.1 us.)
+__device__ __forceinline__ void ldg_oct(float* r, const float* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+}
+
+struct SpanOct {
+    float o[32];
+    int off;           // span_first - (in-row index of o[0]): 0, 2, 4 or 6
+    int span_first;
+    float cb;
+};
+
+__device__ __forceinline__ void span_load_oct(SpanOct& sp, const float* __restrict__ base, long long p, float c0, int lb, int Wb) {
+    const int Wu = Wb >> 1;
+    sp.cb = c0 * (1.0f / (float)(1 << lb));
+    const int fu = (int)fminf(fmaxf(floorf(sp.cb * 0.5f), -16.0f), (float)(Wu + 16));
+    const int span_first = 2 * (fu - 5);
+    sp.span_first = span_first;
+    const int win_first = span_first & ~7;                           // row starts are multiples of 8 floats
+    sp.off = span_first - win_first;
+    const float* row = base + p * Wb;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int q_lo = win_first + 8 * k;
+        float* r = sp.o + 8 * k;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = 0.0f;
+        if (q_lo >= 0 && q_lo < Wb && q_lo <= span_first + 23) ldg_oct(r, row + q_lo);
+    }
+}
+
+template <bool kKeep>
+__device__ __forceinline__ void span_taps_oct(const SpanOct& sp, float* __restrict__ out, long long out_px, int HW, int b, int lb,
+                                              int Wb, float* keep) {
+    float t1[30], R[24];
+#pragma unroll
+    for (int j = 0; j < 30; ++j) t1[j] = (sp.off & 2) ? sp.o[j + 2] : sp.o[j];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) R[j] = (sp.off & 4) ? t1[j + 4] : t1[j];
+    span_taps_R<kKeep, true>(R, sp.span_first, sp.cb, out, out_px, HW, 4, b, lb, Wb, keep);
+}
+
+__global__ void __launch_bounds__(kLookThreads)
+corr_lookup_r4x4o_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
+                         float* __restrict__ out, int HW, int W2) {
+    const int b = blockIdx.z;
+    const int hw = blockIdx.x * kLookThreads + threadIdx.x;
+    if (hw >= HW) return;
+    const long long npix = (long long)gridDim.z * HW;
+    const long long p = (long long)b * HW + hw;
+    const float c0 = sane_coord(__ldg(coords + b * coords_bstride + hw));
+    SpanOct s0;
+    Span s1;
+    span_load_oct(s0, lv.p[0], p, c0, 0, W2);
+    span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
+    span_taps_oct<false>(s0, out, hw, HW, b, 0, W2, nullptr);
+    span_taps_reg<false, true>(s1, out, hw, HW, 4, b, 2, W2 >> 2, nullptr);
+}
+
+// The standard configuration (4 levels): no shared memory at all.  kPadded: W2 % 16 == 0, i.e. the rows of levels
+// 0 and 2 start on 16-byte boundaries and the taps need no bounds predicates.
+template <bool kPadded>
 __global__ void __launch_bounds__(kLookThreads)
 corr_lookup_r4x4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
                         float* __restrict__ out, int HW, int W2) {
@@ -227,12 +334,13 @@ corr_lookup_r4x4_kernel(const LevelPtrs lv, const float* __restrict__ coords, lo
     if (hw >= HW) return;
     const long long npix = (long long)gridDim.z * HW;
     const long long p = (long long)b * HW + hw;
-    const float c0 = __ldg(coords + b * coords_bstride + hw);
+    float c0 = __ldg(coords + b * coords_bstride + hw);
+    if (kPadded) c0 = sane_coord(c0);
     Span s0, s1;
     span_load(s0, lv.p[0], p, npix, c0, 0, W2, true);
     span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
-    span_taps_reg<false>(s0, out, hw, HW, 4, b, 0, W2, nullptr);
-    span_taps_reg<false>(s1, out, hw, HW, 4, b, 2, W2 >> 2, nullptr);
+    span_taps_reg<false, kPadded>(s0, out, hw, HW, 4, b, 0, W2, nullptr);
+    span_taps_reg<false, kPadded>(s1, out, hw, HW, 4, b, 2, W2 >> 2, nullptr);
 }
 
 // One thread per pixel, both level pairs: the loads of pair 1 (levels 2,3) are issued before the taps of pair 0
@@ -264,6 +372,7 @@ corr_lookup_r4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long
 constexpr int kEncTaps = 36;
 constexpr int kEncMaxOut = 128;
 
+template <int kMode>   // 0: any width; 1: W2 % 16 == 0 (no bounds predicates); 2: + level 0 32-byte aligned (32-byte loads)
 __global__ void __launch_bounds__(kLookThreads)
 corr_lookup_encode_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
                           const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ out,
@@ -279,13 +388,23 @@ corr_lookup_encode_kernel(const LevelPtrs lv, const float* __restrict__ coords, 
     if (hw >= HW) return;
     const long long npix = (long long)gridDim.z * HW;
     const long long p = (long long)b * HW + hw;
-    const float c0 = __ldg(coords + b * coords_bstride + hw);
-    Span s0, s1;
-    span_load(s0, lv.p[0], p, npix, c0, 0, W2, true);
-    span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
+    constexpr bool kPadded = kMode != 0;
+    float c0 = __ldg(coords + b * coords_bstride + hw);
+    if (kPadded) c0 = sane_coord(c0);
     float tp[kEncTaps];
-    span_taps_reg<true>(s0, nullptr, 0, HW, 4, b, 0, W2, tp);
-    span_taps_reg<true>(s1, nullptr, 0, HW, 4, b, 2, W2 >> 2, tp + 18);
+    Span s1;
+    if (kMode == 2) {
+        SpanOct s0;
+        span_load_oct(s0, lv.p[0], p, c0, 0, W2);
+        span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
+        span_taps_oct<true>(s0, nullptr, 0, HW, b, 0, W2, tp);
+    } else {
+        Span s0;
+        span_load(s0, lv.p[0], p, npix, c0, 0, W2, true);
+        span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
+        span_taps_reg<true, kPadded>(s0, nullptr, 0, HW, 4, b, 0, W2, tp);
+    }
+    span_taps_reg<true, kPadded>(s1, nullptr, 0, HW, 4, b, 2, W2 >> 2, tp + 18);
     float* o = out + (long long)b * Cout * HW + hw;
     for (int oc = 0; oc < Cout; oc += 4) {
         float acc[4] = {s_b[oc], s_b[oc + 1], s_b[oc + 2], s_b[oc + 3]};
@@ -574,8 +693,14 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
             if (carve >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_r4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             attr_done = true;
         }
-        if (num_levels == 4)     // the standard configuration: span in registers, no shared memory (+2 % in the step)
-            corr_lookup_r4x4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
+        // W2 % 16 == 0: the rows of levels 0 and 2 start on 16-byte boundaries (no bounds predicates); with a 32-byte
+        // aligned level 0 its span comes as 32-byte loads
+        if (num_levels == 4 && W2 % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
+            corr_lookup_r4x4o_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
+        else if (num_levels == 4 && W2 % 16 == 0)
+            corr_lookup_r4x4_kernel<true><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
+        else if (num_levels == 4)     // the standard configuration: span in registers, no shared memory (+2 % in the step)
+            corr_lookup_r4x4_kernel<false><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
         else
             corr_lookup_r4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels);
     } else {
@@ -604,11 +729,20 @@ extern "C" int tcs_corr_lookup_encode(const float* lvl0, const float* lvl1, cons
     static bool attr_done = false;
     if (!attr_done) {
         const int carve = carveout_percent("TCS_CARVE_LOOKUP_ENC", 25);
-        if (carve >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        if (carve >= 0) {
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        }
         attr_done = true;
     }
-    corr_lookup_encode_kernel<<<grid, kLookThreads, 0, static_cast<cudaStream_t>(stream)>>>(lp, coords, coords_bstride, weight, bias, out,
-                                                                                            H * W1, W2, Cout, relu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (W2 % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
+        corr_lookup_encode_kernel<2><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, weight, bias, out, H * W1, W2, Cout, relu);
+    else if (W2 % 16 == 0)
+        corr_lookup_encode_kernel<1><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, weight, bias, out, H * W1, W2, Cout, relu);
+    else
+        corr_lookup_encode_kernel<0><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, weight, bias, out, H * W1, W2, Cout, relu);
     TCS_CHECK_LAUNCH("tcs_corr_lookup_encode");
     return 0;
 }

@@ -183,6 +183,31 @@ def test_lookup_integer_coords_return_volume_entries(tcs):
         assert_close(out[0, k + 4][:, w1], vol[0][:, w1, w1 + k], rtol=1e-5, atol=2e-6, what="tap %d" % k)
 
 
+def test_lookup_level0_alignment_variants_agree(tcs):
+    """W2 % 16 == 0 picks the predicate-free kernels: 32-byte loads when level 0 is 32-byte aligned, 16-byte loads
+    otherwise.  Both must reproduce the oracle (and hence each other) bit for bit on the same volume."""
+    B, H, W = 2, 24, 160
+    f1, f2 = make_fmaps(B, 128, H, W, 5)
+    blk = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), num_levels=4, radius=4, precision="fp32")
+    assert blk._levels[0].data_ptr() % 32 == 0
+    coords = make_coords(B, H, W, 9).cuda()
+    w = torch.randn(64, 36, device="cuda") * 0.2
+    out_oct = blk(coords)
+    enc_oct = blk.lookup_encoded(coords, w)
+    n0 = blk._levels[0].numel()
+    shifted = torch.empty(n0 + 12, dtype=torch.float32, device="cuda")
+    lvl0 = shifted[4:4 + n0].view_as(blk._levels[0])             # 16-byte aligned, not 32
+    assert lvl0.data_ptr() % 32 == 16
+    lvl0.copy_(blk._levels[0])
+    blk._levels[0] = lvl0
+    out_quad = blk(coords)
+    enc_quad = blk.lookup_encoded(coords, w)
+    assert torch.equal(out_oct, out_quad)
+    assert torch.equal(enc_oct, enc_quad)
+    ref = orc.corr_lookup([host(x) for x in blk._levels], host(coords), 4)
+    assert_close(host(out_oct), ref, what="lookup, both alignments")
+
+
 def test_lookup_coords_view_and_nan(tcs):
     g = load_golden("corr_small")
     blk = tcs.CorrBlock1D.from_levels([cuda(g["level%d" % l]) for l in range(4)])
