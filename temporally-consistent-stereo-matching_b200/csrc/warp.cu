@@ -222,6 +222,83 @@ warp_splat_kernel(const float* __restrict__ fmap, const float* __restrict__ disp
     }
 }
 
+// ---- forward warp, kernel C': the same when the caller wants only the cost (tc_stereo.py:139-140 is all the model
+// reads of the warped features).  No warped-feature tile and no per-channel divisions: the CURRENT features are
+// transposed through shared memory instead, each warp walks its pixels with the accumulator row straight from
+// global memory (scaled by one reciprocal per pixel, so the range stays that of the normalised features), and the
+// three sums of the cosine are warp-reduced in a fixed order.
+template <int kGroups>
+__global__ void __launch_bounds__(kWarpThreads)
+warp_cost_kernel(const float* __restrict__ accum, const float* __restrict__ cur_fmap, float* __restrict__ out_disp,
+                 float* __restrict__ out_mask, float* __restrict__ out_cost, const int* __restrict__ ctrl, int H, int W) {
+    if (ctrl[kCtrlFallback] == 0) return;   // the gather kernel handled this frame
+    constexpr int C = kGroups * 128;
+    constexpr int CP = C + 4;
+    constexpr int kPerWarp = C / 8;
+    constexpr int kPx = kTileW / 8;
+    extern __shared__ float tile[];            // [C][33]: current features, channel-major
+    const int w0 = blockIdx.x * kTileW, h = blockIdx.y, b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = w0 + lane;
+    const bool in_w = w < W;
+    const size_t plane = (size_t)H * W;
+    const size_t base = ((size_t)b * C * H + h) * W + w;
+    float f[kPerWarp];
+#pragma unroll
+    for (int k = 0; k < kPerWarp; ++k)
+        f[k] = in_w ? ldg_stream_f1(cur_fmap + base + (size_t)(warp + 8 * k) * plane) : 0.0f;
+    float2 tail[kPx];
+    float4 a[kPx][kGroups];
+#pragma unroll
+    for (int i = 0; i < kPx; ++i) {
+        const int wl = warp * kPx + i;
+        const bool live = w0 + wl < W;
+        const float* src = accum + (((size_t)b * H + h) * W + (live ? w0 + wl : 0)) * CP;
+        tail[i] = live ? *reinterpret_cast<const float2*>(src + C) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j)
+            a[i][j] = live ? ldg_stream_f4(reinterpret_cast<const float4*>(src + j * 128 + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kPerWarp; ++k) tile[(warp + 8 * k) * 33 + lane] = f[k];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kPx; ++i) {
+        const int wl = warp * kPx + i;
+        const bool live = w0 + wl < W;
+        const float nrm = fmaxf(tail[i].y, 1e-7f);              // clip(1e-7, None)   softsplat.py:268
+        const float m = (tail[i].y != 0.0f) ? 1.0f : 0.0f;      // softsplat.py:258
+        const float r = __fdiv_rn(1.0f, nrm);
+        float dot = 0.0f, s1 = 0.0f, sw = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j) {
+            const float av[4] = {a[i][j].x, a[i][j].y, a[i][j].z, a[i][j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                        // accumulator position 128j + 4 lane + q  <->  channel below
+                const float fv = tile[(lane + 32 * (4 * j + q)) * 33 + wl];
+                const float v = __fmul_rn(av[q], r);
+                dot = fmaf(fv, v, dot);
+                s1 = fmaf(fv, fv, s1);
+                sw = fmaf(v, v, sw);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            sw += __shfl_xor_sync(0xffffffffu, sw, o);
+        }
+        if (lane == 0 && live) {
+            const size_t idx = ((size_t)b * H + h) * W + w0 + wl;
+            out_disp[idx] = __fdiv_rn(tail[i].x, nrm);
+            out_mask[idx] = m;
+            // sum_c normalize(f)_c * normalize(v)_c  (F.normalize eps 1e-12), times the splat mask (tc_stereo.py:139-140)
+            const float den = __fmul_rn(fmaxf(sqrtf(s1), 1e-12f), fmaxf(sqrtf(sw), 1e-12f));
+            out_cost[idx] = __fmul_rn(__fdiv_rn(dot, den), m);
+        }
+    }
+}
+
 // ---- forward warp, kernel C: normalise, mask, NCHW re-layout, matching cost -------------------------------------
 template <int kGroups>
 __global__ void __launch_bounds__(kWarpThreads)
@@ -725,19 +802,24 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
     const dim3 grid(ceil_div(W, kTileW), H, B);
     const size_t smem_splat = (size_t)kTileW * (C + 1) * sizeof(float);
     const size_t smem_fin = ((size_t)C * 33 + 8 * 32 * 3 + 32) * sizeof(float);
+    const size_t smem_cost = (size_t)C * 33 * sizeof(float);
 #define TCS_WARP_CASE(G)                                                                                              \
     case G: {                                                                                                         \
         static bool attr_done = false;                                                                                \
         if (!attr_done) {                                                                                             \
             TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_splat_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_splat)); \
             TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_finalize_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin)); \
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_cost_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cost)); \
             { const int cv = carveout_percent("TCS_CARVE_SPLAT", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_splat_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); } \
             { const int cv = carveout_percent("TCS_CARVE_FINALIZE", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_finalize_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); } \
             attr_done = true;                                                                                         \
         }                                                                                                             \
         warp_splat_kernel<G><<<grid, kWarpThreads, smem_splat, s>>>(fmap, disp1, tx, ty, valid, ctrl, accum, B, H, W); \
         TCS_CHECK_LAUNCH("tcs_warp_forward(splat)");                                                                  \
-        warp_finalize_kernel<G><<<grid, kWarpThreads, smem_fin, s>>>(accum, cur_fmap, out_disp, out_fmap, out_mask, out_cost, ctrl, H, W); \
+        if (out_fmap == nullptr && out_cost != nullptr && cur_fmap != nullptr)                                        \
+            warp_cost_kernel<G><<<grid, kWarpThreads, smem_cost, s>>>(accum, cur_fmap, out_disp, out_mask, out_cost, ctrl, H, W); \
+        else                                                                                                          \
+            warp_finalize_kernel<G><<<grid, kWarpThreads, smem_fin, s>>>(accum, cur_fmap, out_disp, out_fmap, out_mask, out_cost, ctrl, H, W); \
         TCS_CHECK_LAUNCH("tcs_warp_forward(finalize)");                                                               \
     } break;
     switch (C / 128) {

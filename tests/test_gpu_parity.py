@@ -360,6 +360,12 @@ def test_warp_full_size(tcs, B, H, W, per_sample, deterministic):
     assert_close(host(f), rf, rtol=1e-4, atol=1e-4, what="warped features")
     rc = orc.matching_cost(cur.numpy(), host(f), host(m))
     assert_close(host(c), rc, rtol=1e-5, atol=2e-6, what="matching cost")
+    if not deterministic:                      # the cost-only kernel (no warped-feature output) gives the same cost
+        d2, f2, m2, c2 = tcs.warp_with_cost(disp.cuda(), fmap.cuda(), cuda(T), cuda(K), cuda(Kinv), cuda(base),
+                                            cur_fmap=cur.cuda(), per_sample_mean=per_sample, want_fmap=False)
+        assert f2 is None and torch.equal(m2, m)
+        assert_close(host(d2), rd, rtol=1e-4, atol=1e-4, what="warped disparity (cost-only path)")
+        assert_close(host(c2), rc, rtol=1e-5, atol=2e-6, what="matching cost (cost-only path)")
 
 
 @pytest.mark.parametrize("kind", ["large_flow", "irregular_flow"])

@@ -111,6 +111,8 @@ fwd, inv = fwd.to(dev), inv.to(dev)
 base = torch.full((B, 1), 0.25, device=dev)
 dd = disp.to(dev)
 timeit("warp+cost", lambda: tcs_b200.warp_with_cost(dd, f1, fwd, K, K_inv, base, cur_fmap=f2, per_sample_mean=True), npix * (4 + 1024 * 3 + 12))
+timeit("warp+cost[no fmap]", lambda: tcs_b200.warp_with_cost(dd, f1, fwd, K, K_inv, base, cur_fmap=f2, per_sample_mean=True, want_fmap=False),
+       npix * (4 + 1024 * 2 + 12))
 grid = tcs_b200.get_backward_grid(dd, inv, K, K_inv, base)
 timeit("backward_grid", lambda: tcs_b200.get_backward_grid(dd, inv, K, K_inv, base), npix * 12)
 for i in range(3):
