@@ -342,11 +342,14 @@ corr_lookup_r4x4_kernel(const LevelPtrs lv, const float* __restrict__ coords, lo
     const long long p = (long long)b * HW + hw;
     float c0 = __ldg(coords + b * coords_bstride + hw);
     if (kPadded) c0 = sane_coord(c0);
-    Span s0, s1;
-    span_load(s0, lv.p[0], p, npix, c0, 0, W2, true);
-    span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
-    span_taps_reg<false, kPadded>(s0, out, hw, HW, 4, b, 0, W2, nullptr);
-    span_taps_reg<false, kPadded>(s1, out, hw, HW, 4, b, 2, W2 >> 2, nullptr);
+    Span sp;                                   // blockIdx.y = level pair (see corr_lookup_r4x4o_kernel)
+    if (blockIdx.y == 0) {
+        span_load(sp, lv.p[0], p, npix, c0, 0, W2, true);
+        span_taps_reg<false, kPadded>(sp, out, hw, HW, 4, b, 0, W2, nullptr);
+    } else {
+        span_load(sp, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
+        span_taps_reg<false, kPadded>(sp, out, hw, HW, 4, b, 2, W2 >> 2, nullptr);
+    }
 }
 
 // One thread per pixel, both level pairs: the loads of pair 1 (levels 2,3) are issued before the taps of pair 0
@@ -701,14 +704,13 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
         }
         // W2 % 16 == 0: the rows of levels 0 and 2 start on 16-byte boundaries (no bounds predicates); with a 32-byte
         // aligned level 0 its span comes as 32-byte loads
-        if (num_levels == 4 && W2 % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0) {
-            dim3 grid2(grid.x, 2, B);
+        const dim3 grid2(grid.x, 2, B);            // 4 levels: one thread per (pixel, level pair)
+        if (num_levels == 4 && W2 % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
             corr_lookup_r4x4o_kernel<<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
-        }
         else if (num_levels == 4 && W2 % 16 == 0)
-            corr_lookup_r4x4_kernel<true><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
-        else if (num_levels == 4)     // the standard configuration: span in registers, no shared memory (+2 % in the step)
-            corr_lookup_r4x4_kernel<false><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
+            corr_lookup_r4x4_kernel<true><<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
+        else if (num_levels == 4)     // any width: span in registers, no shared memory (+2 % in the step)
+            corr_lookup_r4x4_kernel<false><<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
         else
             corr_lookup_r4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels);
     } else {
