@@ -158,8 +158,8 @@ long long tcs_warp_scratch_bytes(int B, int C, int H, int W);
  *   out_cost = sum_c normalize(cur_fmap)*normalize(out_fmap) * out_mask   (ref: core/tc_stereo.py:139-140)
  *   flags     TCS_WARP_PER_SAMPLE_MEAN: each sample's own mean disparity for the soft-splat metric instead of the
  *             reference's batch-global mean (geo_utils.py:193) — for batching independent sequences.
- *             TCS_WARP_DETERMINISTIC: collect the splat from the target's side (fixed summation order, no global
- *             accumulator); falls back to the atomic scatter on the device when the flow is too large or irregular.
+ *             TCS_WARP_DETERMINISTIC: collect the splat from the target's side through per-target contributor lists
+ *             sorted by source pixel (fixed summation order, no accumulator, no floating-point atomics; any flow).
  *   scratch   tcs_warp_scratch_bytes() bytes, 16-byte aligned. */
 int tcs_warp_forward(const float* disp, const float* fmap, const float* rel_T, const float* K,
                      const float* K_inv, const float* baseline, const float* cur_fmap,

@@ -28,10 +28,6 @@ namespace tcs {
 constexpr int kTileW = 32;
 constexpr int kWarpThreads = 256;
 
-// control words in the scratch header (zeroed with the sums)
-constexpr int kCtrlMaxFlowX = 0, kCtrlMaxFlowY = 1, kCtrlFallback = 2;
-constexpr int kGatherMaxR = 24;        // search radius (source pixels) the gather kernel is willing to scan
-constexpr int kGatherMaxEntries = 48;  // distinct (dx, dy) offsets a 32-pixel target segment may draw from
 
 struct Cam {
     float K[9], Ki[9], T[12], bf;
@@ -79,12 +75,11 @@ __global__ void __launch_bounds__(256)
 warp_geometry_kernel(const float* __restrict__ disp, const float* __restrict__ rel_T, const float* __restrict__ K,
                      const float* __restrict__ K_inv, const float* __restrict__ baseline,
                      float* __restrict__ disp1, float* __restrict__ tx, float* __restrict__ ty,
-                     float* __restrict__ valid, double* __restrict__ sums, int* __restrict__ ctrl, int H, int W) {
+                     float* __restrict__ valid, double* __restrict__ sums, int H, int W) {
     const int b = blockIdx.y;
     const int HW = H * W;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double local = 0.0;
-    float fmax_x = 0.0f, fmax_y = 0.0f;   // largest |target - source| of a pixel that will be splatted
     if (i < HW) {
         const Cam c = load_cam(rel_T, K, K_inv, baseline, b);
         const int y = i / W, x = i - y * W;
@@ -105,21 +100,7 @@ warp_geometry_kernel(const float* __restrict__ disp, const float* __restrict__ r
         ty[o] = fy_;
         valid[o] = ok ? 1.0f : 0.0f;
         local = (double)d1;
-        if (ok && isfinite(fx_) && isfinite(fy_)) {
-            fmax_x = fabsf(fx_ - (float)x);
-            fmax_y = fabsf(fy_ - (float)y);
-        }
     }
-    // non-negative floats order like their bit patterns: one atomicMax per warp
-    fmax_x = fmaxf(fmax_x, 0.0f);
-    fmax_y = fmaxf(fmax_y, 0.0f);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        fmax_x = fmaxf(fmax_x, __shfl_xor_sync(0xffffffffu, fmax_x, o));
-        fmax_y = fmaxf(fmax_y, __shfl_xor_sync(0xffffffffu, fmax_y, o));
-    }
-    __shared__ float wmax[2][8];
-    if ((threadIdx.x & 31) == 0) { wmax[0][threadIdx.x >> 5] = fmax_x; wmax[1][threadIdx.x >> 5] = fmax_y; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     __shared__ double wsum[8];
@@ -127,11 +108,8 @@ warp_geometry_kernel(const float* __restrict__ disp, const float* __restrict__ r
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0;
-        float mx = 0.0f, my = 0.0f;
-        for (int w = 0; w < 8; ++w) { s += wsum[w]; mx = fmaxf(mx, wmax[0][w]); my = fmaxf(my, wmax[1][w]); }
+        for (int w = 0; w < 8; ++w) s += wsum[w];
         atomicAdd(sums + b, s);
-        if (mx > 0.0f) atomicMax(ctrl + kCtrlMaxFlowX, __float_as_int(mx));
-        if (my > 0.0f) atomicMax(ctrl + kCtrlMaxFlowY, __float_as_int(my));
     }
 }
 
@@ -170,9 +148,8 @@ __device__ __forceinline__ void load_tile_transposed(const float* __restrict__ f
 template <int kGroups>  // C / 128
 __global__ void __launch_bounds__(kWarpThreads)
 warp_splat_kernel(const float* __restrict__ fmap, const float* __restrict__ disp1, const float* __restrict__ tx,
-                  const float* __restrict__ ty, const float* __restrict__ wgt, const int* __restrict__ ctrl,
+                  const float* __restrict__ ty, const float* __restrict__ wgt,
                   float* __restrict__ accum, int B, int H, int W) {
-    if (ctrl[kCtrlFallback] == 0) return;   // deterministic mode and the gather kernel handled this frame
     constexpr int C = kGroups * 128;
     constexpr int CP = C + 4;
     constexpr int pitch = C + 1;
@@ -230,8 +207,7 @@ warp_splat_kernel(const float* __restrict__ fmap, const float* __restrict__ disp
 template <int kGroups>
 __global__ void __launch_bounds__(kWarpThreads)
 warp_cost_kernel(const float* __restrict__ accum, const float* __restrict__ cur_fmap, float* __restrict__ out_disp,
-                 float* __restrict__ out_mask, float* __restrict__ out_cost, const int* __restrict__ ctrl, int H, int W) {
-    if (ctrl[kCtrlFallback] == 0) return;   // the gather kernel handled this frame
+                 float* __restrict__ out_mask, float* __restrict__ out_cost, int H, int W) {
     constexpr int C = kGroups * 128;
     constexpr int CP = C + 4;
     constexpr int kPerWarp = C / 8;
@@ -304,8 +280,7 @@ template <int kGroups>
 __global__ void __launch_bounds__(kWarpThreads)
 warp_finalize_kernel(const float* __restrict__ accum, const float* __restrict__ cur_fmap,
                      float* __restrict__ out_disp, float* __restrict__ out_fmap, float* __restrict__ out_mask,
-                     float* __restrict__ out_cost, const int* __restrict__ ctrl, int H, int W) {
-    if (ctrl[kCtrlFallback] == 0) return;   // the gather kernel handled this frame
+                     float* __restrict__ out_cost, int H, int W) {
     constexpr int C = kGroups * 128;
     constexpr int CP = C + 4;
     extern __shared__ float tile[];            // [C][33] then red[8][32][3] then maskv[32]
@@ -396,17 +371,12 @@ warp_finalize_kernel(const float* __restrict__ accum, const float* __restrict__ 
 
 // ---- forward warp, kernel A2: soft-splat weight of every source pixel -----------------------------------------
 // wgt = valid * exp(clamp(disp' - mean, -50, 50)), 0 for pixels the splat skips (invalid, non-finite target).
-// Also decides whether the gather kernel can handle the frame (flow within its search radius).
 __global__ void __launch_bounds__(256)
 warp_weight_kernel(const float* __restrict__ disp1, const float* __restrict__ tx, const float* __restrict__ ty,
-                   float* __restrict__ valid_to_wgt, const double* __restrict__ sums, int* __restrict__ ctrl,
+                   float* __restrict__ valid_to_wgt, const double* __restrict__ sums,
                    int B, int HW, int per_sample_mean) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-        const float fx = __int_as_float(ctrl[kCtrlMaxFlowX]), fy = __int_as_float(ctrl[kCtrlMaxFlowY]);
-        if (!(fx <= (float)(kGatherMaxR - 2)) || !(fy <= (float)(kGatherMaxR - 2))) atomicExch(ctrl + kCtrlFallback, 1);
-    }
     if (i >= HW) return;
     // softsplat metric: disparity minus its mean (geo_utils.py:193); batch-global unless asked otherwise
     double s = 0.0, n;
@@ -425,198 +395,226 @@ warp_weight_kernel(const float* __restrict__ disp1, const float* __restrict__ tx
     valid_to_wgt[o] = w;
 }
 
-// ---- forward warp, kernel B' (TCS_WARP_DETERMINISTIC): the splat as a gather ---------------------------------------------------
-// A forward splat scatters every source pixel into the 4 integer neighbours of its target.  Frame-to-frame flow is
-// a few pixels, so the same sum can be collected from the target's side: one warp owns 32 consecutive target pixels
-// of a row, scans the (2Rx+1) x (2Ry+1) source offsets the frame's largest flow allows, keeps the offsets (dx, dy)
-// from which at least one of its targets receives a non-zero weight (a handful when the flow is smooth), and then
-// walks the channels: out[c] = sum_e w_e * fmap[c][y+dy_e][x+dx_e] / clip(norm).  Everything stays NCHW (lanes
-// are consecutive x: coalesced loads and stores, no transposes), there is no accumulator in global memory, no
-// memset, no atomics, the sum order is fixed (the result is deterministic, unlike the scatter), and the
-// normalisation, the mask and the matching cost are produced in the same pass.  Frames whose flow exceeds the
-// search radius, or segments that need more than kGatherMaxEntries offsets, raise the fallback flag and the scatter
-// kernels redo the frame.  It is latency-bound (693-769 us against 452 us for the scatter at 540p x 8), so it is
-// the opt-in deterministic mode, not the default.
-constexpr int kGatherWarps = 4;
-constexpr int kGatherRegEntries = 12;   // offsets whose weights are held in registers (the common, smooth-flow case)
-constexpr int kGatherWinFloats = 4 * 1024;   // staged source window: 4 planes (weight, target x, target y, disp')
+// ---- forward warp, list formulation ---------------------------------------------------------------------------
+// The scatter above moves every accumulator byte through DRAM four times (memset, red read-modify-write, finalize
+// read).  The same sum can be collected from the target's side without any accumulator if each target knows who
+// feeds it.  So: (1) count the contributions each target receives (one int atomic per corner instead of 65 vector
+// reds), (2) prefix-sum the counts into list offsets (per row, then across rows), (3) fill the lists with
+// (source pixel, e * bilinear weight), (4) one pass over the targets: walk the list, gather the source features
+// straight from the NCHW map (lanes are neighbouring targets, their sources are neighbours too: coalesced), divide
+// by the summed weights, write mask / disparity / features and fold the matching cost in.  Any flow field is
+// handled (the lists are exact, CSR) and each list is sorted by source index first, which fixes the summation order
+// (the reference's atomic scatter is unordered): this is the TCS_WARP_DETERMINISTIC mode.  The gather of NCHW
+// features at per-lane source pixels costs ~6 sectors per request with i.i.d. flow and the kernel is latency-bound
+// (636 us against 374 us for the scatter at 540p x 8), so the scatter stays the default.
+struct SplatCorners {
+    int t[4];      // target pixel index inside the sample, -1 when outside the image or the product is zero
+    float w[4];    // e * bilinear weight
+};
 
-// sum over the entries of w_e * fmap[c][.. + off_e] for kCh consecutive channels, the first kN entries held in
-// registers.  The loads are UNCONDITIONAL (an entry that does not feed this lane has offset 0 = the lane's own
-// pixel, always in range, and its value is replaced by 0), so all kN * kCh of them are independent and issued
-// back to back: the kernel is latency-bound and this is what buys memory-level parallelism.
-template <int kN, int kCh>
-__device__ __forceinline__ void gather_block(const float* __restrict__ src, size_t plane, const float (&w)[kGatherRegEntries],
-                                             const int (&off)[kGatherRegEntries], float (&acc)[kCh]) {
-    float v[kN][kCh];
+__device__ __forceinline__ SplatCorners splat_corners(float e, float fx_, float fy_, int H, int W) {
+    SplatCorners c;
+    const int nwx = (int)floorf(fx_), nwy = (int)floorf(fy_);
+    const int sex = nwx + 1, sey = nwy + 1;
+    // softsplat.py:314-317
+    const float wt[4] = {__fmul_rn(__fsub_rn((float)sex, fx_), __fsub_rn((float)sey, fy_)),    // NW
+                         __fmul_rn(__fsub_rn(fx_, (float)nwx), __fsub_rn((float)sey, fy_)),    // NE
+                         __fmul_rn(__fsub_rn((float)sex, fx_), __fsub_rn(fy_, (float)nwy)),    // SW
+                         __fmul_rn(__fsub_rn(fx_, (float)nwx), __fsub_rn(fy_, (float)nwy))};   // SE
+    const int txs[4] = {nwx, sex, nwx, sex};
+    const int tys[4] = {nwy, nwy, sey, sey};
 #pragma unroll
-    for (int e = 0; e < kN; ++e)
-#pragma unroll
-        for (int k = 0; k < kCh; ++k) v[e][k] = ldg_ordered_f1(src + (size_t)k * plane + off[e]);
-#pragma unroll
-    for (int e = 0; e < kN; ++e)
-#pragma unroll
-        for (int k = 0; k < kCh; ++k) acc[k] = fmaf((w[e] != 0.0f) ? v[e][k] : 0.0f, w[e], acc[k]);
+    for (int k = 0; k < 4; ++k) {
+        const bool in = txs[k] >= 0 && txs[k] < W && tys[k] >= 0 && tys[k] < H;
+        c.w[k] = __fmul_rn(e, wt[k]);
+        c.t[k] = (in && c.w[k] != 0.0f) ? tys[k] * W + txs[k] : -1;   // a zero product adds nothing, not even to the mask
+    }
+    return c;
 }
 
-__global__ void __launch_bounds__(kGatherWarps * 32)
-warp_gather_kernel(const float* __restrict__ fmap, const float* __restrict__ disp1, const float* __restrict__ tx,
-                   const float* __restrict__ ty, const float* __restrict__ wgt, const float* __restrict__ cur_fmap,
-                   float* __restrict__ out_disp, float* __restrict__ out_fmap, float* __restrict__ out_mask,
-                   float* __restrict__ out_cost, int* __restrict__ ctrl, int C, int H, int W) {
-    __shared__ float s_w[kGatherWarps][kGatherMaxEntries][32];
-    __shared__ int s_off[kGatherWarps][kGatherMaxEntries];
-    __shared__ float s_win[kGatherWinFloats];
-    if (ctrl[kCtrlFallback] != 0) return;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int Y0 = blockIdx.y * kGatherWarps;
-    const int Y = Y0 + wib;
-    const int b = blockIdx.z;
-    const int X0 = blockIdx.x * 32;
-    const int X = X0 + lane;
-    const bool in_w = X < W;
-    const int Rx = min((int)ceilf(__int_as_float(ctrl[kCtrlMaxFlowX])) + 1, kGatherMaxR);
-    const int Ry = min((int)ceilf(__int_as_float(ctrl[kCtrlMaxFlowY])) + 1, kGatherMaxR);
-    const size_t pbase = (size_t)b * H * W;
-    float (*sw)[32] = s_w[wib];
-    int* soff = s_off[wib];
-
-    // ---- stage the CTA's source window (weight, target x, target y, disp') in shared memory when it fits
-    const int win_w = 32 + 2 * Rx, win_h = kGatherWarps + 2 * Ry;
-    const int win_n = win_w * win_h;
-    const bool staged = 4 * win_n <= kGatherWinFloats;
-    if (staged) {
-        for (int i = threadIdx.x; i < win_n; i += kGatherWarps * 32) {
-            const int wy = i / win_w, wx = i - wy * win_w;
-            const int y = Y0 - Ry + wy, x = X0 - Rx + wx;
-            float e = 0.0f, fx_ = 0.0f, fy_ = 0.0f, d1 = 0.0f;
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                const size_t so = pbase + (size_t)y * W + x;
-                e = __ldg(wgt + so);
-                fx_ = __ldg(tx + so);
-                fy_ = __ldg(ty + so);
-                d1 = __ldg(disp1 + so);
-            }
-            s_win[i] = e;
-            s_win[win_n + i] = fx_;
-            s_win[2 * win_n + i] = fy_;
-            s_win[3 * win_n + i] = d1;
+// (1) and (3): kFill = false counts, kFill = true appends (cnt then serves as the cursor and ends at zero).
+template <bool kFill>
+__global__ void __launch_bounds__(256)
+warp_list_kernel(const float* __restrict__ wgt, const float* __restrict__ tx, const float* __restrict__ ty,
+                 int* __restrict__ cnt, const int* __restrict__ start, int2* __restrict__ entries, int H, int W) {
+    const int b = blockIdx.y;
+    const int HW = H * W;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW) return;
+    const size_t o = (size_t)b * HW + i;
+    const float e = __ldg(wgt + o);
+    if (e == 0.0f) return;
+    const SplatCorners c = splat_corners(e, __ldg(tx + o), __ldg(ty + o), H, W);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (c.t[k] < 0) continue;
+        const size_t t = (size_t)b * HW + c.t[k];
+        if (!kFill) {
+            atomicAdd(cnt + t, 1);
+        } else {
+            const int slot = atomicSub(cnt + t, 1) - 1;
+            entries[(size_t)__ldg(start + t) + slot] = make_int2(i, __float_as_int(c.w[k]));
         }
+    }
+}
+
+// (2a) contributions per target row.
+__global__ void __launch_bounds__(256)
+warp_rowsum_kernel(const int* __restrict__ cnt, int* __restrict__ rowtot, int W) {
+    const int row = blockIdx.x;
+    int s = 0;
+    for (int x = threadIdx.x; x < W; x += 256) s += cnt[(size_t)row * W + x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ int ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += ws[w];
+        rowtot[row] = t;
+    }
+}
+
+// (2b) list offsets: rows before this one (summed here: a few thousand ints) + exclusive scan inside the row.
+__global__ void __launch_bounds__(256)
+warp_offsets_kernel(const int* __restrict__ cnt, const int* __restrict__ rowtot, int* __restrict__ start, int W, int rows) {
+    const int row = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int ws[8];
+    __shared__ int carry;
+    int s = 0;
+    for (int r = threadIdx.x; r < row; r += 256) s += rowtot[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) ws[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += ws[w];
+        carry = t;
     }
     __syncthreads();
-    if (Y >= H) return;                          // warp-uniform
+    for (int x0 = 0; x0 < W; x0 += 256) {
+        const int x = x0 + threadIdx.x;
+        const int v = (x < W) ? cnt[(size_t)row * W + x] : 0;
+        int inc = v;                                            // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        const int base = carry;
+        __syncthreads();                                        // everyone has read carry and the previous ws
+        if (lane == 31) ws[warp] = inc;
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += ws[w];
+        if (x < W) start[(size_t)row * W + x] = base + before + inc - v;
+        if (threadIdx.x == 255) carry = base + before + inc;
+        __syncthreads();
+    }
+    if (row == rows - 1 && threadIdx.x == 0) start[(size_t)rows * W] = carry;   // one past the end
+}
 
-    // ---- phase A: which source offsets feed this segment, and with what weight per target
-    int n_ent = 0;
-    float norm = 0.0f, dsum = 0.0f;
-    const float Xf = (float)X, Yf = (float)Y;
-    for (int dy = -Ry; dy <= Ry; ++dy) {
-        const int y = Y + dy;
-        if (y < 0 || y >= H) continue;           // warp-uniform
-        for (int dx = -Rx; dx <= Rx; ++dx) {
-            const int x = X + dx;
-            float w = 0.0f, d1 = 0.0f;
-            if (in_w && x >= 0 && x < W) {
-                float e, fx_, fy_;
-                if (staged) {
-                    const int i = (wib + Ry + dy) * win_w + (lane + Rx + dx);
-                    e = s_win[i]; fx_ = s_win[win_n + i]; fy_ = s_win[2 * win_n + i]; d1 = s_win[3 * win_n + i];
-                } else {
-                    const size_t so = pbase + (size_t)y * W + x;
-                    e = __ldg(wgt + so); fx_ = __ldg(tx + so); fy_ = __ldg(ty + so); d1 = __ldg(disp1 + so);
-                }
-                if (e != 0.0f) {
-                    const float nwx = floorf(fx_), nwy = floorf(fy_);
-                    // bilinear weights of softsplat.py:314-317, seen from the target: x part * y part
-                    float wx = 0.0f, wy = 0.0f;
-                    if (Xf == nwx) wx = __fsub_rn(__fadd_rn(nwx, 1.0f), fx_);
-                    else if (Xf == __fadd_rn(nwx, 1.0f)) wx = __fsub_rn(fx_, nwx);
-                    if (Yf == nwy) wy = __fsub_rn(__fadd_rn(nwy, 1.0f), fy_);
-                    else if (Yf == __fadd_rn(nwy, 1.0f)) wy = __fsub_rn(fy_, nwy);
-                    w = __fmul_rn(e, __fmul_rn(wx, wy));
-                }
-            }
-            if (__any_sync(0xffffffffu, w != 0.0f)) {
-                if (n_ent < kGatherMaxEntries) {
-                    sw[n_ent][lane] = w;
-                    if (lane == 0) soff[n_ent] = dy * W + dx;
-                }
-                ++n_ent;
-                norm = __fadd_rn(norm, w);
-                dsum = fmaf(d1, w, dsum);
-            }
-        }
-    }
-    if (n_ent > kGatherMaxEntries) {             // flow too irregular for the gather: let the scatter path redo the frame
-        if (lane == 0) atomicExch(ctrl + kCtrlFallback, 1);
-        return;
-    }
-    __syncwarp();
-    const float nrm = fmaxf(norm, 1e-7f);                       // clip(1e-7, None)   softsplat.py:268
-    const float m = (norm != 0.0f) ? 1.0f : 0.0f;               // softsplat.py:258
-    const size_t po = pbase + (size_t)Y * W + X;
-    if (in_w) {
-        out_disp[po] = __fdiv_rn(dsum, nrm);
-        out_mask[po] = m;
-    }
-
-    // ---- phase B: channels
-    const size_t plane = (size_t)H * W;
-    const float* src = fmap + (size_t)b * C * plane + (size_t)Y * W + X;
-    const size_t obase = (size_t)b * C * plane + (size_t)Y * W + X;
-    const bool want_cost = (out_cost != nullptr) && (cur_fmap != nullptr);
-    float dot = 0.0f, s1 = 0.0f, s2 = 0.0f;
-    float wreg[kGatherRegEntries];
-    int offreg[kGatherRegEntries];
-#pragma unroll
-    for (int e = 0; e < kGatherRegEntries; ++e) {
-        wreg[e] = (e < n_ent) ? sw[e][lane] : 0.0f;
-        offreg[e] = (e < n_ent && wreg[e] != 0.0f) ? soff[e] : 0;   // lanes an entry does not feed read their own pixel
-    }
-    constexpr int kCh = 4;
-    const bool few = n_ent <= kGatherRegEntries / 2;              // warp-uniform
-    for (int c = 0; c < C; c += kCh) {
-        float acc[kCh];
-#pragma unroll
-        for (int k = 0; k < kCh; ++k) acc[k] = 0.0f;
-        const float* sc = src + (size_t)c * plane;
-        if (few) gather_block<kGatherRegEntries / 2, kCh>(sc, plane, wreg, offreg, acc);
-        else gather_block<kGatherRegEntries, kCh>(sc, plane, wreg, offreg, acc);
-        for (int e = kGatherRegEntries; e < n_ent; ++e) {       // the rare tail beyond the register-held entries
-            const float w = sw[e][lane];
-            const int off = soff[e];
-            if (w != 0.0f) {
-#pragma unroll
-                for (int k = 0; k < kCh; ++k) acc[k] = fmaf(__ldg(sc + (size_t)k * plane + off), w, acc[k]);
-            }
-        }
-        if (in_w) {
-#pragma unroll
-            for (int k = 0; k < kCh; ++k) {
-                const float v = __fdiv_rn(acc[k], nrm);
-                if (out_fmap != nullptr) stg_stream_f1(out_fmap + obase + (size_t)(c + k) * plane, v);
-                if (want_cost) {
-                    const float f = ldg_stream_f1(cur_fmap + obase + (size_t)(c + k) * plane);
-                    dot = fmaf(f, v, dot);
-                    s1 = fmaf(f, f, s1);
-                    s2 = fmaf(v, v, s2);
-                }
-            }
-        }
-    }
-    if (want_cost && in_w) {
-        // sum_c normalize(f)_c * normalize(v)_c  (F.normalize eps 1e-12), times the splat mask (tc_stereo.py:139-140)
-        const float den = __fmul_rn(fmaxf(sqrtf(s1), 1e-12f), fmaxf(sqrtf(s2), 1e-12f));
-        out_cost[po] = __fmul_rn(__fdiv_rn(dot, den), m);
+// (3b) TCS_WARP_DETERMINISTIC: order each list by source pixel.
+__global__ void __launch_bounds__(256)
+warp_sort_kernel(const int* __restrict__ start, int2* __restrict__ entries, long long npix) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npix) return;
+    const int s0 = start[t], n = start[t + 1] - s0;
+    int2* e = entries + s0;
+    for (int i = 1; i < n; ++i) {                               // insertion sort: lists are a handful of entries
+        const int2 key = e[i];
+        int j = i - 1;
+        while (j >= 0 && e[j].x > key.x) { e[j + 1] = e[j]; --j; }
+        e[j + 1] = key;
     }
 }
 
-// ---- fallback: zero the scatter accumulator (only when the gather kernel gave up) ------------------------------
-__global__ void __launch_bounds__(256)
-warp_zero_kernel(float4* __restrict__ accum, size_t n4, const int* __restrict__ ctrl) {
-    if (ctrl[kCtrlFallback] == 0) return;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) accum[i] = z;
+// (4) one block = 32 consecutive targets of a row (the lanes) x 8 channel slices (the warps: channels warp + 8k).
+template <int kGroups, bool kWantFmap>
+__global__ void __launch_bounds__(kWarpThreads)
+warp_collect_kernel(const float* __restrict__ fmap, const float* __restrict__ disp1, const int* __restrict__ start,
+                    const int2* __restrict__ entries, const float* __restrict__ cur_fmap, float* __restrict__ out_disp,
+                    float* __restrict__ out_fmap, float* __restrict__ out_mask, float* __restrict__ out_cost, int H, int W) {
+    constexpr int C = kGroups * 128;
+    constexpr int kPerWarp = C / 8;
+    constexpr int kE = 4;                       // list entries per round
+    __shared__ float red[8 * 32 * 3];
+    const int w0 = blockIdx.x * kTileW, h = blockIdx.y, b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = w0 + lane;
+    const bool in_w = w < W;
+    const size_t plane = (size_t)H * W;
+    const size_t tpix = ((size_t)b * H + h) * W + (in_w ? w : 0);
+    const int s0 = in_w ? __ldg(start + tpix) : 0;
+    const int n = in_w ? __ldg(start + tpix + 1) - s0 : 0;
+    const int n_max = __reduce_max_sync(0xffffffffu, n);
+    const float* fb = fmap + (size_t)b * C * plane + (size_t)warp * plane;   // this warp's first channel
+    const bool want_cost = out_cost != nullptr;
+
+    float acc[kPerWarp];
+#pragma unroll
+    for (int k = 0; k < kPerWarp; ++k) acc[k] = 0.0f;
+    float norm = 0.0f, dsum = 0.0f;
+    for (int j0 = 0; j0 < n_max; j0 += kE) {
+        const float* ptr[kE];
+        float wj[kE];
+        bool live[kE];
+#pragma unroll
+        for (int u = 0; u < kE; ++u) {
+            live[u] = j0 + u < n;
+            const int2 en = live[u] ? __ldg(entries + s0 + j0 + u) : make_int2(0, 0);
+            wj[u] = __int_as_float(en.y);                      // 0 for the padding of shorter lists
+            ptr[u] = fb + en.x;
+            norm = __fadd_rn(norm, wj[u]);
+            if (warp == 0 && live[u]) dsum = fmaf(__ldg(disp1 + (size_t)b * plane + en.x), wj[u], dsum);
+        }
+#pragma unroll
+        for (int k = 0; k < kPerWarp; ++k) {
+#pragma unroll
+            for (int u = 0; u < kE; ++u)
+                if (live[u]) acc[k] = fmaf(__ldg(ptr[u] + (size_t)(8 * k) * plane), wj[u], acc[k]);
+        }
+    }
+    const float nrm = fmaxf(norm, 1e-7f);                       // clip(1e-7, None)   softsplat.py:268
+    const float m = (norm != 0.0f) ? 1.0f : 0.0f;               // softsplat.py:258
+    const float rcp = __fdiv_rn(1.0f, nrm);
+    const size_t obase = ((size_t)b * C * H + h) * W + w + (size_t)warp * plane;
+    float dot = 0.0f, s1 = 0.0f, sw = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kPerWarp; ++k) {
+        const float v = kWantFmap ? __fdiv_rn(acc[k], nrm) : __fmul_rn(acc[k], rcp);
+        if (kWantFmap && in_w) stg_stream_f1(out_fmap + obase + (size_t)(8 * k) * plane, v);
+        if (want_cost) {
+            const float f = in_w ? ldg_stream_f1(cur_fmap + obase + (size_t)(8 * k) * plane) : 0.0f;
+            dot = fmaf(f, v, dot);
+            s1 = fmaf(f, f, s1);
+            sw = fmaf(v, v, sw);
+        }
+    }
+    if (warp == 0 && in_w) {
+        out_disp[tpix] = __fdiv_rn(dsum, nrm);
+        out_mask[tpix] = m;
+    }
+    if (!want_cost) return;
+    red[(warp * 32 + lane) * 3 + 0] = dot;
+    red[(warp * 32 + lane) * 3 + 1] = s1;
+    red[(warp * 32 + lane) * 3 + 2] = sw;
+    __syncthreads();
+    if (warp == 0 && in_w) {
+        dot = s1 = sw = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            dot += red[(k * 32 + lane) * 3 + 0];
+            s1 += red[(k * 32 + lane) * 3 + 1];
+            sw += red[(k * 32 + lane) * 3 + 2];
+        }
+        // sum_c normalize(f)_c * normalize(v)_c  (F.normalize eps 1e-12), times the splat mask (tc_stereo.py:139-140)
+        const float den = __fmul_rn(fmaxf(sqrtf(s1), 1e-12f), fmaxf(sqrtf(sw), 1e-12f));
+        out_cost[tpix] = __fmul_rn(__fdiv_rn(dot, den), m);
+    }
 }
 
 // ---- get_backward_grid ---------------------------------------------------------------------------------------------
@@ -730,18 +728,22 @@ grid_halve_kernel(const float* __restrict__ in, float* __restrict__ out, int H, 
 static size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
 
 struct WarpScratch {
-    size_t sums, accum, disp1, tx, ty, valid, total;
+    size_t sums, cnt, accum, disp1, tx, ty, valid, start, rowtot, entries, total;
 };
 static WarpScratch warp_scratch_layout(int B, int C, int H, int W) {
     WarpScratch s;
     const size_t npix = (size_t)B * H * W;
     s.sums = 0;
-    s.accum = align256((size_t)B * sizeof(double) + 64);   // per-sample sums, then the control words
+    s.cnt = align256((size_t)B * sizeof(double) + 64);     // per-sample sums, then the control words
+    s.accum = s.cnt + align256(npix * sizeof(int));        // contributions per target (list mode), zeroed with the header
     s.disp1 = s.accum + align256(npix * (C + 4) * sizeof(float));
     s.tx = s.disp1 + align256(npix * sizeof(float));
     s.ty = s.tx + align256(npix * sizeof(float));
     s.valid = s.ty + align256(npix * sizeof(float));
-    s.total = s.valid + align256(npix * sizeof(float));
+    s.start = s.valid + align256(npix * sizeof(float));
+    s.rowtot = s.start + align256((npix + 1) * sizeof(int));
+    s.entries = s.rowtot + align256((size_t)B * H * sizeof(int));
+    s.total = s.entries + align256(4 * npix * sizeof(int2));
     return s;
 }
 
@@ -776,28 +778,52 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
     float* ty = reinterpret_cast<float*>(base + L.ty);
     float* valid = reinterpret_cast<float*>(base + L.valid);
 
-    int* ctrl = reinterpret_cast<int*>(base + L.sums + (size_t)B * sizeof(double));
     const int per_sample_mean = (flags & TCS_WARP_PER_SAMPLE_MEAN) ? 1 : 0;
-    const bool gather = (flags & TCS_WARP_DETERMINISTIC) != 0;
-    // scatter (default): zero sums + control words + accumulator and preset the "scatter" flag;
-    // gather: zero only the header; the accumulator is zeroed by a kernel, and only if the gather gives up
-    TCS_CHECK_CUDA(cudaMemsetAsync(base, 0, gather ? L.accum : L.disp1, s));
-    if (!gather) TCS_CHECK_CUDA(cudaMemsetAsync(ctrl + kCtrlFallback, 1, 1, s));
-    {
-        dim3 grid(ceil_div(H * W, 256), B);
-        warp_geometry_kernel<<<grid, 256, 0, s>>>(disp, rel_T, K, K_inv, baseline, disp1, tx, ty, valid, sums, ctrl, H, W);
-        TCS_CHECK_LAUNCH("tcs_warp_forward(geometry)");
-        warp_weight_kernel<<<grid, 256, 0, s>>>(disp1, tx, ty, valid, sums, ctrl, B, H * W, per_sample_mean);
-        TCS_CHECK_LAUNCH("tcs_warp_forward(weights)");
-        if (gather) {
-            dim3 ggrid(ceil_div(W, 32), ceil_div(H, kGatherWarps), B);
-            warp_gather_kernel<<<ggrid, kGatherWarps * 32, 0, s>>>(fmap, disp1, tx, ty, valid, cur_fmap, out_disp, out_fmap, out_mask,
-                                                                   out_cost, ctrl, C, H, W);
-            TCS_CHECK_LAUNCH("tcs_warp_forward(gather)");
-            const size_t n4 = (size_t)B * H * W * (C + 4) / 4;
-            warp_zero_kernel<<<num_sms() * 4, 256, 0, s>>>(reinterpret_cast<float4*>(accum), n4, ctrl);
-            TCS_CHECK_LAUNCH("tcs_warp_forward(zero)");
+    const bool lists = (flags & TCS_WARP_DETERMINISTIC) != 0;
+    // scatter (default): zero the sums and the accumulator; lists: the sums and the per-target counters only
+    TCS_CHECK_CUDA(cudaMemsetAsync(base, 0, lists ? L.accum : L.disp1, s));
+    const dim3 pgrid(ceil_div(H * W, 256), B);
+    warp_geometry_kernel<<<pgrid, 256, 0, s>>>(disp, rel_T, K, K_inv, baseline, disp1, tx, ty, valid, sums, H, W);
+    TCS_CHECK_LAUNCH("tcs_warp_forward(geometry)");
+    warp_weight_kernel<<<pgrid, 256, 0, s>>>(disp1, tx, ty, valid, sums, B, H * W, per_sample_mean);
+    TCS_CHECK_LAUNCH("tcs_warp_forward(weights)");
+    if (lists) {
+        // ---- list formulation: no accumulator, no floating-point atomics, fixed summation order
+        int* cnt = reinterpret_cast<int*>(base + L.cnt);
+        int* start = reinterpret_cast<int*>(base + L.start);
+        int* rowtot = reinterpret_cast<int*>(base + L.rowtot);
+        int2* entries = reinterpret_cast<int2*>(base + L.entries);
+        const long long npix = (long long)B * H * W;
+        TCS_REQUIRE(npix * 4 < 0x7fffffffLL, TCS_E_SHAPE, "tcs_warp_forward: too many pixels for 32-bit list offsets");
+        warp_list_kernel<false><<<pgrid, 256, 0, s>>>(valid, tx, ty, cnt, start, entries, H, W);
+        TCS_CHECK_LAUNCH("tcs_warp_forward(count)");
+        warp_rowsum_kernel<<<B * H, 256, 0, s>>>(cnt, rowtot, W);
+        TCS_CHECK_LAUNCH("tcs_warp_forward(row sums)");
+        warp_offsets_kernel<<<B * H, 256, 0, s>>>(cnt, rowtot, start, W, B * H);
+        TCS_CHECK_LAUNCH("tcs_warp_forward(offsets)");
+        warp_list_kernel<true><<<pgrid, 256, 0, s>>>(valid, tx, ty, cnt, start, entries, H, W);
+        TCS_CHECK_LAUNCH("tcs_warp_forward(fill)");
+        warp_sort_kernel<<<(unsigned)ceil_div_ll(npix, 256), 256, 0, s>>>(start, entries, npix);
+        TCS_CHECK_LAUNCH("tcs_warp_forward(sort)");
+        const dim3 cgrid(ceil_div(W, kTileW), H, B);
+#define TCS_COLLECT_CASE(G)                                                                                           \
+    case G:                                                                                                           \
+        if (out_fmap != nullptr)                                                                                      \
+            warp_collect_kernel<G, true><<<cgrid, kWarpThreads, 0, s>>>(fmap, disp1, start, entries, cur_fmap, out_disp, out_fmap, \
+                                                                        out_mask, out_cost, H, W);                    \
+        else                                                                                                          \
+            warp_collect_kernel<G, false><<<cgrid, kWarpThreads, 0, s>>>(fmap, disp1, start, entries, cur_fmap, out_disp, out_fmap, \
+                                                                         out_mask, out_cost, H, W);                   \
+        break;
+        switch (C / 128) {
+            TCS_COLLECT_CASE(1)
+            TCS_COLLECT_CASE(2)
+            TCS_COLLECT_CASE(3)
+            TCS_COLLECT_CASE(4)
         }
+#undef TCS_COLLECT_CASE
+        TCS_CHECK_LAUNCH("tcs_warp_forward(collect)");
+        return 0;
     }
     const dim3 grid(ceil_div(W, kTileW), H, B);
     const size_t smem_splat = (size_t)kTileW * (C + 1) * sizeof(float);
@@ -814,12 +840,12 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
             { const int cv = carveout_percent("TCS_CARVE_FINALIZE", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_finalize_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); } \
             attr_done = true;                                                                                         \
         }                                                                                                             \
-        warp_splat_kernel<G><<<grid, kWarpThreads, smem_splat, s>>>(fmap, disp1, tx, ty, valid, ctrl, accum, B, H, W); \
+        warp_splat_kernel<G><<<grid, kWarpThreads, smem_splat, s>>>(fmap, disp1, tx, ty, valid, accum, B, H, W); \
         TCS_CHECK_LAUNCH("tcs_warp_forward(splat)");                                                                  \
         if (out_fmap == nullptr && out_cost != nullptr && cur_fmap != nullptr)                                        \
-            warp_cost_kernel<G><<<grid, kWarpThreads, smem_cost, s>>>(accum, cur_fmap, out_disp, out_mask, out_cost, ctrl, H, W); \
+            warp_cost_kernel<G><<<grid, kWarpThreads, smem_cost, s>>>(accum, cur_fmap, out_disp, out_mask, out_cost, H, W); \
         else                                                                                                          \
-            warp_finalize_kernel<G><<<grid, kWarpThreads, smem_fin, s>>>(accum, cur_fmap, out_disp, out_fmap, out_mask, out_cost, ctrl, H, W); \
+            warp_finalize_kernel<G><<<grid, kWarpThreads, smem_fin, s>>>(accum, cur_fmap, out_disp, out_fmap, out_mask, out_cost, H, W); \
         TCS_CHECK_LAUNCH("tcs_warp_forward(finalize)");                                                               \
     } break;
     switch (C / 128) {

@@ -56,7 +56,8 @@ def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, pe
 
     -> (disp', fmap', mask, cost)  with cost None when cur_fmap is None.  want_fmap=False skips materialising
     fmap' (TCStereo.forward only ever reads its cost, tc_stereo.py:139-140) and returns None in its place.
-    deterministic=True collects the splat from the target's side in a fixed order (bitwise repeatable, slower)."""
+    deterministic=True collects the splat from the target's side through sorted contributor lists (bitwise
+    repeatable, no accumulator; about 1.7x the time of the default atomic scatter)."""
     disp = _f32c("disp", disp)
     fmap = _f32c("fmap", fmap)
     if disp.dim() != 4 or disp.shape[1] != 1:

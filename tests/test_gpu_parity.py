@@ -369,9 +369,9 @@ def test_warp_full_size(tcs, B, H, W, per_sample, deterministic):
 
 
 @pytest.mark.parametrize("kind", ["large_flow", "irregular_flow"])
-def test_warp_scatter_fallback(tcs, kind):
-    """Deterministic mode: frames the gather kernel cannot take (flow beyond its search radius, or too many distinct source offsets
-    per target segment) fall back to the scatter kernels on the device; the result must be the same splat."""
+def test_warp_lists_take_any_flow(tcs, kind):
+    """Deterministic mode (sorted per-target contributor lists): large flows and flows that jump from pixel to pixel, where
+    a target collects from many, far-apart sources, give the same splat as the oracle."""
     B, H, W = 1, 40, 96
     K, Kinv, T, _, base = camera(B, H, W, 5)
     g = torch.Generator().manual_seed(23)
@@ -395,7 +395,7 @@ def test_warp_scatter_fallback(tcs, kind):
 
 
 def test_warp_is_deterministic(tcs):
-    """The gather formulation adds a target's contributions in a fixed order: bitwise repeatable (the reference's
+    """The list formulation adds a target's contributions in source order: bitwise repeatable (the reference's
     atomic scatter is not)."""
     g = load_golden("warp_small")
     args = [cuda(g[k]) for k in ("disp", "fmap", "rel_T", "K", "K_inv", "baseline")]
@@ -407,6 +407,18 @@ def test_warp_is_deterministic(tcs):
     assert_close(host(a[0]), g["warped_disp"], rtol=1e-5, atol=1e-5, what="gather warped disparity vs reference")
     assert_close(host(a[1]), g["warped_fmap"], rtol=1e-5, atol=1e-5, what="gather warped features vs reference")
     assert_close(host(a[3]), g["cost"], rtol=1e-5, atol=2e-6, what="gather matching cost vs reference")
+    # a larger frame with i.i.d. depths: the lists are filled in whatever order the atomics land, the sort undoes it
+    B, H, W = 2, 60, 128
+    K, Kinv, T, _, base = camera(B, H, W, 9)
+    gen = torch.Generator().manual_seed(5)
+    disp = (0.5 + torch.rand(B, 1, H, W, generator=gen) * 8).cuda()
+    fmap = torch.randn(B, 128, H, W, generator=gen).cuda()
+    cur = torch.randn(B, 128, H, W, generator=gen).cuda()
+    runs = [tcs.warp_with_cost(disp, fmap, cuda(T), cuda(K), cuda(Kinv), cuda(base), cur_fmap=cur, deterministic=True)
+            for _ in range(3)]
+    for r in runs[1:]:
+        for x, y in zip(runs[0], r):
+            assert torch.equal(x, y)
 
 
 def test_warp_identity_pose_keeps_everything(tcs):
