@@ -199,14 +199,93 @@ warp_splat_kernel(const float* __restrict__ fmap, const float* __restrict__ disp
     }
 }
 
+// ---- list formulation, front end of the two normalise kernels ---------------------------------------------------
+// Contributor lists (built by the kernels further down): target t owns entries[start[t] .. start[t+1]), each
+// (source pixel inside the sample, e * bilinear weight), sorted by source pixel.  src_t is the previous frame's
+// features transposed to pixel-major rows in the accumulator's channel permutation, so one entry is one coalesced
+// 4*C-byte read for a warp.
+struct ListArgs {
+    const float* src_t;     // [B*H*W][C]
+    const int* start;       // [B*H*W + 1]
+    const int2* entries;
+    const float* disp1;     // [B*H*W] reprojected disparity of the source pixels
+};
+
+// Sum of the contributions to one target (the whole warp works on it; n is warp-uniform).  tail = (sum w * disp', sum w).
+// (Staging the block's offsets and entries in shared memory first was measured: 482 us instead of 355 -- the extra
+// barrier behind the current-feature loads and 20 more registers cost more than the index round trips.)
+template <int kGroups>
+__device__ __forceinline__ void gather_target(const ListArgs& la, size_t sample_px0, int s0, int n, int lane,
+                                              float4 (&a)[kGroups], float2& tail) {
+    constexpr int C = kGroups * 128;
+    constexpr int kE = 4;                                       // entries per round: 4 * kGroups 16-byte loads in flight per lane (2: spills, 370 us)
+#pragma unroll
+    for (int j = 0; j < kGroups; ++j) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float norm = 0.0f, dsum = 0.0f;
+    for (int j0 = 0; j0 < n; j0 += kE) {
+        int2 en[kE];
+        float4 v[kE][kGroups];
+        float d1[kE];
+#pragma unroll
+        for (int u = 0; u < kE; ++u) {
+            const bool live = j0 + u < n;
+            en[u] = live ? __ldg(la.entries + s0 + j0 + u) : make_int2(0, 0);   // weight 0: contributes nothing
+            const float* row = la.src_t + (sample_px0 + en[u].x) * C + 4 * lane;
+#pragma unroll
+            for (int j = 0; j < kGroups; ++j)
+                v[u][j] = live ? ldg_stream_f4(reinterpret_cast<const float4*>(row + j * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            d1[u] = live ? __ldg(la.disp1 + sample_px0 + en[u].x) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < kE; ++u) {
+            const float w = __int_as_float(en[u].y);
+#pragma unroll
+            for (int j = 0; j < kGroups; ++j) {
+                a[j].x = fmaf(v[u][j].x, w, a[j].x);
+                a[j].y = fmaf(v[u][j].y, w, a[j].y);
+                a[j].z = fmaf(v[u][j].z, w, a[j].z);
+                a[j].w = fmaf(v[u][j].w, w, a[j].w);
+            }
+            norm = __fadd_rn(norm, w);
+            dsum = fmaf(d1[u], w, dsum);
+        }
+    }
+    tail = make_float2(dsum, norm);
+}
+
+// NCHW features -> pixel-major rows [B*H*W][C] in the accumulator's channel permutation (position 128 j + 4 lane + q
+// holds channel lane + 32 (4 j + q)): coalesced both ways through the transposed shared-memory tile.
+template <int kGroups>
+__global__ void __launch_bounds__(kWarpThreads)
+warp_transpose_kernel(const float* __restrict__ fmap, float* __restrict__ dst, int H, int W) {
+    constexpr int C = kGroups * 128;
+    constexpr int pitch = C + 1;
+    extern __shared__ float tile[];  // [32][C + 1]
+    const int w0 = blockIdx.x * kTileW, h = blockIdx.y, b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    load_tile_transposed(fmap, tile, pitch, b, h, w0, C, H, W);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kTileW / 8; ++i) {
+        const int wl = warp * (kTileW / 8) + i;
+        if (w0 + wl >= W) break;
+        const float* row = tile + wl * pitch;
+        float* out = dst + (((size_t)b * H + h) * W + w0 + wl) * C + 4 * lane;
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j)
+            *reinterpret_cast<float4*>(out + j * 128) = make_float4(row[lane + 32 * (4 * j + 0)], row[lane + 32 * (4 * j + 1)],
+                                                                    row[lane + 32 * (4 * j + 2)], row[lane + 32 * (4 * j + 3)]);
+    }
+}
+
 // ---- forward warp, kernel C': the same when the caller wants only the cost (tc_stereo.py:139-140 is all the model
 // reads of the warped features).  No warped-feature tile and no per-channel divisions: the CURRENT features are
 // transposed through shared memory instead, each warp walks its pixels with the accumulator row straight from
 // global memory (scaled by one reciprocal per pixel, so the range stays that of the normalised features), and the
 // three sums of the cosine are warp-reduced in a fixed order.
-template <int kGroups>
-__global__ void __launch_bounds__(kWarpThreads)
-warp_cost_kernel(const float* __restrict__ accum, const float* __restrict__ cur_fmap, float* __restrict__ out_disp,
+template <int kGroups, bool kLists>
+__global__ void __launch_bounds__(kWarpThreads, kLists ? 3 : 4)   // 80 / 64 registers; a fourth list block would spill
+warp_cost_kernel(const float* __restrict__ accum, const ListArgs la, const float* __restrict__ cur_fmap, float* __restrict__ out_disp,
                  float* __restrict__ out_mask, float* __restrict__ out_cost, int H, int W) {
     constexpr int C = kGroups * 128;
     constexpr int CP = C + 4;
@@ -219,24 +298,46 @@ warp_cost_kernel(const float* __restrict__ accum, const float* __restrict__ cur_
     const bool in_w = w < W;
     const size_t plane = (size_t)H * W;
     const size_t base = ((size_t)b * C * H + h) * W + w;
+    int ls0[kPx], ln[kPx];                     // list offsets of this warp's targets: fetched first, needed last
+    if (kLists) {
+#pragma unroll
+        for (int i = 0; i < kPx; ++i) {
+            const int wl = warp * kPx + i;
+            const bool live = w0 + wl < W;
+            const size_t tpix = ((size_t)b * H + h) * W + (live ? w0 + wl : 0);
+            ls0[i] = __ldg(la.start + tpix);
+            ln[i] = live ? __ldg(la.start + tpix + 1) - ls0[i] : 0;
+        }
+    }
     float f[kPerWarp];
 #pragma unroll
     for (int k = 0; k < kPerWarp; ++k)
         f[k] = in_w ? ldg_stream_f1(cur_fmap + base + (size_t)(warp + 8 * k) * plane) : 0.0f;
+    if (kLists) {                              // park the tile first: the gather below needs the registers
+#pragma unroll
+        for (int k = 0; k < kPerWarp; ++k) tile[(warp + 8 * k) * 33 + lane] = f[k];
+    }
     float2 tail[kPx];
     float4 a[kPx][kGroups];
 #pragma unroll
     for (int i = 0; i < kPx; ++i) {
         const int wl = warp * kPx + i;
         const bool live = w0 + wl < W;
-        const float* src = accum + (((size_t)b * H + h) * W + (live ? w0 + wl : 0)) * CP;
-        tail[i] = live ? *reinterpret_cast<const float2*>(src + C) : make_float2(0.f, 0.f);
+        const size_t tpix = ((size_t)b * H + h) * W + (live ? w0 + wl : 0);
+        if (kLists) {
+            gather_target<kGroups>(la, (size_t)b * plane, ls0[i], ln[i], lane, a[i], tail[i]);   // n = 0 for a dead pixel
+        } else {
+            const float* src = accum + tpix * CP;
+            tail[i] = live ? *reinterpret_cast<const float2*>(src + C) : make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < kGroups; ++j)
-            a[i][j] = live ? ldg_stream_f4(reinterpret_cast<const float4*>(src + j * 128 + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < kGroups; ++j)
+                a[i][j] = live ? ldg_stream_f4(reinterpret_cast<const float4*>(src + j * 128 + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
+    if (!kLists) {
 #pragma unroll
-    for (int k = 0; k < kPerWarp; ++k) tile[(warp + 8 * k) * 33 + lane] = f[k];
+        for (int k = 0; k < kPerWarp; ++k) tile[(warp + 8 * k) * 33 + lane] = f[k];
+    }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kPx; ++i) {
@@ -276,9 +377,9 @@ warp_cost_kernel(const float* __restrict__ accum, const float* __restrict__ cur_
 }
 
 // ---- forward warp, kernel C: normalise, mask, NCHW re-layout, matching cost -------------------------------------
-template <int kGroups>
+template <int kGroups, bool kLists>
 __global__ void __launch_bounds__(kWarpThreads)
-warp_finalize_kernel(const float* __restrict__ accum, const float* __restrict__ cur_fmap,
+warp_finalize_kernel(const float* __restrict__ accum, const ListArgs la, const float* __restrict__ cur_fmap,
                      float* __restrict__ out_disp, float* __restrict__ out_fmap, float* __restrict__ out_mask,
                      float* __restrict__ out_cost, int H, int W) {
     constexpr int C = kGroups * 128;
@@ -309,11 +410,22 @@ warp_finalize_kernel(const float* __restrict__ accum, const float* __restrict__ 
         const int wl = warp * (kTileW / 8) + i;
         const bool live = w0 + wl < W;
         const size_t idx = ((size_t)b * H + h) * W + (live ? w0 + wl : 0);
-        const float* src = accum + idx * CP;
-        tail[i] = live ? *reinterpret_cast<const float2*>(src + C) : make_float2(0.f, 0.f);
+        if (kLists) {
+            if (live) {
+                const int s0 = __ldg(la.start + idx);
+                gather_target<kGroups>(la, (size_t)b * plane, s0, __ldg(la.start + idx + 1) - s0, lane, a[i], tail[i]);
+            } else {
+                tail[i] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < kGroups; ++j)
-            a[i][j] = live ? *reinterpret_cast<const float4*>(src + j * 128 + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < kGroups; ++j) a[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            const float* src = accum + idx * CP;
+            tail[i] = live ? *reinterpret_cast<const float2*>(src + C) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < kGroups; ++j)
+                a[i][j] = live ? *reinterpret_cast<const float4*>(src + j * 128 + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 #pragma unroll
     for (int i = 0; i < kTileW / 8; ++i) {
@@ -532,91 +644,6 @@ warp_sort_kernel(const int* __restrict__ start, int2* __restrict__ entries, long
     }
 }
 
-// (4) one block = 32 consecutive targets of a row (the lanes) x 8 channel slices (the warps: channels warp + 8k).
-template <int kGroups, bool kWantFmap>
-__global__ void __launch_bounds__(kWarpThreads)
-warp_collect_kernel(const float* __restrict__ fmap, const float* __restrict__ disp1, const int* __restrict__ start,
-                    const int2* __restrict__ entries, const float* __restrict__ cur_fmap, float* __restrict__ out_disp,
-                    float* __restrict__ out_fmap, float* __restrict__ out_mask, float* __restrict__ out_cost, int H, int W) {
-    constexpr int C = kGroups * 128;
-    constexpr int kPerWarp = C / 8;
-    constexpr int kE = 4;                       // list entries per round
-    __shared__ float red[8 * 32 * 3];
-    const int w0 = blockIdx.x * kTileW, h = blockIdx.y, b = blockIdx.z;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int w = w0 + lane;
-    const bool in_w = w < W;
-    const size_t plane = (size_t)H * W;
-    const size_t tpix = ((size_t)b * H + h) * W + (in_w ? w : 0);
-    const int s0 = in_w ? __ldg(start + tpix) : 0;
-    const int n = in_w ? __ldg(start + tpix + 1) - s0 : 0;
-    const int n_max = __reduce_max_sync(0xffffffffu, n);
-    const float* fb = fmap + (size_t)b * C * plane + (size_t)warp * plane;   // this warp's first channel
-    const bool want_cost = out_cost != nullptr;
-
-    float acc[kPerWarp];
-#pragma unroll
-    for (int k = 0; k < kPerWarp; ++k) acc[k] = 0.0f;
-    float norm = 0.0f, dsum = 0.0f;
-    for (int j0 = 0; j0 < n_max; j0 += kE) {
-        const float* ptr[kE];
-        float wj[kE];
-        bool live[kE];
-#pragma unroll
-        for (int u = 0; u < kE; ++u) {
-            live[u] = j0 + u < n;
-            const int2 en = live[u] ? __ldg(entries + s0 + j0 + u) : make_int2(0, 0);
-            wj[u] = __int_as_float(en.y);                      // 0 for the padding of shorter lists
-            ptr[u] = fb + en.x;
-            norm = __fadd_rn(norm, wj[u]);
-            if (warp == 0 && live[u]) dsum = fmaf(__ldg(disp1 + (size_t)b * plane + en.x), wj[u], dsum);
-        }
-#pragma unroll
-        for (int k = 0; k < kPerWarp; ++k) {
-#pragma unroll
-            for (int u = 0; u < kE; ++u)
-                if (live[u]) acc[k] = fmaf(__ldg(ptr[u] + (size_t)(8 * k) * plane), wj[u], acc[k]);
-        }
-    }
-    const float nrm = fmaxf(norm, 1e-7f);                       // clip(1e-7, None)   softsplat.py:268
-    const float m = (norm != 0.0f) ? 1.0f : 0.0f;               // softsplat.py:258
-    const float rcp = __fdiv_rn(1.0f, nrm);
-    const size_t obase = ((size_t)b * C * H + h) * W + w + (size_t)warp * plane;
-    float dot = 0.0f, s1 = 0.0f, sw = 0.0f;
-#pragma unroll
-    for (int k = 0; k < kPerWarp; ++k) {
-        const float v = kWantFmap ? __fdiv_rn(acc[k], nrm) : __fmul_rn(acc[k], rcp);
-        if (kWantFmap && in_w) stg_stream_f1(out_fmap + obase + (size_t)(8 * k) * plane, v);
-        if (want_cost) {
-            const float f = in_w ? ldg_stream_f1(cur_fmap + obase + (size_t)(8 * k) * plane) : 0.0f;
-            dot = fmaf(f, v, dot);
-            s1 = fmaf(f, f, s1);
-            sw = fmaf(v, v, sw);
-        }
-    }
-    if (warp == 0 && in_w) {
-        out_disp[tpix] = __fdiv_rn(dsum, nrm);
-        out_mask[tpix] = m;
-    }
-    if (!want_cost) return;
-    red[(warp * 32 + lane) * 3 + 0] = dot;
-    red[(warp * 32 + lane) * 3 + 1] = s1;
-    red[(warp * 32 + lane) * 3 + 2] = sw;
-    __syncthreads();
-    if (warp == 0 && in_w) {
-        dot = s1 = sw = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            dot += red[(k * 32 + lane) * 3 + 0];
-            s1 += red[(k * 32 + lane) * 3 + 1];
-            sw += red[(k * 32 + lane) * 3 + 2];
-        }
-        // sum_c normalize(f)_c * normalize(v)_c  (F.normalize eps 1e-12), times the splat mask (tc_stereo.py:139-140)
-        const float den = __fmul_rn(fmaxf(sqrtf(s1), 1e-12f), fmaxf(sqrtf(sw), 1e-12f));
-        out_cost[tpix] = __fmul_rn(__fdiv_rn(dot, den), m);
-    }
-}
-
 // ---- get_backward_grid ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 backward_grid_kernel(const float* __restrict__ disp, const float* __restrict__ rel_T, const float* __restrict__ K,
@@ -787,12 +814,17 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
     TCS_CHECK_LAUNCH("tcs_warp_forward(geometry)");
     warp_weight_kernel<<<pgrid, 256, 0, s>>>(disp1, tx, ty, valid, sums, B, H * W, per_sample_mean);
     TCS_CHECK_LAUNCH("tcs_warp_forward(weights)");
+    ListArgs la = {nullptr, nullptr, nullptr, nullptr};
     if (lists) {
         // ---- list formulation: no accumulator, no floating-point atomics, fixed summation order
         int* cnt = reinterpret_cast<int*>(base + L.cnt);
         int* start = reinterpret_cast<int*>(base + L.start);
         int* rowtot = reinterpret_cast<int*>(base + L.rowtot);
         int2* entries = reinterpret_cast<int2*>(base + L.entries);
+        la.src_t = accum;           // the accumulator's space holds the transposed source features instead
+        la.start = start;
+        la.entries = entries;
+        la.disp1 = disp1;
         const long long npix = (long long)B * H * W;
         TCS_REQUIRE(npix * 4 < 0x7fffffffLL, TCS_E_SHAPE, "tcs_warp_forward: too many pixels for 32-bit list offsets");
         warp_list_kernel<false><<<pgrid, 256, 0, s>>>(valid, tx, ty, cnt, start, entries, H, W);
@@ -805,25 +837,6 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
         TCS_CHECK_LAUNCH("tcs_warp_forward(fill)");
         warp_sort_kernel<<<(unsigned)ceil_div_ll(npix, 256), 256, 0, s>>>(start, entries, npix);
         TCS_CHECK_LAUNCH("tcs_warp_forward(sort)");
-        const dim3 cgrid(ceil_div(W, kTileW), H, B);
-#define TCS_COLLECT_CASE(G)                                                                                           \
-    case G:                                                                                                           \
-        if (out_fmap != nullptr)                                                                                      \
-            warp_collect_kernel<G, true><<<cgrid, kWarpThreads, 0, s>>>(fmap, disp1, start, entries, cur_fmap, out_disp, out_fmap, \
-                                                                        out_mask, out_cost, H, W);                    \
-        else                                                                                                          \
-            warp_collect_kernel<G, false><<<cgrid, kWarpThreads, 0, s>>>(fmap, disp1, start, entries, cur_fmap, out_disp, out_fmap, \
-                                                                         out_mask, out_cost, H, W);                   \
-        break;
-        switch (C / 128) {
-            TCS_COLLECT_CASE(1)
-            TCS_COLLECT_CASE(2)
-            TCS_COLLECT_CASE(3)
-            TCS_COLLECT_CASE(4)
-        }
-#undef TCS_COLLECT_CASE
-        TCS_CHECK_LAUNCH("tcs_warp_forward(collect)");
-        return 0;
     }
     const dim3 grid(ceil_div(W, kTileW), H, B);
     const size_t smem_splat = (size_t)kTileW * (C + 1) * sizeof(float);
@@ -834,18 +847,30 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
         static bool attr_done = false;                                                                                \
         if (!attr_done) {                                                                                             \
             TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_splat_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_splat)); \
-            TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_finalize_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin)); \
-            TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_cost_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cost)); \
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_transpose_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_splat)); \
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_finalize_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin)); \
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_finalize_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin)); \
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_cost_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cost)); \
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_cost_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cost)); \
             { const int cv = carveout_percent("TCS_CARVE_SPLAT", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_splat_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); } \
-            { const int cv = carveout_percent("TCS_CARVE_FINALIZE", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_finalize_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); } \
             attr_done = true;                                                                                         \
         }                                                                                                             \
-        warp_splat_kernel<G><<<grid, kWarpThreads, smem_splat, s>>>(fmap, disp1, tx, ty, valid, accum, B, H, W); \
-        TCS_CHECK_LAUNCH("tcs_warp_forward(splat)");                                                                  \
-        if (out_fmap == nullptr && out_cost != nullptr && cur_fmap != nullptr)                                        \
-            warp_cost_kernel<G><<<grid, kWarpThreads, smem_cost, s>>>(accum, cur_fmap, out_disp, out_mask, out_cost, H, W); \
-        else                                                                                                          \
-            warp_finalize_kernel<G><<<grid, kWarpThreads, smem_fin, s>>>(accum, cur_fmap, out_disp, out_fmap, out_mask, out_cost, H, W); \
+        const bool cost_only = out_fmap == nullptr && out_cost != nullptr && cur_fmap != nullptr;                     \
+        if (lists) {                                                                                                  \
+            warp_transpose_kernel<G><<<grid, kWarpThreads, smem_splat, s>>>(fmap, accum, H, W);                       \
+            TCS_CHECK_LAUNCH("tcs_warp_forward(transpose)");                                                          \
+            if (cost_only)                                                                                            \
+                warp_cost_kernel<G, true><<<grid, kWarpThreads, smem_cost, s>>>(accum, la, cur_fmap, out_disp, out_mask, out_cost, H, W); \
+            else                                                                                                      \
+                warp_finalize_kernel<G, true><<<grid, kWarpThreads, smem_fin, s>>>(accum, la, cur_fmap, out_disp, out_fmap, out_mask, out_cost, H, W); \
+        } else {                                                                                                      \
+            warp_splat_kernel<G><<<grid, kWarpThreads, smem_splat, s>>>(fmap, disp1, tx, ty, valid, accum, B, H, W);  \
+            TCS_CHECK_LAUNCH("tcs_warp_forward(splat)");                                                              \
+            if (cost_only)                                                                                            \
+                warp_cost_kernel<G, false><<<grid, kWarpThreads, smem_cost, s>>>(accum, la, cur_fmap, out_disp, out_mask, out_cost, H, W); \
+            else                                                                                                      \
+                warp_finalize_kernel<G, false><<<grid, kWarpThreads, smem_fin, s>>>(accum, la, cur_fmap, out_disp, out_fmap, out_mask, out_cost, H, W); \
+        }                                                                                                             \
         TCS_CHECK_LAUNCH("tcs_warp_forward(finalize)");                                                               \
     } break;
     switch (C / 128) {
