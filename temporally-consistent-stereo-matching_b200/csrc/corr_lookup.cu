@@ -212,9 +212,31 @@ __device__ __forceinline__ void span_taps_R(const float* R, int span_first, floa
     const int Wu = Wb >> 1;
     const float cb = cb_, cu = cb_ * 0.5f;
     const int fu = (span_first >> 1) + 5;                       // span_first = 2 * (fu - 5)
+    // Regular pixels: grid_sample's round trip moves a tap by less than 2e-4 px (levels up to 1024 wide), so when the
+    // fractional part of the level coordinate keeps 2^-9 away from 0 and 1 every tap's floor is floor(coordinate) +
+    // (t - 4) and the neighbours sit at ONE statically known offset: no per-tap index arithmetic or selects.  Taken
+    // only when the whole warp is regular (exact-integer coordinates, e.g. a zero-flow first iteration, are not).
+    constexpr float kRegLo = 1.0f / 512.0f, kRegHi = 1.0f - 1.0f / 512.0f;
+    const unsigned active = __activemask();
     {   // ---- level lb
         const float wm1 = (float)(Wb - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
         float* o = out + (((long long)b * num_levels + lb) * 9) * HW + out_px;
+        const float fbf = floorf(cb), frac = cb - fbf;
+        const int cs = (int)fbf - span_first - 9;               // the select index c every tap would get: 1 or 2
+        const bool regular = kPadded && Wb <= 1024 && frac >= kRegLo && frac <= kRegHi && (cs == 1 || cs == 2);
+        if (kPadded && __all_sync(active, regular)) {
+            float Q[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) Q[i] = (cs == 2) ? R[i + 7] : R[i + 6];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float ix = sample_pos_fast(__fadd_rn((float)(t - 4), cb), wm1, rc, hwm1);
+                const float x0f = floorf(ix);
+                const float r = fmaf(Q[t + 1], __fsub_rn(ix, x0f), __fmul_rn(Q[t], __fsub_rn(__fadd_rn(x0f, 1.0f), ix)));
+                if (kKeep) keep[t] = r; else stg_stream_f1(o, r);
+                o += HW;
+            }
+        } else {
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const float xk = __fadd_rn((float)(t - 4), cb);                    // corr.py:43
@@ -233,6 +255,7 @@ __device__ __forceinline__ void span_taps_R(const float* R, int span_first, floa
             if (kKeep) keep[t] = r; else stg_stream_f1(o, r);
             o += HW;
         }
+        }
     }
     {   // ---- level lb + 1: entries re-pooled from pairs of the span
         float P[12];
@@ -240,6 +263,18 @@ __device__ __forceinline__ void span_taps_R(const float* R, int span_first, floa
         for (int j = 0; j < 12; ++j) P[j] = __fmul_rn(__fadd_rn(R[2 * j], R[2 * j + 1]), 0.5f);
         const float wm1 = (float)(Wu - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
         float* o = out + (((long long)b * num_levels + lb + 1) * 9) * HW + out_px;
+        const float fuf = floorf(cu), frac = cu - fuf;
+        const bool regular = kPadded && Wu <= 1024 && frac >= kRegLo && frac <= kRegHi && (int)fuf == fu;   // fu unclamped
+        if (kPadded && __all_sync(active, regular)) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {                        // the select index is 1 for every tap
+                const float ix = sample_pos_fast(__fadd_rn((float)(t - 4), cu), wm1, rc, hwm1);
+                const float x0f = floorf(ix);
+                const float r = fmaf(P[t + 2], __fsub_rn(ix, x0f), __fmul_rn(P[t + 1], __fsub_rn(__fadd_rn(x0f, 1.0f), ix)));
+                if (kKeep) keep[9 + t] = r; else stg_stream_f1(o, r);
+                o += HW;
+            }
+        } else {
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const float xk = __fadd_rn((float)(t - 4), cu);
@@ -256,6 +291,7 @@ __device__ __forceinline__ void span_taps_R(const float* R, int span_first, floa
             }
             if (kKeep) keep[9 + t] = r; else stg_stream_f1(o, r);
             o += HW;
+        }
         }
     }
 }

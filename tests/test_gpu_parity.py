@@ -208,6 +208,32 @@ def test_lookup_level0_alignment_variants_agree(tcs):
     assert_close(host(out_oct), ref, what="lookup, both alignments")
 
 
+def test_lookup_regular_fast_path_is_bit_identical(tcs):
+    """The aligned 4-level kernel takes a select-free path when a whole warp's coordinates keep away from integers.
+    The 3-level call runs the general shared-memory kernel on the same levels: levels 0..2 must agree bit for bit,
+    for coordinates that are regular, integer (never regular) and a fraction of 1e-3 from an integer (borderline)."""
+    B, H, W = 2, 16, 240
+    f1, f2 = make_fmaps(B, 128, H, W, 31)
+    blk = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), num_levels=4, radius=4, precision="fp32")
+    g = torch.Generator().manual_seed(4)
+    xs = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+    base = xs - torch.rand(B, 1, H, W, generator=g) * (W / 8)
+    variants = {"regular": base,
+                "integer": base.round(),
+                "borderline": base.round() + (torch.rand(B, 1, H, W, generator=g) - 0.5) * 4e-3,
+                "mixed": torch.where(torch.rand(B, 1, H, W, generator=g) < 0.02, base.round(), base),
+                "outside": base - 200.0}
+    lv = [x for x in blk._levels]
+    three = tcs.CorrBlock1D.from_levels([x.clone() for x in lv[:3]], radius=4)
+    for name, c in variants.items():
+        c = c.cuda()
+        a = blk(c)
+        b3 = three(c)
+        assert torch.equal(a[:, :27], b3), name
+        ref = orc.corr_lookup([host(x) for x in lv], host(c), 4)
+        assert_close(host(a), ref, what="lookup (%s coordinates)" % name)
+
+
 def test_lookup_coords_view_and_nan(tcs):
     g = load_golden("corr_small")
     blk = tcs.CorrBlock1D.from_levels([cuda(g["level%d" % l]) for l in range(4)])
