@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--precision", default="fp16x3")
     ap.add_argument("--mode", default="pyramid", choices=["pyramid", "alternate"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-warp-carry", dest="warp_carry", action="store_false",
+                    help="do not hand each frame's transposed features to the next frame's warp (atomic scatter instead)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
@@ -244,10 +246,14 @@ def run_b200(args):
     def phase_build(s):
         live[s]["blk"] = tcs_b200.CorrBlock1D(slots[s]["f1"], slots[s]["f2"], **kw)
 
+    carries = [tcs_b200.WarpCarry(), tcs_b200.WarpCarry()]   # each frame's fmap1, transposed by its own cost kernel for the next
+
     def phase_warp(s):
         o = slots[1 - s]
         d, _, m, c = tcs_b200.warp_with_cost(o["last_disp"], o["f1"], cam["rel_T"], cam["K"], cam["K_inv"], cam["baseline"],
-                                             cur_fmap=slots[s]["f1"], per_sample_mean=True, want_fmap=False)
+                                             cur_fmap=slots[s]["f1"], per_sample_mean=True, want_fmap=False,
+                                             carry_in=carries[1 - s] if args.warp_carry else None,
+                                             carry_out=carries[s] if args.warp_carry else None)
         grid = tcs_b200.get_backward_grid(d, cam["rel_T_inv"], cam["K"], cam["K_inv"], cam["baseline"])
         live[s]["init"] = (d, c, m)
         live[s]["nets"] = tcs_b200.warp_hidden_states(o["nets"], grid)
@@ -350,13 +356,16 @@ def run_b200(args):
             cur, prev = stage[k % 3], stage[(k - 1) % 3]
             out = tcs_b200.hot_path_frame(cur["f1"], cur["f2"], slots[s]["coords"],
                                           state=(o["last_disp"], prev["f1"], o["nets"]), rel_T=cam["rel_T"],
-                                          rel_T_inv=cam["rel_T_inv"], K=cam["K"], K_inv=cam["K_inv"], baseline=cam["baseline"], **kw)
+                                          rel_T_inv=cam["rel_T_inv"], K=cam["K"], K_inv=cam["K_inv"], baseline=cam["baseline"],
+                                          carry_in=e2e_carry[(k - 1) % 3] if args.warp_carry else None,
+                                          carry_out=e2e_carry[k % 3] if args.warp_carry else None, **kw)
             r = res_host[s]
             r["corr"].copy_(out["corr"], non_blocking=True)
             for dst, name in zip(r["init"], ("sparse_disp", "cost", "mask")):
                 dst.copy_(out[name], non_blocking=True)
             done[k].record(main)
 
+        e2e_carry = [tcs_b200.WarpCarry().reserve(slots[0]["f1"]) for _ in range(3)]    # one per staging buffer
         stage[2]["f1"].copy_(slots[1]["f1"])                    # "frame -1" features for the first warp
         upload(0)
         for k in range(2):                                       # warm-up of the e2e loop itself
@@ -412,9 +421,10 @@ def run_b200(args):
             "config": {"workload": "%dx%d temporal frames, %d lookup iters, 4-level pyramid r=4, C=256, %d sequences per GPU batched"
                                    % (args.height, args.width, iters, B),
                        "feature_hw": [H, W], "seqs_per_gpu": B, "precision": args.precision, "mode": args.mode,
-                       "cuda_graphs": graphs is not None, "fused_build": fused_build, "l2": "inputs larger than L2 (%.0f MB of feature maps per step, 2 alternating slots)" % (2 * npix * C * 4 / 1e6),
+                       "cuda_graphs": graphs is not None, "fused_build": fused_build, "warp": "lists on carried transposition" if args.warp_carry else "scatter", "l2": "inputs larger than L2 (%.0f MB of feature maps per step, 2 alternating slots)" % (2 * npix * C * 4 / 1e6),
                        "parallelism": "sequences sharded per GPU, no data-path collective"},
-            "e2e": e2e, "gpu_launches": K_steps * sequence.launches_per_frame(iters, False, mode=args.mode, fused_build=fused_build),
+            "e2e": e2e, "gpu_launches": K_steps * sequence.launches_per_frame(iters, False, mode=args.mode, fused_build=fused_build,
+                                                                                    warp_lists=args.warp_carry),
             "clocks": clocks, "roofline": roofline, "phases": phases_out, "cpu_baseline": cpu, "checksum": checksum,
         }))
     if world > 1:

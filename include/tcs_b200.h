@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCS_ABI_VERSION 1
+#define TCS_ABI_VERSION 2
 
 /* argument errors (negative); CUDA launch errors are returned as positive cudaError_t values */
 #define TCS_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported combination */
@@ -160,10 +160,16 @@ long long tcs_warp_scratch_bytes(int B, int C, int H, int W);
  *             reference's batch-global mean (geo_utils.py:193) — for batching independent sequences.
  *             TCS_WARP_DETERMINISTIC: collect the splat from the target's side through per-target contributor lists
  *             sorted by source pixel (fixed summation order, no accumulator, no floating-point atomics; any flow).
+ *   cur_t_out [B*H*W][C] (nullable; cost-only call, i.e. out_fmap null and out_cost given): cur_fmap as pixel-major rows
+ *             in the library's private channel order, written while its tile is in shared memory for the cost anyway.
+ *   fmap_t    (nullable; TCS_WARP_DETERMINISTIC only) the cur_t_out of the call in which `fmap` was cur_fmap, i.e. the
+ *             previous frame's call (core/tc_stereo.py carries fmap1 to the next frame as last_fmap1): the list
+ *             formulation then skips its transposition of fmap.  The caller vouches that fmap is unchanged since.
  *   scratch   tcs_warp_scratch_bytes() bytes, 16-byte aligned. */
 int tcs_warp_forward(const float* disp, const float* fmap, const float* rel_T, const float* K,
                      const float* K_inv, const float* baseline, const float* cur_fmap,
                      float* out_disp, float* out_fmap, float* out_mask, float* out_cost,
+                     const float* fmap_t, float* cur_t_out,
                      void* scratch, int B, int C, int H, int W, int flags, void* stream);
 
 /* ref: core/utils/geo_utils.py:201-236 (get_backward_grid).  disp [B,1,H,W] -> grid [B,2,H,W] (x,y). */

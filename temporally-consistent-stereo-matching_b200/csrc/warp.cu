@@ -286,7 +286,7 @@ warp_transpose_kernel(const float* __restrict__ fmap, float* __restrict__ dst, i
 template <int kGroups, bool kLists>
 __global__ void __launch_bounds__(kWarpThreads, kLists ? 3 : 4)   // 80 / 64 registers; a fourth list block would spill
 warp_cost_kernel(const float* __restrict__ accum, const ListArgs la, const float* __restrict__ cur_fmap, float* __restrict__ out_disp,
-                 float* __restrict__ out_mask, float* __restrict__ out_cost, int H, int W) {
+                 float* __restrict__ out_mask, float* __restrict__ out_cost, float* __restrict__ cur_t_out, int H, int W) {
     constexpr int C = kGroups * 128;
     constexpr int CP = C + 4;
     constexpr int kPerWarp = C / 8;
@@ -350,14 +350,20 @@ warp_cost_kernel(const float* __restrict__ accum, const ListArgs la, const float
 #pragma unroll
         for (int j = 0; j < kGroups; ++j) {
             const float av[4] = {a[i][j].x, a[i][j].y, a[i][j].z, a[i][j].w};
+            float fq[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {                        // accumulator position 128j + 4 lane + q  <->  channel below
                 const float fv = tile[(lane + 32 * (4 * j + q)) * 33 + wl];
                 const float v = __fmul_rn(av[q], r);
+                fq[q] = fv;
                 dot = fmaf(fv, v, dot);
                 s1 = fmaf(fv, fv, s1);
                 sw = fmaf(v, v, sw);
             }
+            // the current features are next frame's source: hand them on already transposed (pixel-major, permuted)
+            if (cur_t_out != nullptr && live)
+                *reinterpret_cast<float4*>(cur_t_out + (((size_t)b * H + h) * W + w0 + wl) * C + j * 128 + 4 * lane) =
+                    make_float4(fq[0], fq[1], fq[2], fq[3]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -784,6 +790,7 @@ extern "C" long long tcs_warp_scratch_bytes(int B, int C, int H, int W) {
 extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const float* rel_T, const float* K,
                                 const float* K_inv, const float* baseline, const float* cur_fmap,
                                 float* out_disp, float* out_fmap, float* out_mask, float* out_cost,
+                                const float* fmap_t, float* cur_t_out,
                                 void* scratch, int B, int C, int H, int W, int flags, void* stream) {
     using namespace tcs;
     TCS_REQUIRE(disp && fmap && rel_T && K && K_inv && baseline && out_disp && out_mask && scratch,
@@ -793,8 +800,12 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
     TCS_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, TCS_E_BADARG, "tcs_warp_forward: non-positive size");
     TCS_REQUIRE(C == 128 || C == 256 || C == 384 || C == 512, TCS_E_SHAPE, "tcs_warp_forward: C=%d must be 128, 256, 384 or 512", C);
     TCS_REQUIRE(H <= 65535 && B <= 65535, TCS_E_SHAPE, "tcs_warp_forward: H and B must be <= 65535");
-    TCS_REQUIRE(aligned16(fmap) && aligned16(scratch) && aligned16(cur_fmap), TCS_E_ALIGN,
-                "tcs_warp_forward: fmap, cur_fmap and scratch must be 16-byte aligned");
+    TCS_REQUIRE(aligned16(fmap) && aligned16(scratch) && aligned16(cur_fmap) && aligned16(fmap_t) && aligned16(cur_t_out), TCS_E_ALIGN,
+                "tcs_warp_forward: fmap, cur_fmap, fmap_t, cur_t_out and scratch must be 16-byte aligned");
+    TCS_REQUIRE(cur_t_out == nullptr || (out_fmap == nullptr && out_cost != nullptr), TCS_E_BADARG,
+                "tcs_warp_forward: cur_t_out is produced by the cost-only call (out_fmap null, out_cost given)");
+    TCS_REQUIRE(fmap_t == nullptr || (flags & TCS_WARP_DETERMINISTIC), TCS_E_BADARG,
+                "tcs_warp_forward: fmap_t is consumed by the TCS_WARP_DETERMINISTIC (list) formulation only");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const WarpScratch L = warp_scratch_layout(B, C, H, W);
     char* base = static_cast<char*>(scratch);
@@ -821,7 +832,7 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
         int* start = reinterpret_cast<int*>(base + L.start);
         int* rowtot = reinterpret_cast<int*>(base + L.rowtot);
         int2* entries = reinterpret_cast<int2*>(base + L.entries);
-        la.src_t = accum;           // the accumulator's space holds the transposed source features instead
+        la.src_t = fmap_t != nullptr ? fmap_t : accum;   // else the accumulator's space holds the transposed features
         la.start = start;
         la.entries = entries;
         la.disp1 = disp1;
@@ -857,17 +868,19 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
         }                                                                                                             \
         const bool cost_only = out_fmap == nullptr && out_cost != nullptr && cur_fmap != nullptr;                     \
         if (lists) {                                                                                                  \
-            warp_transpose_kernel<G><<<grid, kWarpThreads, smem_splat, s>>>(fmap, accum, H, W);                       \
-            TCS_CHECK_LAUNCH("tcs_warp_forward(transpose)");                                                          \
+            if (fmap_t == nullptr) {                                                                                  \
+                warp_transpose_kernel<G><<<grid, kWarpThreads, smem_splat, s>>>(fmap, accum, H, W);                   \
+                TCS_CHECK_LAUNCH("tcs_warp_forward(transpose)");                                                      \
+            }                                                                                                         \
             if (cost_only)                                                                                            \
-                warp_cost_kernel<G, true><<<grid, kWarpThreads, smem_cost, s>>>(accum, la, cur_fmap, out_disp, out_mask, out_cost, H, W); \
+                warp_cost_kernel<G, true><<<grid, kWarpThreads, smem_cost, s>>>(accum, la, cur_fmap, out_disp, out_mask, out_cost, cur_t_out, H, W); \
             else                                                                                                      \
                 warp_finalize_kernel<G, true><<<grid, kWarpThreads, smem_fin, s>>>(accum, la, cur_fmap, out_disp, out_fmap, out_mask, out_cost, H, W); \
         } else {                                                                                                      \
             warp_splat_kernel<G><<<grid, kWarpThreads, smem_splat, s>>>(fmap, disp1, tx, ty, valid, accum, B, H, W);  \
             TCS_CHECK_LAUNCH("tcs_warp_forward(splat)");                                                              \
             if (cost_only)                                                                                            \
-                warp_cost_kernel<G, false><<<grid, kWarpThreads, smem_cost, s>>>(accum, la, cur_fmap, out_disp, out_mask, out_cost, H, W); \
+                warp_cost_kernel<G, false><<<grid, kWarpThreads, smem_cost, s>>>(accum, la, cur_fmap, out_disp, out_mask, out_cost, cur_t_out, H, W); \
             else                                                                                                      \
                 warp_finalize_kernel<G, false><<<grid, kWarpThreads, smem_fin, s>>>(accum, la, cur_fmap, out_disp, out_fmap, out_mask, out_cost, H, W); \
         }                                                                                                             \

@@ -50,14 +50,44 @@ def _camera_args(relative_T, K, K_inv, baseline, B):
     return relative_T, K, K_inv, baseline
 
 
+class WarpCarry:
+    """The current frame's features, already transposed for the next frame's warp.
+
+    The cost-only call of warp_with_cost has cur_fmap in shared memory anyway and writes it out as pixel-major rows
+    (`rows`, [B*H*W, C] in the library's private channel order).  TC-Stereo hands fmap1 to the next frame as
+    last_fmap1 (core/tc_stereo.py:137, evaluate_stereo.py:192-197); when that next call receives this object as
+    `carry_in` and its `fmap` is the very tensor recorded here, unchanged, the list formulation skips its
+    transposition pass.  The tensor is kept referenced so that its storage cannot be reused in between."""
+
+    def __init__(self):
+        self.tensor = None
+        self.version = -1
+        self.rows = None
+
+    def reserve(self, like):
+        """Allocate the row buffer for feature maps shaped like `like` [B,C,H,W] now (e.g. outside a timed loop)."""
+        B, C, H, W = like.shape
+        if self.rows is None or tuple(self.rows.shape) != (B * H * W, C) or self.rows.device != like.device:
+            self.rows = torch.empty((B * H * W, C), dtype=torch.float32, device=like.device)
+            self.tensor = None
+        return self
+
+    def matches(self, fmap):
+        return (self.tensor is not None and self.rows is not None and fmap is self.tensor
+                and fmap._version == self.version and fmap.is_contiguous() and fmap.dtype == torch.float32)
+
+
 def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, per_sample_mean=False, want_fmap=True,
-                   deterministic=False):
+                   deterministic=False, carry_in=None, carry_out=None):
     """warp() plus the matching cost of core/tc_stereo.py:139-140 fused into the normalise kernel.
 
     -> (disp', fmap', mask, cost)  with cost None when cur_fmap is None.  want_fmap=False skips materialising
     fmap' (TCStereo.forward only ever reads its cost, tc_stereo.py:139-140) and returns None in its place.
     deterministic=True collects the splat from the target's side through sorted contributor lists (bitwise
-    repeatable, no accumulator; about 1.7x the time of the default atomic scatter)."""
+    repeatable, no accumulator, as fast as the default atomic scatter).
+    carry_out (a WarpCarry; cost-only calls) receives cur_fmap transposed for the next frame; carry_in (the
+    WarpCarry filled when `fmap` was the current frame) selects the list formulation and saves its transposition."""
+    fmap_in, cur_in = fmap, cur_fmap                          # the caller's own tensors: what a WarpCarry is keyed on
     disp = _f32c("disp", disp)
     fmap = _f32c("fmap", fmap)
     if disp.dim() != 4 or disp.shape[1] != 1:
@@ -76,13 +106,30 @@ def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, pe
     out_fmap = torch.empty_like(fmap) if want_fmap else None
     out_mask = torch.empty_like(disp)
     out_cost = torch.empty_like(disp) if cur_fmap is not None else None
+    fmap_t = None
+    if carry_in is not None and carry_in.matches(fmap_in) and tuple(carry_in.rows.shape) == (B * H * W, C):
+        fmap_t = carry_in.rows
+        deterministic = True                                  # the list formulation is the one that reads rows
+    cur_t = None
+    if carry_out is not None:
+        if want_fmap or cur_fmap is None:
+            raise ValueError("carry_out is filled by the cost-only call (want_fmap=False with cur_fmap)")
+        carry_out.reserve(fmap)
+        if fmap_t is not None and carry_out.rows.data_ptr() == fmap_t.data_ptr():
+            raise ValueError("carry_in and carry_out must be different WarpCarry objects")
+        cur_t = carry_out.rows
     with torch.cuda.device(dev):
         scratch = _warp_scratch(B, C, H, W, dev)
         _lib.call("tcs_warp_forward", disp.data_ptr(), fmap.data_ptr(), relative_T.data_ptr(), K.data_ptr(),
                   K_inv.data_ptr(), baseline.data_ptr(), cur_fmap.data_ptr() if cur_fmap is not None else None,
                   out_disp.data_ptr(), out_fmap.data_ptr() if out_fmap is not None else None, out_mask.data_ptr(),
-                  out_cost.data_ptr() if out_cost is not None else None, scratch.data_ptr(),
+                  out_cost.data_ptr() if out_cost is not None else None,
+                  fmap_t.data_ptr() if fmap_t is not None else None, cur_t.data_ptr() if cur_t is not None else None,
+                  scratch.data_ptr(),
                   B, C, H, W, (1 if per_sample_mean else 0) | (2 if deterministic else 0), _stream())
+    if carry_out is not None:
+        carry_out.tensor = cur_in
+        carry_out.version = cur_in._version
     return out_disp, out_fmap, out_mask, out_cost
 
 

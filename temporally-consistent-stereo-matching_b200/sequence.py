@@ -76,7 +76,8 @@ def relative_pose(prev_T, cur_T):
 
 
 def hot_path_frame(fmap1, fmap2, coords_seq, state=None, disp_init=None, rel_T=None, rel_T_inv=None, K=None,
-                   K_inv=None, baseline=None, num_levels=4, radius=4, precision=None, mode=None, per_sample_mean=True):
+                   K_inv=None, baseline=None, num_levels=4, radius=4, precision=None, mode=None, per_sample_mean=True,
+                   carry_in=None, carry_out=None):
     """The hot path's share of one frame for B batched sequences (order of core/tc_stereo.py:114-177).
 
       fmap1, fmap2  [B,C,H,W] features of the current stereo pair
@@ -85,6 +86,8 @@ def hot_path_frame(fmap1, fmap2, coords_seq, state=None, disp_init=None, rel_T=N
       disp_init     [B,1,H,W] completed disparity the backward grid is built from (tc_stereo.py:159);
                     defaults to the warped disparity (get_backward_grid clips it at 0.01 itself)
       rel_T, rel_T_inv  previous->current and current->previous camera transforms [B,4,4]
+      carry_out     a geo.WarpCarry that receives fmap1 transposed for the next frame's warp (a by-product of the cost);
+      carry_in      the WarpCarry filled by the previous frame: the warp then runs its list formulation on those rows
     Returns a dict: the last lookup, the sparse initialisation (disp, cost, mask), the warped hidden states.
     Every device operation inside is a libtcs_b200 kernel (plus one memset)."""
     corr_fn = CorrBlock1D(fmap1, fmap2, num_levels=num_levels, radius=radius, precision=precision, mode=mode)
@@ -94,7 +97,8 @@ def hot_path_frame(fmap1, fmap2, coords_seq, state=None, disp_init=None, rel_T=N
     else:
         last_disp, last_fmap1, last_net_list = state
         sparse_disp, _, mask, cost = geo.warp_with_cost(last_disp, last_fmap1, rel_T, K, K_inv, baseline,
-                                                        cur_fmap=fmap1, per_sample_mean=per_sample_mean, want_fmap=False)
+                                                        cur_fmap=fmap1, per_sample_mean=per_sample_mean, want_fmap=False,
+                                                        carry_in=carry_in, carry_out=carry_out)
         if last_net_list is not None:
             grid = geo.get_backward_grid(disp_init if disp_init is not None else sparse_disp,   # the kernel clips at 0.01
                                          rel_T_inv, K, K_inv, baseline)
@@ -106,15 +110,17 @@ def hot_path_frame(fmap1, fmap2, coords_seq, state=None, disp_init=None, rel_T=N
             "corr_fn": corr_fn}
 
 
-def launches_per_frame(iters, first_frame, hidden_levels=3, mode="pyramid", num_levels=4, fused_build=True):
-    """Number of libtcs_b200 kernel launches hot_path_frame issues (memset nodes not counted)."""
+def launches_per_frame(iters, first_frame, hidden_levels=3, mode="pyramid", num_levels=4, fused_build=True, warp_lists=False):
+    """Number of libtcs_b200 kernel launches hot_path_frame issues (memset nodes not counted).  warp_lists: the warp
+    runs its list formulation on a carried transposition (a HotPathRunner's frames after the second)."""
     n = (1 if fused_build else 3) if mode == "pyramid" else 2 + (num_levels - 1)   # fused build | prepass x2 + build | prepass x2 + pools
     if first_frame:
         n += 1 if mode == "pyramid" else 2                         # argmax (+ an on-demand level-0 build)
         if mode != "pyramid":
             n += 2                                                 # its prepasses
     else:
-        n += 4 + 1 + hidden_levels + (hidden_levels - 1)           # geometry, weights, splat, finalize; grid; gathers; halves
+        # scatter: geometry, weights, splat, cost | lists: geometry, weights, count, row sums, offsets, fill, sort, cost
+        n += (8 if warp_lists else 4) + 1 + hidden_levels + (hidden_levels - 1)   # + grid; gathers; halves
     return n + iters
 
 
@@ -130,10 +136,14 @@ class HotPathRunner:
         self.last_disp = None
         self.last_fmap1 = None
         self.last_net_list = None
+        self._carry = [geo.WarpCarry(), geo.WarpCarry()]     # fmap1 transposed for the next frame, double-buffered
+        self._frame = 0
 
     def frame(self, fmap1, fmap2, coords_seq, net_list=None, **camera):
         state = None if self.last_disp is None else (self.last_disp, self.last_fmap1, self.last_net_list)
-        out = hot_path_frame(fmap1, fmap2, coords_seq, state=state, **camera, **self.kw)
+        out = hot_path_frame(fmap1, fmap2, coords_seq, state=state, **camera, **self.kw,
+                             carry_in=self._carry[(self._frame + 1) % 2], carry_out=self._carry[self._frame % 2])
+        self._frame += 1
         W = fmap1.shape[3]
         xs = torch.arange(W, device=fmap1.device, dtype=torch.float32).view(1, 1, 1, W)
         self.last_disp = (xs - coords_seq[-1]).clamp_min(0)      # disp = coords0 - coords1; flow_q is clipped at 0

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libtcs_b200.so does not export %s" % n
     assert sorted(tcs_b200._lib.SIGNATURES) == names, "ctypes signatures and header disagree"
-    assert lib.tcs_abi_version() == 1
+    assert lib.tcs_abi_version() == tcs_b200._lib.ABI_VERSION == 2
 
 
 def test_argument_errors_are_reported_without_a_gpu():
@@ -187,3 +187,5 @@ def test_launch_count_model():
     assert sequence.launches_per_frame(32, False) == 1 + 4 + 1 + 3 + 2 + 32   # fused build; geometry, weights, splat, finalize; grid; 3 gathers; 2 halvings; lookups
     assert sequence.launches_per_frame(32, True) == 1 + 1 + 32
     assert sequence.launches_per_frame(32, False, fused_build=False) == sequence.launches_per_frame(32, False) + 2
+    # list formulation on a carried transposition: geometry, weights, count, row sums, offsets, fill, sort, cost
+    assert sequence.launches_per_frame(32, False, warp_lists=True) == 1 + 8 + 1 + 3 + 2 + 32

@@ -447,6 +447,47 @@ def test_warp_is_deterministic(tcs):
             assert torch.equal(x, y)
 
 
+def test_warp_carry_skips_the_transposition_and_changes_nothing(tcs):
+    """Frame t's cost kernel hands fmap1_t on transposed (WarpCarry); frame t+1's warp of that very tensor reads the rows
+    instead of transposing again.  Same bits as the list formulation without a carry; a stale or foreign carry is ignored."""
+    B, H, W = 2, 40, 96
+    K, Kinv, T, _, base = camera(B, H, W, 7)
+    g = torch.Generator().manual_seed(3)
+    disp = (0.5 + torch.rand(B, 1, H, W, generator=g) * 6).cuda()
+    f_prev = torch.randn(B, 128, H, W, generator=g).cuda()
+    f_cur = torch.randn(B, 128, H, W, generator=g).cuda()
+    f_next = torch.randn(B, 128, H, W, generator=g).cuda()
+    cam = (cuda(T), cuda(K), cuda(Kinv), cuda(base))
+    c0, c1 = tcs.WarpCarry(), tcs.WarpCarry()
+    # frame t: warps f_prev, cost against f_cur, carry_out <- f_cur transposed
+    a = tcs.warp_with_cost(disp, f_prev, *cam, cur_fmap=f_cur, want_fmap=False, carry_out=c0)
+    assert c0.tensor is f_cur and tuple(c0.rows.shape) == (B * H * W, 128)
+    rows = c0.rows.view(B, H, W, 128)
+    perm = torch.tensor([lane + 32 * q for lane in range(32) for q in range(4)])       # position 4*lane + q <-> channel lane + 32 q
+    assert torch.equal(rows, f_cur.permute(0, 2, 3, 1)[..., perm])
+    # frame t+1: warps f_cur (the carried tensor)
+    ref = tcs.warp_with_cost(disp, f_cur, *cam, cur_fmap=f_next, want_fmap=False, deterministic=True)
+    got = tcs.warp_with_cost(disp, f_cur, *cam, cur_fmap=f_next, want_fmap=False, carry_in=c0, carry_out=c1)
+    for x, y in zip(ref, got):
+        assert (x is None and y is None) or torch.equal(x, y)
+    rd, rf, rm = orc.warp(host(disp), host(f_cur), T, K, Kinv, base)
+    assert_exact(host(got[2]), rm, what="splat mask (carry)")
+    assert_close(host(got[3]), orc.matching_cost(host(f_next), rf, rm), rtol=1e-5, atol=2e-6, what="matching cost (carry)")
+    # a carry keyed on another tensor, or on a tensor modified since, must not be used
+    other = f_cur.clone()
+    o1 = tcs.warp_with_cost(disp, other, *cam, cur_fmap=f_next, want_fmap=False, carry_in=c0)
+    s1 = tcs.warp_with_cost(disp, other, *cam, cur_fmap=f_next, want_fmap=False)
+    assert torch.equal(o1[2], s1[2])
+    f_cur.mul_(2.0)                                    # bumps the version: the rows are stale now
+    assert not c0.matches(f_cur)
+    stale = tcs.warp_with_cost(disp, f_cur, *cam, cur_fmap=f_next, want_fmap=False, carry_in=c0, deterministic=True)
+    fresh = tcs.warp_with_cost(disp, f_cur, *cam, cur_fmap=f_next, want_fmap=False, deterministic=True)
+    for x, y in zip(stale, fresh):
+        assert (x is None and y is None) or torch.equal(x, y)
+    with pytest.raises(ValueError):
+        tcs.warp_with_cost(disp, f_cur, *cam, cur_fmap=f_next, want_fmap=True, carry_out=c1)
+
+
 def test_warp_identity_pose_keeps_everything(tcs):
     """Zero motion: every pixel lands on itself, the splat is the identity and the mask is all ones."""
     B, H, W = 1, 24, 48
