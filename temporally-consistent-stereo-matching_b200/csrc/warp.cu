@@ -218,7 +218,7 @@ template <int kGroups>
 __device__ __forceinline__ void gather_target(const ListArgs& la, size_t sample_px0, int s0, int n, int lane,
                                               float4 (&a)[kGroups], float2& tail) {
     constexpr int C = kGroups * 128;
-    constexpr int kE = 4;                                       // entries per round: 4 * kGroups 16-byte loads in flight per lane (2: spills, 370 us)
+    constexpr int kE = 4;                                       // entries per round: 4 * kGroups 16-byte loads in flight per lane
 #pragma unroll
     for (int j = 0; j < kGroups; ++j) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     float norm = 0.0f, dsum = 0.0f;
@@ -281,10 +281,52 @@ warp_transpose_kernel(const float* __restrict__ fmap, float* __restrict__ dst, i
 // ---- forward warp, kernel C': the same when the caller wants only the cost (tc_stereo.py:139-140 is all the model
 // reads of the warped features).  No warped-feature tile and no per-channel divisions: the CURRENT features are
 // transposed through shared memory instead, each warp walks its pixels with the accumulator row straight from
-// global memory (scaled by one reciprocal per pixel, so the range stays that of the normalised features), and the
-// three sums of the cosine are warp-reduced in a fixed order.
+// global memory -- or, kLists, summed from the target's contributor list -- scaled by one reciprocal per pixel (so
+// the range stays that of the normalised features), and the three sums of the cosine are warp-reduced in a fixed
+// order.  cur_t_out (nullable) receives the current features as pixel-major rows: next frame's source.
+template <int kGroups>
+__device__ __forceinline__ void cost_pixel(const float4 (&a)[kGroups], float2 tail, const float* tile, int wl, bool live, int lane,
+                                           size_t tpix, float* __restrict__ out_disp, float* __restrict__ out_mask,
+                                           float* __restrict__ out_cost, float* __restrict__ cur_t_out) {
+    constexpr int C = kGroups * 128;
+    const float nrm = fmaxf(tail.y, 1e-7f);                     // clip(1e-7, None)   softsplat.py:268
+    const float m = (tail.y != 0.0f) ? 1.0f : 0.0f;             // softsplat.py:258
+    const float r = __fdiv_rn(1.0f, nrm);
+    float dot = 0.0f, s1 = 0.0f, sw = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kGroups; ++j) {
+        const float av[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+        float fq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                            // accumulator position 128j + 4 lane + q  <->  channel below
+            const float fv = tile[(lane + 32 * (4 * j + q)) * 33 + wl];
+            const float v = __fmul_rn(av[q], r);
+            fq[q] = fv;
+            dot = fmaf(fv, v, dot);
+            s1 = fmaf(fv, fv, s1);
+            sw = fmaf(v, v, sw);
+        }
+        // the current features are next frame's source: hand them on already transposed (pixel-major, permuted)
+        if (cur_t_out != nullptr && live)
+            *reinterpret_cast<float4*>(cur_t_out + tpix * C + j * 128 + 4 * lane) = make_float4(fq[0], fq[1], fq[2], fq[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        sw += __shfl_xor_sync(0xffffffffu, sw, o);
+    }
+    if (lane == 0 && live) {
+        out_disp[tpix] = __fdiv_rn(tail.x, nrm);
+        out_mask[tpix] = m;
+        // sum_c normalize(f)_c * normalize(v)_c  (F.normalize eps 1e-12), times the splat mask (tc_stereo.py:139-140)
+        const float den = __fmul_rn(fmaxf(sqrtf(s1), 1e-12f), fmaxf(sqrtf(sw), 1e-12f));
+        out_cost[tpix] = __fmul_rn(__fdiv_rn(dot, den), m);
+    }
+}
+
 template <int kGroups, bool kLists>
-__global__ void __launch_bounds__(kWarpThreads, kLists ? 3 : 4)   // 80 / 64 registers; a fourth list block would spill
+__global__ void __launch_bounds__(kWarpThreads, 4)   // 64 registers; lists: 3 CTAs at 80 registers 0.379 ms, 5 at 48 spill (0.42 ms)
 warp_cost_kernel(const float* __restrict__ accum, const ListArgs la, const float* __restrict__ cur_fmap, float* __restrict__ out_disp,
                  float* __restrict__ out_mask, float* __restrict__ out_cost, float* __restrict__ cur_t_out, int H, int W) {
     constexpr int C = kGroups * 128;
@@ -298,13 +340,14 @@ warp_cost_kernel(const float* __restrict__ accum, const ListArgs la, const float
     const bool in_w = w < W;
     const size_t plane = (size_t)H * W;
     const size_t base = ((size_t)b * C * H + h) * W + w;
+    const size_t row_px = ((size_t)b * H + h) * W;
     int ls0[kPx], ln[kPx];                     // list offsets of this warp's targets: fetched first, needed last
     if (kLists) {
 #pragma unroll
         for (int i = 0; i < kPx; ++i) {
             const int wl = warp * kPx + i;
             const bool live = w0 + wl < W;
-            const size_t tpix = ((size_t)b * H + h) * W + (live ? w0 + wl : 0);
+            const size_t tpix = row_px + (live ? w0 + wl : 0);
             ls0[i] = __ldg(la.start + tpix);
             ln[i] = live ? __ldg(la.start + tpix + 1) - ls0[i] : 0;
         }
@@ -313,72 +356,42 @@ warp_cost_kernel(const float* __restrict__ accum, const ListArgs la, const float
 #pragma unroll
     for (int k = 0; k < kPerWarp; ++k)
         f[k] = in_w ? ldg_stream_f1(cur_fmap + base + (size_t)(warp + 8 * k) * plane) : 0.0f;
-    if (kLists) {                              // park the tile first: the gather below needs the registers
+    if (kLists) {
+        // lists: one pixel at a time (gather, then its cosine), so only one accumulator row is live in registers and
+        // the block's only barrier comes before the list walks, whose lengths differ from warp to warp
 #pragma unroll
         for (int k = 0; k < kPerWarp; ++k) tile[(warp + 8 * k) * 33 + lane] = f[k];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kPx; ++i) {
+            const int wl = warp * kPx + i;
+            const bool live = w0 + wl < W;
+            float4 a[kGroups];
+            float2 tail;
+            gather_target<kGroups>(la, (size_t)b * plane, ls0[i], ln[i], lane, a, tail);   // n = 0 for a dead pixel
+            cost_pixel<kGroups>(a, tail, tile, wl, live, lane, row_px + w0 + wl, out_disp, out_mask, out_cost, cur_t_out);
+        }
+        return;
     }
     float2 tail[kPx];
     float4 a[kPx][kGroups];
 #pragma unroll
-    for (int i = 0; i < kPx; ++i) {
+    for (int i = 0; i < kPx; ++i) {            // all rows of the warp's pixels in flight at once
         const int wl = warp * kPx + i;
         const bool live = w0 + wl < W;
-        const size_t tpix = ((size_t)b * H + h) * W + (live ? w0 + wl : 0);
-        if (kLists) {
-            gather_target<kGroups>(la, (size_t)b * plane, ls0[i], ln[i], lane, a[i], tail[i]);   // n = 0 for a dead pixel
-        } else {
-            const float* src = accum + tpix * CP;
-            tail[i] = live ? *reinterpret_cast<const float2*>(src + C) : make_float2(0.f, 0.f);
+        const float* src = accum + (row_px + (live ? w0 + wl : 0)) * CP;
+        tail[i] = live ? *reinterpret_cast<const float2*>(src + C) : make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < kGroups; ++j)
-                a[i][j] = live ? ldg_stream_f4(reinterpret_cast<const float4*>(src + j * 128 + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int j = 0; j < kGroups; ++j)
+            a[i][j] = live ? ldg_stream_f4(reinterpret_cast<const float4*>(src + j * 128 + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (!kLists) {
 #pragma unroll
-        for (int k = 0; k < kPerWarp; ++k) tile[(warp + 8 * k) * 33 + lane] = f[k];
-    }
+    for (int k = 0; k < kPerWarp; ++k) tile[(warp + 8 * k) * 33 + lane] = f[k];
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kPx; ++i) {
         const int wl = warp * kPx + i;
-        const bool live = w0 + wl < W;
-        const float nrm = fmaxf(tail[i].y, 1e-7f);              // clip(1e-7, None)   softsplat.py:268
-        const float m = (tail[i].y != 0.0f) ? 1.0f : 0.0f;      // softsplat.py:258
-        const float r = __fdiv_rn(1.0f, nrm);
-        float dot = 0.0f, s1 = 0.0f, sw = 0.0f;
-#pragma unroll
-        for (int j = 0; j < kGroups; ++j) {
-            const float av[4] = {a[i][j].x, a[i][j].y, a[i][j].z, a[i][j].w};
-            float fq[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {                        // accumulator position 128j + 4 lane + q  <->  channel below
-                const float fv = tile[(lane + 32 * (4 * j + q)) * 33 + wl];
-                const float v = __fmul_rn(av[q], r);
-                fq[q] = fv;
-                dot = fmaf(fv, v, dot);
-                s1 = fmaf(fv, fv, s1);
-                sw = fmaf(v, v, sw);
-            }
-            // the current features are next frame's source: hand them on already transposed (pixel-major, permuted)
-            if (cur_t_out != nullptr && live)
-                *reinterpret_cast<float4*>(cur_t_out + (((size_t)b * H + h) * W + w0 + wl) * C + j * 128 + 4 * lane) =
-                    make_float4(fq[0], fq[1], fq[2], fq[3]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            sw += __shfl_xor_sync(0xffffffffu, sw, o);
-        }
-        if (lane == 0 && live) {
-            const size_t idx = ((size_t)b * H + h) * W + w0 + wl;
-            out_disp[idx] = __fdiv_rn(tail[i].x, nrm);
-            out_mask[idx] = m;
-            // sum_c normalize(f)_c * normalize(v)_c  (F.normalize eps 1e-12), times the splat mask (tc_stereo.py:139-140)
-            const float den = __fmul_rn(fmaxf(sqrtf(s1), 1e-12f), fmaxf(sqrtf(sw), 1e-12f));
-            out_cost[idx] = __fmul_rn(__fdiv_rn(dot, den), m);
-        }
+        cost_pixel<kGroups>(a[i], tail[i], tile, wl, w0 + wl < W, lane, row_px + w0 + wl, out_disp, out_mask, out_cost, cur_t_out);
     }
 }
 
