@@ -501,43 +501,6 @@ warp_finalize_kernel(const float* __restrict__ accum, const ListArgs la, const f
 }
 
 // ---- forward warp, kernel A2: soft-splat weight of every source pixel -----------------------------------------
-// wgt = valid * exp(clamp(disp' - mean, -50, 50)), 0 for pixels the splat skips (invalid, non-finite target).
-__global__ void __launch_bounds__(256)
-warp_weight_kernel(const float* __restrict__ disp1, const float* __restrict__ tx, const float* __restrict__ ty,
-                   float* __restrict__ valid_to_wgt, const double* __restrict__ sums,
-                   int B, int HW, int per_sample_mean) {
-    const int b = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= HW) return;
-    // softsplat metric: disparity minus its mean (geo_utils.py:193); batch-global unless asked otherwise
-    double s = 0.0, n;
-    if (per_sample_mean) {
-        s = sums[b];
-        n = (double)HW;
-    } else {
-        for (int k = 0; k < B; ++k) s += sums[k];
-        n = (double)B * HW;
-    }
-    const float mean = (float)(s / n);
-    const size_t o = (size_t)b * HW + i;
-    float w = 0.0f;
-    if (valid_to_wgt[o] != 0.0f && isfinite(tx[o]) && isfinite(ty[o]))      // softsplat.py:236,300-301
-        w = expf(fminf(fmaxf(__fsub_rn(disp1[o], mean), -50.0f), 50.0f));
-    valid_to_wgt[o] = w;
-}
-
-// ---- forward warp, list formulation ---------------------------------------------------------------------------
-// The scatter above moves every accumulator byte through DRAM four times (memset, red read-modify-write, finalize
-// read).  The same sum can be collected from the target's side without any accumulator if each target knows who
-// feeds it.  So: (1) count the contributions each target receives (one int atomic per corner instead of 65 vector
-// reds), (2) prefix-sum the counts into list offsets (per row, then across rows), (3) fill the lists with
-// (source pixel, e * bilinear weight), (4) one pass over the targets: walk the list, gather the source features
-// straight from the NCHW map (lanes are neighbouring targets, their sources are neighbours too: coalesced), divide
-// by the summed weights, write mask / disparity / features and fold the matching cost in.  Any flow field is
-// handled (the lists are exact, CSR) and each list is sorted by source index first, which fixes the summation order
-// (the reference's atomic scatter is unordered): this is the TCS_WARP_DETERMINISTIC mode.  The gather of NCHW
-// features at per-lane source pixels costs ~6 sectors per request with i.i.d. flow and the kernel is latency-bound
-// (636 us against 374 us for the scatter at 540p x 8), so the scatter stays the default.
 struct SplatCorners {
     int t[4];      // target pixel index inside the sample, -1 when outside the image or the product is zero
     float w[4];    // e * bilinear weight
@@ -563,10 +526,52 @@ __device__ __forceinline__ SplatCorners splat_corners(float e, float fx_, float 
     return c;
 }
 
-// (1) and (3): kFill = false counts, kFill = true appends (cnt then serves as the cursor and ends at zero).
-template <bool kFill>
+// wgt = valid * exp(clamp(disp' - mean, -50, 50)), 0 for pixels the splat skips (invalid, non-finite target).
 __global__ void __launch_bounds__(256)
-warp_list_kernel(const float* __restrict__ wgt, const float* __restrict__ tx, const float* __restrict__ ty,
+warp_weight_kernel(const float* __restrict__ disp1, const float* __restrict__ tx, const float* __restrict__ ty,
+                   float* __restrict__ valid_to_wgt, const double* __restrict__ sums,
+                   int B, int HW, int per_sample_mean, int* __restrict__ cnt, int H, int W) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW) return;
+    // softsplat metric: disparity minus its mean (geo_utils.py:193); batch-global unless asked otherwise
+    double s = 0.0, n;
+    if (per_sample_mean) {
+        s = sums[b];
+        n = (double)HW;
+    } else {
+        for (int k = 0; k < B; ++k) s += sums[k];
+        n = (double)B * HW;
+    }
+    const float mean = (float)(s / n);
+    const size_t o = (size_t)b * HW + i;
+    float w = 0.0f;
+    if (valid_to_wgt[o] != 0.0f && isfinite(tx[o]) && isfinite(ty[o]))      // softsplat.py:236,300-301
+        w = expf(fminf(fmaxf(__fsub_rn(disp1[o], mean), -50.0f), 50.0f));
+    valid_to_wgt[o] = w;
+    if (cnt != nullptr && w != 0.0f) {          // list formulation, step (1): contributions per target
+        const SplatCorners c = splat_corners(w, tx[o], ty[o], H, W);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c.t[k] >= 0) atomicAdd(cnt + (size_t)b * HW + c.t[k], 1);
+    }
+}
+
+// ---- forward warp, list formulation ---------------------------------------------------------------------------
+// The scatter above moves every accumulator byte through DRAM four times (memset, red read-modify-write, finalize
+// read).  The same sum can be collected from the target's side without any accumulator if each target knows who
+// feeds it.  So: (1) count the contributions each target receives (one int atomic per corner instead of 65 vector
+// reds), (2) prefix-sum the counts into list offsets (per row, then across rows), (3) fill the lists with
+// (source pixel, e * bilinear weight), (4) one pass over the targets: walk the list, gather the source features
+// straight from the NCHW map (lanes are neighbouring targets, their sources are neighbours too: coalesced), divide
+// by the summed weights, write mask / disparity / features and fold the matching cost in.  Any flow field is
+// handled (the lists are exact, CSR) and each list is sorted by source index first, which fixes the summation order
+// (the reference's atomic scatter is unordered): this is the TCS_WARP_DETERMINISTIC mode.  The gather of NCHW
+// features at per-lane source pixels costs ~6 sectors per request with i.i.d. flow and the kernel is latency-bound
+// (636 us against 374 us for the scatter at 540p x 8), so the scatter stays the default.
+// (3) append the entries (the counters of step (1), made by warp_weight_kernel, serve as cursors and end at zero).
+__global__ void __launch_bounds__(256)
+warp_fill_kernel(const float* __restrict__ wgt, const float* __restrict__ tx, const float* __restrict__ ty,
                  int* __restrict__ cnt, const int* __restrict__ start, int2* __restrict__ entries, int H, int W) {
     const int b = blockIdx.y;
     const int HW = H * W;
@@ -580,12 +585,8 @@ warp_list_kernel(const float* __restrict__ wgt, const float* __restrict__ tx, co
     for (int k = 0; k < 4; ++k) {
         if (c.t[k] < 0) continue;
         const size_t t = (size_t)b * HW + c.t[k];
-        if (!kFill) {
-            atomicAdd(cnt + t, 1);
-        } else {
-            const int slot = atomicSub(cnt + t, 1) - 1;
-            entries[(size_t)__ldg(start + t) + slot] = make_int2(i, __float_as_int(c.w[k]));
-        }
+        const int slot = atomicSub(cnt + t, 1) - 1;
+        entries[(size_t)__ldg(start + t) + slot] = make_int2(i, __float_as_int(c.w[k]));
     }
 }
 
@@ -836,7 +837,8 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
     const dim3 pgrid(ceil_div(H * W, 256), B);
     warp_geometry_kernel<<<pgrid, 256, 0, s>>>(disp, rel_T, K, K_inv, baseline, disp1, tx, ty, valid, sums, H, W);
     TCS_CHECK_LAUNCH("tcs_warp_forward(geometry)");
-    warp_weight_kernel<<<pgrid, 256, 0, s>>>(disp1, tx, ty, valid, sums, B, H * W, per_sample_mean);
+    warp_weight_kernel<<<pgrid, 256, 0, s>>>(disp1, tx, ty, valid, sums, B, H * W, per_sample_mean,
+                                             lists ? reinterpret_cast<int*>(base + L.cnt) : nullptr, H, W);
     TCS_CHECK_LAUNCH("tcs_warp_forward(weights)");
     ListArgs la = {nullptr, nullptr, nullptr, nullptr};
     if (lists) {
@@ -851,13 +853,11 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
         la.disp1 = disp1;
         const long long npix = (long long)B * H * W;
         TCS_REQUIRE(npix * 4 < 0x7fffffffLL, TCS_E_SHAPE, "tcs_warp_forward: too many pixels for 32-bit list offsets");
-        warp_list_kernel<false><<<pgrid, 256, 0, s>>>(valid, tx, ty, cnt, start, entries, H, W);
-        TCS_CHECK_LAUNCH("tcs_warp_forward(count)");
         warp_rowsum_kernel<<<B * H, 256, 0, s>>>(cnt, rowtot, W);
         TCS_CHECK_LAUNCH("tcs_warp_forward(row sums)");
         warp_offsets_kernel<<<B * H, 256, 0, s>>>(cnt, rowtot, start, W, B * H);
         TCS_CHECK_LAUNCH("tcs_warp_forward(offsets)");
-        warp_list_kernel<true><<<pgrid, 256, 0, s>>>(valid, tx, ty, cnt, start, entries, H, W);
+        warp_fill_kernel<<<pgrid, 256, 0, s>>>(valid, tx, ty, cnt, start, entries, H, W);
         TCS_CHECK_LAUNCH("tcs_warp_forward(fill)");
         warp_sort_kernel<<<(unsigned)ceil_div_ll(npix, 256), 256, 0, s>>>(start, entries, npix);
         TCS_CHECK_LAUNCH("tcs_warp_forward(sort)");

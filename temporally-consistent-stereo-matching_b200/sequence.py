@@ -119,8 +119,8 @@ def launches_per_frame(iters, first_frame, hidden_levels=3, mode="pyramid", num_
         if mode != "pyramid":
             n += 2                                                 # its prepasses
     else:
-        # scatter: geometry, weights, splat, cost | lists: geometry, weights, count, row sums, offsets, fill, sort, cost
-        n += (8 if warp_lists else 4) + 1 + hidden_levels + (hidden_levels - 1)   # + grid; gathers; halves
+        # scatter: geometry, weights, splat, cost | lists: geometry, weights + count, row sums, offsets, fill, sort, cost
+        n += (7 if warp_lists else 4) + 1 + hidden_levels + (hidden_levels - 1)   # + grid; gathers; halves
     return n + iters
 
 

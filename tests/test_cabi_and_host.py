@@ -187,5 +187,5 @@ def test_launch_count_model():
     assert sequence.launches_per_frame(32, False) == 1 + 4 + 1 + 3 + 2 + 32   # fused build; geometry, weights, splat, finalize; grid; 3 gathers; 2 halvings; lookups
     assert sequence.launches_per_frame(32, True) == 1 + 1 + 32
     assert sequence.launches_per_frame(32, False, fused_build=False) == sequence.launches_per_frame(32, False) + 2
-    # list formulation on a carried transposition: geometry, weights, count, row sums, offsets, fill, sort, cost
-    assert sequence.launches_per_frame(32, False, warp_lists=True) == 1 + 8 + 1 + 3 + 2 + 32
+    # list formulation on a carried transposition: geometry, weights + count, row sums, offsets, fill, sort, cost
+    assert sequence.launches_per_frame(32, False, warp_lists=True) == 1 + 7 + 1 + 3 + 2 + 32
