@@ -186,6 +186,22 @@ int tcs_bilinear_sample(const float* img, const float* grid_xy, float* out,
  * align_corners=True).  in [B,2,H,W] -> out [B,2,H/2,W/2]. */
 int tcs_grid_halve(const float* in, float* out, int B, int H, int W, void* stream);
 
+/* ---- (5) "next" row: the per-GRU-iteration 3x3 stencils on the disparity ---------- */
+
+/* ref: core/utils/geo_utils.py:115-132 (disp2disp_gradient_xy).  disp [N,1,H,W] -> grads [N,2,H,W] (forward
+ * differences in x and y on the replicate-padded map) and edge_mask [N,1,H,W] bytes (|gx| < 5 && |gy| < 5; nullable). */
+int tcs_disp_gradient_xy(const float* disp, float* grads, unsigned char* edge_mask, int N, int H, int W, void* stream);
+
+/* ref: core/utils/geo_utils.py:73-101 (disp2disp_grad_candidates).  disp [N,1,H,W] -> out [N,2,8*levels,H,W]:
+ * -n_xy / n_z of the normals of the triangles (centre, ring[k], ring[k+2]) on the zero-padded map, rings at distance
+ * 1..levels concatenated before the pairing.  levels 1..4. */
+int tcs_disp_grad_candidates(const float* disp, float* out, int N, int H, int W, int levels, void* stream);
+
+/* ref: core/update.py:259-289 (DispRefine.propagate_disparity).  grad [N,2,H,W], disp [N,1,H,W] -> prop [N,9,H,W]
+ * (the neighbour's disparity extrapolated along its gradient to the centre) and matrix [N,18,H,W] (|grad_c - grad_nb|,
+ * channel = component * 9 + neighbour). */
+int tcs_disp_propagate(const float* grad, const float* disp, float* prop, float* matrix, int N, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -337,3 +337,69 @@ def warp_hidden_states(net_list, grid_xy):
         if i + 1 < len(net_list):
             g = grid_halve(g)
     return out
+
+
+# ---- "next" row: the per-GRU-iteration 3x3 stencils ------------------------------------
+
+RING_VU = [(0, 0), (0, 1), (0, 2), (1, 2), (2, 2), (2, 1), (2, 0), (1, 0)]     # geo_utils.py:83
+
+
+def disp_gradient_xy(disp):
+    """ref: core/utils/geo_utils.py:115-132 (disp2disp_gradient_xy).  disp [N,1,H,W] -> (grads [N,2,H,W], edge_mask
+    [N,1,H,W] bool): forward differences on the replicate-padded map; the mask keeps |gx| < 5 and |gy| < 5."""
+    d = _f(disp)
+    pad = np.pad(d, ((0, 0), (0, 0), (1, 1), (1, 1)), mode="edge")
+    c = pad[:, :, 1:-1, 1:-1]
+    gx = pad[:, :, 1:-1, 2:] - c                                    # kernel (v,u) = (1,2) minus the centre
+    gy = pad[:, :, 2:, 1:-1] - c                                    # kernel (2,1) minus the centre
+    grads = np.concatenate([gx, gy], axis=1).astype(F32)
+    return grads, (np.abs(gx) < 5) & (np.abs(gy) < 5)
+
+
+def disp_grad_candidates(disp, level=1):
+    """ref: core/utils/geo_utils.py:73-101 (disp2disp_grad_candidates).  disp [N,1,H,W] -> [N,2,8*level,H,W]."""
+    d = _f(disp)
+    N, _, H, W = d.shape
+    vecs = []                                                        # per candidate: (dx, dy, ddisp) as [N,H,W] arrays
+    for i in range(level):
+        r = i + 1
+        pad = np.pad(d[:, 0], ((0, 0), (r, r), (r, r)))             # zeros (F.pad default)
+        c = pad[:, r:r + H, r:r + W]
+        for v, u in RING_VU:                                         # dilation r: neighbour at ((v-1) r, (u-1) r)
+            dy, dx = (v - 1) * r, (u - 1) * r
+            nb = pad[:, r + dy:r + dy + H, r + dx:r + dx + W]
+            vecs.append((np.full((N, H, W), dx, F32), np.full((N, H, W), dy, F32), (nb - c).astype(F32)))
+    K = len(vecs)
+    out = np.empty((N, 2, K, H, W), F32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for k in range(K):
+            ax, ay, ad = vecs[k]
+            bx, by, bd = vecs[(k + 2) % K]                           # torch.roll(grads, -2, dims=2)
+            c0 = (ay * bd - ad * by).astype(F32)                     # torch.cross along (x, y, disp)
+            c1 = (ad * bx - ax * bd).astype(F32)
+            c2 = (ax * by - ay * bx).astype(F32)
+            out[:, 0, k] = (-c0) / c2
+            out[:, 1, k] = (-c1) / c2
+    return out
+
+
+def disp_propagate(disparity_grad, disparity_map):
+    """ref: core/update.py:259-289 (DispRefine.propagate_disparity).  grad [N,2,H,W], disp [N,1,H,W] ->
+    (propagated [N,9,H,W], matrix [N,18,H,W])."""
+    g = _f(disparity_grad)
+    d = _f(disparity_map)
+    N, _, H, W = g.shape
+    gp = np.pad(g, ((0, 0), (0, 0), (1, 1), (1, 1)))                # zeros
+    dp = np.pad(d, ((0, 0), (0, 0), (1, 1), (1, 1)), mode="edge")   # replicate
+    prop = np.empty((N, 9, H, W), F32)
+    matrix = np.empty((N, 18, H, W), F32)
+    for k in range(9):
+        v, u = divmod(k, 3)                                          # update.py:221: row-major 3x3
+        m = dp[:, 0, v:v + H, u:u + W]
+        gx = gp[:, 0, v:v + H, u:u + W]
+        gy = gp[:, 1, v:v + H, u:u + W]
+        cx, cy = F32(1 - u), F32(1 - v)                              # centre minus neighbour coordinates
+        prop[:, k] = ((m + gx * cx).astype(F32) + gy * cy).astype(F32)
+        matrix[:, k] = np.abs(g[:, 0] - gx)
+        matrix[:, 9 + k] = np.abs(g[:, 1] - gy)
+    return prop, matrix

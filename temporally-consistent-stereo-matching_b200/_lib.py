@@ -40,6 +40,9 @@ SIGNATURES = {
     "tcs_backward_grid": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "tcs_bilinear_sample": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_grid_halve": (_i, [_p, _p, _i, _i, _i, _p]),
+    "tcs_disp_gradient_xy": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "tcs_disp_grad_candidates": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "tcs_disp_propagate": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
 }
 
 _lib = None

@@ -8,8 +8,12 @@ _saved = {}
 _NAMES = ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler")
 
 
-def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=None):
+def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=None, stencils=None):
     """tc_stereo_module: the imported `core.tc_stereo`.  Returns the dict of names that were replaced.
+
+    stencils: the imported `core.update`.  When given, the three per-iteration 3x3 stencils also run as single kernels
+    (SURVEY.md section 8f rank 2): `disp2disp_gradient_xy` (tc_stereo.py:192), `disp2disp_grad_candidates`
+    (update.py:202) and `DispRefine.propagate_disparity` (update.py:294); fp32, inference only.
 
     fuse_motion_encoder: the imported `core.update`.  When given, corr_fn(coords) returns a deferred lookup and
     BasicMotionEncoder.forward (update.py:103-112) evaluates `relu(convc1(corr))` with the fused lookup + 1x1
@@ -32,6 +36,8 @@ def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=Non
         block = _Configured
     if fuse_motion_encoder is not None:
         _patch_motion_encoder(fuse_motion_encoder)
+    if stencils is not None:
+        _patch_stencils(tc_stereo_module, stencils)
     new = {"CorrBlock1D": block, "warp": geo.warp, "get_backward_grid": geo.get_backward_grid,
            "bilinear_sampler": geo.bilinear_sampler}
     for name in _NAMES:
@@ -64,11 +70,36 @@ def _patch_motion_encoder(update_module):
     enc.forward = forward
 
 
+def _patch_stencils(tc_stereo_module, update_module):
+    from . import geo
+
+    _saved.setdefault((id(tc_stereo_module), "disp2disp_gradient_xy"), tc_stereo_module.disp2disp_gradient_xy)
+    tc_stereo_module.disp2disp_gradient_xy = geo.disp2disp_gradient_xy
+    _saved.setdefault((id(update_module), "disp2disp_grad_candidates"), update_module.disp2disp_grad_candidates)
+    update_module.disp2disp_grad_candidates = geo.disp2disp_grad_candidates
+    ref = update_module.DispRefine
+    _saved.setdefault((id(update_module), "DispRefine.propagate_disparity"), ref.propagate_disparity)
+
+    def propagate_disparity(self, disparity_grad, disparity_map):       # update.py:259-289
+        return geo.propagate_disparity(disparity_grad, disparity_map)
+
+    ref.propagate_disparity = propagate_disparity
+
+
 def uninstall(tc_stereo_module, update_module=None):
     if update_module is not None:
         old = _saved.pop((id(update_module), "BasicMotionEncoder.forward"), None)
         if old is not None:
             update_module.BasicMotionEncoder.forward = old
+        old = _saved.pop((id(update_module), "disp2disp_grad_candidates"), None)
+        if old is not None:
+            update_module.disp2disp_grad_candidates = old
+        old = _saved.pop((id(update_module), "DispRefine.propagate_disparity"), None)
+        if old is not None:
+            update_module.DispRefine.propagate_disparity = old
+    old = _saved.pop((id(tc_stereo_module), "disp2disp_gradient_xy"), None)
+    if old is not None:
+        tc_stereo_module.disp2disp_gradient_xy = old
     for name in _NAMES:
         old = _saved.pop((id(tc_stereo_module), name), None)
         if old is not None:

@@ -209,3 +209,50 @@ def warp_hidden_states(net_list, backward_grid):
 def cal_relative_transformation(T1, T2):
     """ref: geo_utils.py:148-155.  T2 @ inv(T1) for world2cam poses.  4x4 bookkeeping, stays in torch."""
     return torch.matmul(T2, torch.linalg.inv(T1))
+
+
+# ---- "next" row (SURVEY.md section 8f rank 2): the per-GRU-iteration 3x3 stencils on the disparity ------------------
+
+def _disp_map(name, t):
+    t = _f32c(name, t)
+    if t.dim() != 4 or t.shape[1] != 1:
+        raise ValueError("%s must be [N,1,H,W], got %s" % (name, tuple(t.shape)))
+    return t
+
+
+def disp2disp_gradient_xy(disp):
+    """ref: geo_utils.py:115-132.  disp [N,1,H,W] -> (grads [N,2,H,W], edge_mask [N,1,H,W] bool), one kernel."""
+    disp = _disp_map("disp", disp)
+    N, _, H, W = disp.shape
+    grads = torch.empty((N, 2, H, W), dtype=torch.float32, device=disp.device)
+    edge = torch.empty((N, 1, H, W), dtype=torch.bool, device=disp.device)
+    with torch.cuda.device(disp.device):
+        _lib.call("tcs_disp_gradient_xy", disp.data_ptr(), grads.data_ptr(), edge.data_ptr(), N, H, W, _stream())
+    return grads, edge
+
+
+def disp2disp_grad_candidates(disp, level=1):
+    """ref: geo_utils.py:73-101.  disp [N,1,H,W] -> [N,2,8*level,H,W], one kernel (bit-identical for level <= 2, the
+    model's setting; level 3 and 4 multiply by 3 and agree to an ulp)."""
+    disp = _disp_map("disp", disp)
+    if not 1 <= int(level) <= 4:
+        raise ValueError("level must be 1..4, got %r" % (level,))
+    N, _, H, W = disp.shape
+    out = torch.empty((N, 2, 8 * int(level), H, W), dtype=torch.float32, device=disp.device)
+    with torch.cuda.device(disp.device):
+        _lib.call("tcs_disp_grad_candidates", disp.data_ptr(), out.data_ptr(), N, H, W, int(level), _stream())
+    return out
+
+
+def propagate_disparity(disparity_grad, disparity_map):
+    """ref: update.py:259-289 (DispRefine.propagate_disparity).  grad [N,2,H,W], disp [N,1,H,W] ->
+    (propagated [N,9,H,W], matrix [N,18,H,W]), one kernel."""
+    disparity_map = _disp_map("disparity_map", disparity_map)
+    N, _, H, W = disparity_map.shape
+    disparity_grad = _f32c("disparity_grad", disparity_grad, (N, 2, H, W))
+    prop = torch.empty((N, 9, H, W), dtype=torch.float32, device=disparity_map.device)
+    matrix = torch.empty((N, 18, H, W), dtype=torch.float32, device=disparity_map.device)
+    with torch.cuda.device(disparity_map.device):
+        _lib.call("tcs_disp_propagate", disparity_grad.data_ptr(), disparity_map.data_ptr(), prop.data_ptr(), matrix.data_ptr(),
+                  N, H, W, _stream())
+    return prop, matrix

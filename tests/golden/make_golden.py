@@ -131,10 +131,33 @@ def warp_case(rutils, rgeo, name, B, C, H, W, seed):
     print(name, "splat mask density %.3f" % wmask.mean().item(), "grid -1 fraction %.3f" % (grid == -1).float().mean().item())
 
 
+def stencil_case(rgeo, name, N, H, W, seed):
+    """The per-iteration 3x3 stencils: geo_utils.py:73-101, :115-132, update.py:259-289."""
+    import core.update as rupdate
+
+    class Args:
+        n_downsample = 2
+
+    g = torch.Generator().manual_seed(seed)
+    disp = torch.rand(N, 1, H, W, generator=g) * 24
+    disp[0, 0, 2:5, 3:9] = 0.0                                      # flow_q is clipped at 0: exact zeros are common
+    disp[-1, 0, :, W // 2:] += 11.0                                 # a depth edge: gradients beyond the |g| < 5 mask
+    grad = torch.randn(N, 2, H, W, generator=g)
+    grads, edge = rgeo.disp2disp_gradient_xy(disp)
+    cands1 = rgeo.disp2disp_grad_candidates(disp, level=1)
+    cands2 = rgeo.disp2disp_grad_candidates(disp, level=2)         # the level the model uses (update.py:202)
+    prop, matrix = rupdate.DispRefine(Args()).propagate_disparity(grad, disp)
+    out = {"disp": disp.numpy(), "grad": grad.numpy(), "grads": grads.numpy(), "edge_mask": edge.numpy(),
+           "cands1": cands1.numpy(), "cands2": cands2.numpy(), "prop": prop.numpy(), "matrix": matrix.numpy()}
+    np.savez(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items()}, "edge mask density %.3f" % edge.float().mean().item())
+
+
 def main():
     torch.manual_seed(1234)
     rcorr, rutils, rgeo = import_reference()
     with torch.no_grad():
+        stencil_case(rgeo, "stencils_small", N=2, H=11, W=19, seed=77)
         corr_case(rcorr, "corr_small", B=2, C=128, H=3, W=40, seed=1234, correlated_shift=5)
         corr_case(rcorr, "corr_oddwidth", B=1, C=128, H=2, W=78, seed=4321, correlated_shift=0)
         warp_case(rutils, rgeo, "warp_small", B=2, C=128, H=12, W=16, seed=1234)

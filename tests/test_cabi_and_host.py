@@ -135,6 +135,31 @@ def test_dropin_patches_motion_encoder():
     assert BasicMotionEncoder.forward is original
 
 
+def test_dropin_patches_the_iteration_stencils():
+    import tcs_b200
+    tcs_mod = types.ModuleType("core.tc_stereo")
+    for n in ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler"):
+        setattr(tcs_mod, n, object())
+    orig_grad = tcs_mod.disp2disp_gradient_xy = lambda disp: "gradient"
+    upd = types.ModuleType("core.update")
+    orig_cands = upd.disp2disp_grad_candidates = lambda disp, level=1: "candidates"
+
+    class DispRefine(torch.nn.Module):
+        def propagate_disparity(self, disparity_grad, disparity_map):
+            return "propagate"
+    upd.DispRefine = DispRefine
+    orig_prop = DispRefine.propagate_disparity
+    tcs_b200.install(tcs_mod, stencils=upd)
+    assert tcs_mod.disp2disp_gradient_xy is tcs_b200.disp2disp_gradient_xy
+    assert upd.disp2disp_grad_candidates is tcs_b200.disp2disp_grad_candidates
+    assert DispRefine.propagate_disparity is not orig_prop
+    with pytest.raises(TypeError):                       # no CPU path: a CPU tensor is refused, not silently computed
+        DispRefine().propagate_disparity(torch.zeros(1, 2, 4, 4), torch.zeros(1, 1, 4, 4))
+    tcs_b200.uninstall(tcs_mod, upd)
+    assert tcs_mod.disp2disp_gradient_xy is orig_grad and upd.disp2disp_grad_candidates is orig_cands
+    assert DispRefine.propagate_disparity is orig_prop
+
+
 GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, %r)

@@ -571,3 +571,56 @@ def test_bad_shapes_raise(tcs):
     with pytest.raises(RuntimeError):                # warp needs C in {128,...,512}
         tcs.warp(torch.ones(1, 1, 2, 16).cuda(), f, torch.eye(4)[None].cuda(), torch.eye(3)[None].cuda(),
                  torch.eye(3)[None].cuda(), torch.ones(1, 1).cuda())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# "next" row: the per-GRU-iteration 3x3 stencils, one kernel each
+# ---------------------------------------------------------------------------------------------------------
+
+def test_stencils_golden_bit_exact(tcs):
+    """Against the reference's own outputs (tests/golden/stencils_small.npz): exact, including the boolean mask."""
+    g = load_golden("stencils_small")
+    disp, grad = cuda(g["disp"]), cuda(g["grad"])
+    grads, edge = tcs.disp2disp_gradient_xy(disp)
+    assert edge.dtype == torch.bool and grads.shape == g["grads"].shape
+    assert_exact(host(grads), g["grads"], what="disp2disp_gradient_xy")
+    assert np.array_equal(host(edge), g["edge_mask"])
+    assert_exact(host(tcs.disp2disp_grad_candidates(disp, level=1)), g["cands1"], what="grad candidates level 1")
+    assert_exact(host(tcs.disp2disp_grad_candidates(disp, level=2)), g["cands2"], what="grad candidates level 2")
+    prop, matrix = tcs.propagate_disparity(grad, disp)
+    assert_exact(host(prop), g["prop"], what="propagate_disparity")
+    assert_exact(host(matrix), g["matrix"], what="propagate_disparity matrix")
+
+
+@pytest.mark.parametrize("N,H,W", [(8, 136, 240), (1, 1, 7), (3, 5, 1), (2, 96, 312)])
+def test_stencils_full_size(tcs, N, H, W):
+    gen = torch.Generator().manual_seed(N * 1000 + W)
+    disp = torch.rand(N, 1, H, W, generator=gen) * (W / 8 + 1)
+    disp.view(-1)[::7] = 0.0
+    grad = torch.randn(N, 2, H, W, generator=gen)
+    grads, edge = tcs.disp2disp_gradient_xy(disp.cuda())
+    rg, re = orc.disp_gradient_xy(disp.numpy())
+    assert_exact(host(grads), rg, what="gradient_xy %dx%dx%d" % (N, H, W))
+    assert np.array_equal(host(edge), re)
+    for level in (1, 2):
+        assert_exact(host(tcs.disp2disp_grad_candidates(disp.cuda(), level=level)), orc.disp_grad_candidates(disp.numpy(), level),
+                     what="grad candidates level %d" % level)
+    for level in (3, 4):       # factors of 3: a product is no longer exact, the reference's own rounding is an ulp away
+        assert_close(host(tcs.disp2disp_grad_candidates(disp.cuda(), level=level)), orc.disp_grad_candidates(disp.numpy(), level),
+                     rtol=1e-5, atol=1e-5, what="grad candidates level %d" % level)
+    prop, matrix = tcs.propagate_disparity(grad.cuda(), disp.cuda())
+    rp, rm = orc.disp_propagate(grad.numpy(), disp.numpy())
+    assert_exact(host(prop), rp, what="propagate")
+    assert_exact(host(matrix), rm, what="propagate matrix")
+
+
+def test_stencils_reject_bad_arguments(tcs):
+    d = torch.zeros(1, 1, 4, 4, device="cuda")
+    with pytest.raises(ValueError):
+        tcs.disp2disp_grad_candidates(d, level=5)
+    with pytest.raises(ValueError):
+        tcs.disp2disp_gradient_xy(torch.zeros(1, 2, 4, 4, device="cuda"))
+    with pytest.raises(ValueError):
+        tcs.propagate_disparity(torch.zeros(1, 3, 4, 4, device="cuda"), d)
+    with pytest.raises(TypeError):
+        tcs.disp2disp_gradient_xy(torch.zeros(1, 1, 4, 4))

@@ -111,3 +111,17 @@ def test_torch_port_matches_golden():
     outs = tp.warp_hidden([t(g["net%d" % i]) for i in range(3)], t(g["backward_grid"]))
     for i in range(3):
         assert_close(outs[i].numpy(), g["warped_net%d" % i], rtol=1e-5, atol=2e-6, what="port hidden %d" % i)
+
+
+def test_stencil_oracles_match_reference_bit_for_bit():
+    """geo_utils.py:73-101, :115-132 and update.py:259-289 restated in numpy: every product has an exact small-integer
+    factor, so the restatement reproduces the reference's outputs exactly (level 2 is what the model uses)."""
+    g = load_golden("stencils_small")
+    grads, edge = orc.disp_gradient_xy(g["disp"])
+    assert_exact(grads, g["grads"], what="disp2disp_gradient_xy")
+    assert np.array_equal(edge, g["edge_mask"]) and 0 < g["edge_mask"].mean() < 1
+    assert_exact(orc.disp_grad_candidates(g["disp"], 1), g["cands1"], what="disp2disp_grad_candidates level 1")
+    assert_exact(orc.disp_grad_candidates(g["disp"], 2), g["cands2"], what="disp2disp_grad_candidates level 2")
+    prop, matrix = orc.disp_propagate(g["grad"], g["disp"])
+    assert_exact(prop, g["prop"], what="propagate_disparity")
+    assert_exact(matrix, g["matrix"], what="propagate_disparity matrix")

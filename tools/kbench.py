@@ -119,3 +119,46 @@ for i in range(3):
     net = torch.tanh(torch.randn(B, 128, H >> i, W >> i, generator=g)).to(dev)
     timeit("sample[l%d]" % i, lambda: tcs_b200.sample_planar(net, grid), net.numel() * 8 + grid.numel() * 4)
     grid = tcs_b200.halve_grid(grid)
+
+# ---- "next" row, rank 2: the per-iteration stencils; beside them the reference's own op sequence (grouped conv2d on
+# padded copies) written out with torch ops on the GPU
+import torch.nn.functional as F  # noqa: E402
+
+ggrad = torch.randn(B, 2, H, W, generator=g).to(dev)
+
+
+def ref_gradient_xy(disp):                                           # geo_utils.py:115-132
+    pad = F.pad(disp, (1, 1, 1, 1), mode="replicate")
+    k = torch.zeros(2, 1, 3, 3, device=disp.device)
+    k[:, :, 1, 1] = -1
+    k[0, :, 1, 2] = 1
+    k[1, :, 2, 1] = 1
+    gr = F.conv2d(pad.repeat(1, 2, 1, 1), k, groups=2)
+    return gr, (gr[:, :1].abs() < 5) & (gr[:, 1:].abs() < 5)
+
+
+def ref_grad_candidates(disp, level=2):                              # geo_utils.py:73-101
+    N = disp.shape[0]
+    k = torch.zeros(8, 1, 3, 3, device=disp.device)
+    k[:, :, 1, 1] = -1
+    for i, (v, u) in enumerate([(0, 0), (0, 1), (0, 2), (1, 2), (2, 2), (2, 1), (2, 0), (1, 0)]):
+        k[i, :, v, u] = 1
+    cands = []
+    for i in range(level):
+        p = 1 + i
+        dp = F.pad(disp, (p, p, p, p))
+        Hp, Wp = H + 2 * p, W + 2 * p
+        ys, xs = torch.meshgrid(torch.arange(Hp, device=disp.device), torch.arange(Wp, device=disp.device), indexing="ij")
+        coord = torch.stack([xs, ys], 0).float()[None].repeat(N, 1, 1, 1)
+        cd = torch.cat((coord, dp), 1).reshape(-1, 1, Hp, Wp).repeat(1, 8, 1, 1)
+        cands.append(F.conv2d(cd, k, groups=8, dilation=p).reshape(N, 3, 8, H, W))
+    gr = torch.cat(cands, 2)
+    c = torch.cross(gr, torch.roll(gr, -2, 2), dim=1)
+    return -c[:, :2] / c[:, 2:]
+
+
+timeit("gradient_xy", lambda: tcs_b200.disp2disp_gradient_xy(dd), npix * 13)
+timeit("gradient_xy[torch ops]", lambda: ref_gradient_xy(dd), npix * 13)
+timeit("grad_candidates[l2]", lambda: tcs_b200.disp2disp_grad_candidates(dd, 2), npix * 132)
+timeit("grad_candidates[l2, torch ops]", lambda: ref_grad_candidates(dd, 2), npix * 132)
+timeit("propagate", lambda: tcs_b200.propagate_disparity(ggrad, dd), npix * 120)
