@@ -202,6 +202,12 @@ int tcs_disp_grad_candidates(const float* disp, float* out, int N, int H, int W,
  * channel = component * 9 + neighbour). */
 int tcs_disp_propagate(const float* grad, const float* disp, float* prop, float* matrix, int N, int H, int W, void* stream);
 
+/* ref: core/tc_stereo.py:75-88 (TCStereo.upsample_flow).  flow [N,D,H,W], mask
+ * [N,9*factor^2,H,W] -> out [N,D,factor*H,factor*W]: softmax over the 9 logits of each sub-pixel, convex combination of
+ * the 3x3 zero-padded neighbours of (factor *) flow.  factor 2, 4 or 8; scale != 0 multiplies flow by factor. */
+int tcs_convex_upsample(const float* flow, const float* mask, float* out, int N, int D, int H, int W,
+                        int factor, int scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -403,3 +403,21 @@ def disp_propagate(disparity_grad, disparity_map):
         matrix[:, k] = np.abs(g[:, 0] - gx)
         matrix[:, 9 + k] = np.abs(g[:, 1] - gy)
     return prop, matrix
+
+
+def convex_upsample(flow, mask, factor=4, scale=True):
+    """ref: core/tc_stereo.py:75-88 (TCStereo.upsample_flow).  flow [N,D,H,W], mask
+    [N,9*factor^2,H,W] -> [N,D,factor*H,factor*W]."""
+    fl = _f(flow)
+    N, D, H, W = fl.shape
+    m = _f(mask).reshape(N, 1, 9, factor, factor, H, W)
+    m = m - m.max(axis=2, keepdims=True)
+    e = np.exp(m).astype(F32)
+    w = (e / e.sum(axis=2, keepdims=True, dtype=F32)).astype(F32)                     # softmax over the 9 neighbours
+    src = (F32(factor) * fl if scale else fl).astype(F32)
+    pad = np.pad(src, ((0, 0), (0, 0), (1, 1), (1, 1)))                               # F.unfold(.., [3,3], padding=1)
+    up = np.stack([pad[:, :, v:v + H, u:u + W] for v in range(3) for u in range(3)], axis=2)   # [N,D,9,H,W]
+    out = np.zeros((N, D, factor, factor, H, W), F32)
+    for k in range(9):
+        out = (out + w[:, :, k] * up[:, :, k][:, :, None, None]).astype(F32)
+    return out.transpose(0, 1, 4, 2, 5, 3).reshape(N, D, factor * H, factor * W)     # permute(0,1,4,2,5,3)

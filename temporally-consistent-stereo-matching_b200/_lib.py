@@ -43,6 +43,7 @@ SIGNATURES = {
     "tcs_disp_gradient_xy": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "tcs_disp_grad_candidates": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tcs_disp_propagate": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "tcs_convex_upsample": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
 }
 
 _lib = None

@@ -4,6 +4,7 @@
 //   tcs_disp_gradient_xy      ref: core/utils/geo_utils.py:115-132 (disp2disp_gradient_xy)
 //   tcs_disp_grad_candidates  ref: core/utils/geo_utils.py:73-101  (disp2disp_grad_candidates)
 //   tcs_disp_propagate        ref: core/update.py:259-289          (DispRefine.propagate_disparity)
+//   tcs_convex_upsample       ref: core/tc_stereo.py:75-88         (TCStereo.upsample_flow; rank 3)
 // All arithmetic that the reference does on small integers (coordinate differences 0, +-1, +-2 ...) is exact in fp32,
 // every product below has such a factor, and the remaining additions / divisions are single IEEE operations in the
 // reference's order: the results are bit-identical to the reference's, not merely close.
@@ -107,7 +108,84 @@ disp_propagate_kernel(const float* __restrict__ grad, const float* __restrict__ 
     }
 }
 
+// ---- TCStereo.upsample_flow: convex combination of the 3x3 coarse neighbours ------------
+// One thread per (coarse pixel, sub-row): lanes are consecutive x, blockIdx.y is the sub-row, so every logit load is
+// coalesced and all 9 f of them are in flight at once; max / exp / sum / divide and the weighted sum in registers; the
+// f sub-pixels of the row leave as one contiguous store per lane (f = 4: a 16-byte store, 512 bytes per warp).
+template <int kF>
+__global__ void __launch_bounds__(128)
+convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ mask, float* __restrict__ out,
+                       int D, int H, int W, int scale, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int si = blockIdx.y;
+    const int HW = H * W;
+    const long long n = i / HW;
+    const int p = (int)(i - n * HW);
+    const int y = p / W, x = p - y * W;
+    const float* mk = mask + n * 9 * kF * kF * (long long)HW + p;
+    float w[kF][9];
+#pragma unroll
+    for (int sj = 0; sj < kF; ++sj)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[sj][k] = ldg_stream_f1(mk + (long long)((k * kF + si) * kF + sj) * HW);
+#pragma unroll
+    for (int sj = 0; sj < kF; ++sj) {                                   // softmax(mask - max) over k   tc_stereo.py:80-81
+        float mx = w[sj][0];
+#pragma unroll
+        for (int k = 1; k < 9; ++k) mx = fmaxf(mx, w[sj][k]);
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            w[sj][k] = expf(__fsub_rn(w[sj][k], mx));
+            s = __fadd_rn(s, w[sj][k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[sj][k] = __fdiv_rn(w[sj][k], s);
+    }
+    for (int d = 0; d < D; ++d) {
+        const float* fl = flow + (n * D + d) * HW;
+        float r[kF];
+#pragma unroll
+        for (int sj = 0; sj < kF; ++sj) r[sj] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;               // F.unfold(.., [3,3], padding=1): zeros outside
+            const float v = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? fl[yy * W + xx] : 0.0f;
+            const float u = scale ? __fmul_rn((float)kF, v) : v;
+#pragma unroll
+            for (int sj = 0; sj < kF; ++sj) r[sj] = __fadd_rn(r[sj], __fmul_rn(w[sj][k], u));
+        }
+        float* row = out + ((n * D + d) * (long long)(kF * H) + (long long)y * kF + si) * (kF * W) + (long long)x * kF;
+        if (kF == 4) {
+            *reinterpret_cast<float4*>(row) = make_float4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+            for (int sj = 0; sj < kF; ++sj) row[sj] = r[sj];
+        }
+    }
+}
+
 }  // namespace tcs
+
+extern "C" int tcs_convex_upsample(const float* flow, const float* mask, float* out, int N, int D, int H, int W,
+                                   int factor, int scale, void* stream) {
+    using namespace tcs;
+    TCS_REQUIRE(flow && mask && out, TCS_E_BADARG, "tcs_convex_upsample: null pointer");
+    TCS_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0 && (long long)H * W * 16 < 0x7fffffffLL, TCS_E_BADARG, "tcs_convex_upsample: bad sizes");
+    TCS_REQUIRE(factor == 2 || factor == 4 || factor == 8, TCS_E_SHAPE, "tcs_convex_upsample: factor=%d must be 2, 4 or 8", factor);
+    TCS_REQUIRE(aligned16(out), TCS_E_ALIGN, "tcs_convex_upsample: out must be 16-byte aligned");
+    const long long total = (long long)N * H * W;
+    const unsigned blocks = (unsigned)ceil_div_ll(total, 128);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (factor) {
+        case 2: convex_upsample_kernel<2><<<dim3(blocks, 2), 128, 0, s>>>(flow, mask, out, D, H, W, scale, total); break;
+        case 4: convex_upsample_kernel<4><<<dim3(blocks, 4), 128, 0, s>>>(flow, mask, out, D, H, W, scale, total); break;
+        default: convex_upsample_kernel<8><<<dim3(blocks, 8), 128, 0, s>>>(flow, mask, out, D, H, W, scale, total); break;
+    }
+    TCS_CHECK_LAUNCH("tcs_convex_upsample");
+    return 0;
+}
 
 extern "C" int tcs_disp_gradient_xy(const float* disp, float* grads, unsigned char* edge_mask, int N, int H, int W, void* stream) {
     using namespace tcs;

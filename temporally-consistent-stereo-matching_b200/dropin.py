@@ -13,7 +13,8 @@ def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=Non
 
     stencils: the imported `core.update`.  When given, the three per-iteration 3x3 stencils also run as single kernels
     (SURVEY.md section 8f rank 2): `disp2disp_gradient_xy` (tc_stereo.py:192), `disp2disp_grad_candidates`
-    (update.py:202) and `DispRefine.propagate_disparity` (update.py:294); fp32, inference only.
+    (update.py:202) and `DispRefine.propagate_disparity` (update.py:294), and so does the convex upsampling
+    `TCStereo.upsample_flow` (tc_stereo.py:75-88, rank 3); fp32, inference only.
 
     fuse_motion_encoder: the imported `core.update`.  When given, corr_fn(coords) returns a deferred lookup and
     BasicMotionEncoder.forward (update.py:103-112) evaluates `relu(convc1(corr))` with the fused lookup + 1x1
@@ -84,6 +85,14 @@ def _patch_stencils(tc_stereo_module, update_module):
         return geo.propagate_disparity(disparity_grad, disparity_map)
 
     ref.propagate_disparity = propagate_disparity
+    model = getattr(tc_stereo_module, "TCStereo", None)              # rank 3: the convex upsampling of the last iteration
+    if model is not None:
+        _saved.setdefault((id(tc_stereo_module), "TCStereo.upsample_flow"), model.upsample_flow)
+
+        def upsample_flow(self, flow, mask, scale=True):                # tc_stereo.py:75-88
+            return geo.convex_upsample(flow, mask, 2 ** self.args.n_downsample, scale)
+
+        model.upsample_flow = upsample_flow
 
 
 def uninstall(tc_stereo_module, update_module=None):
@@ -100,6 +109,9 @@ def uninstall(tc_stereo_module, update_module=None):
     old = _saved.pop((id(tc_stereo_module), "disp2disp_gradient_xy"), None)
     if old is not None:
         tc_stereo_module.disp2disp_gradient_xy = old
+    old = _saved.pop((id(tc_stereo_module), "TCStereo.upsample_flow"), None)
+    if old is not None:
+        tc_stereo_module.TCStereo.upsample_flow = old
     for name in _NAMES:
         old = _saved.pop((id(tc_stereo_module), name), None)
         if old is not None:

@@ -256,3 +256,21 @@ def propagate_disparity(disparity_grad, disparity_map):
         _lib.call("tcs_disp_propagate", disparity_grad.data_ptr(), disparity_map.data_ptr(), prop.data_ptr(), matrix.data_ptr(),
                   N, H, W, _stream())
     return prop, matrix
+
+
+def convex_upsample(flow, mask, factor=4, scale=True):
+    """ref: tc_stereo.py:75-88 (TCStereo.upsample_flow).  flow [N,D,H,W], mask
+    [N,9*factor^2,H,W] -> [N,D,factor*H,factor*W]: softmax + unfold + weighted sum + re-layout in one kernel."""
+    flow = _f32c("flow", flow)
+    if flow.dim() != 4:
+        raise ValueError("flow must be [N,D,H,W], got %s" % (tuple(flow.shape),))
+    N, D, H, W = flow.shape
+    factor = int(factor)
+    if factor not in (2, 4, 8):
+        raise ValueError("factor must be 2, 4 or 8, got %r" % (factor,))
+    mask = _f32c("mask", mask, (N, 9 * factor * factor, H, W))
+    out = torch.empty((N, D, factor * H, factor * W), dtype=torch.float32, device=flow.device)
+    with torch.cuda.device(flow.device):
+        _lib.call("tcs_convex_upsample", flow.data_ptr(), mask.data_ptr(), out.data_ptr(), N, D, H, W, factor,
+                  1 if scale else 0, _stream())
+    return out

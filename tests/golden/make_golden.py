@@ -147,8 +147,13 @@ def stencil_case(rgeo, name, N, H, W, seed):
     cands1 = rgeo.disp2disp_grad_candidates(disp, level=1)
     cands2 = rgeo.disp2disp_grad_candidates(disp, level=2)         # the level the model uses (update.py:202)
     prop, matrix = rupdate.DispRefine(Args()).propagate_disparity(grad, disp)
+    # convex upsampling (tc_stereo.py:75-88) reads only self.args: call it unbound on a stand-in
+    import core.tc_stereo as rtc
+    up_mask = torch.randn(N, 9 * 16, H, W, generator=g) * 3
+    up = rtc.TCStereo.upsample_flow(types.SimpleNamespace(args=Args()), -disp, up_mask)
     out = {"disp": disp.numpy(), "grad": grad.numpy(), "grads": grads.numpy(), "edge_mask": edge.numpy(),
-           "cands1": cands1.numpy(), "cands2": cands2.numpy(), "prop": prop.numpy(), "matrix": matrix.numpy()}
+           "cands1": cands1.numpy(), "cands2": cands2.numpy(), "prop": prop.numpy(), "matrix": matrix.numpy(),
+           "up_mask": up_mask.numpy(), "up": up.numpy()}
     np.savez(os.path.join(HERE, name + ".npz"), **out)
     print(name, {k: v.shape for k, v in out.items()}, "edge mask density %.3f" % edge.float().mean().item())
 

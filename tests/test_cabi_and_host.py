@@ -149,7 +149,14 @@ def test_dropin_patches_the_iteration_stencils():
             return "propagate"
     upd.DispRefine = DispRefine
     orig_prop = DispRefine.propagate_disparity
+
+    class TCStereo(torch.nn.Module):
+        def upsample_flow(self, flow, mask, scale=True):
+            return "upsample"
+    tcs_mod.TCStereo = TCStereo
+    orig_up = TCStereo.upsample_flow
     tcs_b200.install(tcs_mod, stencils=upd)
+    assert TCStereo.upsample_flow is not orig_up
     assert tcs_mod.disp2disp_gradient_xy is tcs_b200.disp2disp_gradient_xy
     assert upd.disp2disp_grad_candidates is tcs_b200.disp2disp_grad_candidates
     assert DispRefine.propagate_disparity is not orig_prop
@@ -157,7 +164,7 @@ def test_dropin_patches_the_iteration_stencils():
         DispRefine().propagate_disparity(torch.zeros(1, 2, 4, 4), torch.zeros(1, 1, 4, 4))
     tcs_b200.uninstall(tcs_mod, upd)
     assert tcs_mod.disp2disp_gradient_xy is orig_grad and upd.disp2disp_grad_candidates is orig_cands
-    assert DispRefine.propagate_disparity is orig_prop
+    assert DispRefine.propagate_disparity is orig_prop and TCStereo.upsample_flow is orig_up
 
 
 GLOO_WORKER = r"""

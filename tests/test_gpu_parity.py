@@ -624,3 +624,20 @@ def test_stencils_reject_bad_arguments(tcs):
         tcs.propagate_disparity(torch.zeros(1, 3, 4, 4, device="cuda"), d)
     with pytest.raises(TypeError):
         tcs.disp2disp_gradient_xy(torch.zeros(1, 1, 4, 4))
+
+
+def test_convex_upsample_golden_and_full_size(tcs):
+    """TCStereo.upsample_flow (tc_stereo.py:75-88): against the reference's output, then against the oracle at 540p."""
+    g = load_golden("stencils_small")
+    up = tcs.convex_upsample(cuda(-g["disp"]), cuda(g["up_mask"]), 4, True)
+    assert up.shape == g["up"].shape
+    assert_close(host(up), g["up"], rtol=1e-5, atol=1e-5, what="upsample_flow vs reference")
+    gen = torch.Generator().manual_seed(12)
+    for (N, D, H, W, f, scale) in [(2, 1, 136, 240, 4, True), (1, 2, 9, 13, 8, False), (1, 1, 5, 6, 2, True)]:
+        flow = torch.randn(N, D, H, W, generator=gen) * 20
+        mask = torch.randn(N, 9 * f * f, H, W, generator=gen) * 4
+        out = tcs.convex_upsample(flow.cuda(), mask.cuda(), f, scale)
+        ref = orc.convex_upsample(flow.numpy(), mask.numpy(), f, scale)
+        assert_close(host(out), ref, rtol=1e-5, atol=2e-5, what="upsample %dx%dx%dx%d f=%d" % (N, D, H, W, f))
+    with pytest.raises(ValueError):
+        tcs.convex_upsample(torch.zeros(1, 1, 4, 4, device="cuda"), torch.zeros(1, 9 * 9, 4, 4, device="cuda"), 3)

@@ -125,3 +125,5 @@ def test_stencil_oracles_match_reference_bit_for_bit():
     prop, matrix = orc.disp_propagate(g["grad"], g["disp"])
     assert_exact(prop, g["prop"], what="propagate_disparity")
     assert_exact(matrix, g["matrix"], what="propagate_disparity matrix")
+    up = orc.convex_upsample(-g["disp"], g["up_mask"], 4, True)                  # tc_stereo.py:75-88 (exp: not bit-exact)
+    assert_close(up, g["up"], rtol=1e-5, atol=1e-5, what="upsample_flow")

@@ -162,3 +162,17 @@ timeit("gradient_xy[torch ops]", lambda: ref_gradient_xy(dd), npix * 13)
 timeit("grad_candidates[l2]", lambda: tcs_b200.disp2disp_grad_candidates(dd, 2), npix * 132)
 timeit("grad_candidates[l2, torch ops]", lambda: ref_grad_candidates(dd, 2), npix * 132)
 timeit("propagate", lambda: tcs_b200.propagate_disparity(ggrad, dd), npix * 120)
+
+
+def ref_upsample(flow, mask, factor=4):                              # tc_stereo.py:75-88
+    N, D, Hh, Ww = flow.shape
+    m = mask.view(N, 1, 9, factor, factor, Hh, Ww)
+    m = torch.softmax(m - torch.max(m, dim=2, keepdim=True)[0], dim=2)
+    up = F.unfold(factor * flow, [3, 3], padding=1).view(N, D, 9, 1, 1, Hh, Ww)
+    up = torch.sum(m * up, dim=2).permute(0, 1, 4, 2, 5, 3)
+    return up.reshape(N, D, factor * Hh, factor * Ww)
+
+
+umask = torch.randn(B, 144, H, W, generator=g).to(dev)
+timeit("convex_upsample", lambda: tcs_b200.convex_upsample(dd, umask, 4, True), npix * (4 + 144 * 4 + 64))
+timeit("convex_upsample[torch ops]", lambda: ref_upsample(dd, umask, 4), npix * (4 + 144 * 4 + 64))
