@@ -98,7 +98,9 @@ def hot_path_frame(fmap1, fmap2, coords_seq, state=None, disp_init=None, rel_T=N
         last_disp, last_fmap1, last_net_list = state
         sparse_disp, _, mask, cost = geo.warp_with_cost(last_disp, last_fmap1, rel_T, K, K_inv, baseline,
                                                         cur_fmap=fmap1, per_sample_mean=per_sample_mean, want_fmap=False,
-                                                        carry_in=carry_in, carry_out=carry_out)
+                                                        carry_in=carry_in, carry_out=carry_out,
+                                                        deterministic=carry_out is not None)   # a carrying run is
+        # the list formulation from its first warp on (which has to transpose for itself): bitwise repeatable throughout
         if last_net_list is not None:
             grid = geo.get_backward_grid(disp_init if disp_init is not None else sparse_disp,   # the kernel clips at 0.01
                                          rel_T_inv, K, K_inv, baseline)

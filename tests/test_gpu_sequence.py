@@ -59,3 +59,40 @@ def test_fifty_frame_sequence_480x640():
                 for a, r in zip(out["warped_net"], orc.warp_hidden_states(st[2], grid)):
                     assert_close(a.cpu().numpy(), r, rtol=1e-4, atol=1e-4, what="frame %d hidden state" % t)
         prev_T = T
+
+
+def test_runner_is_bitwise_repeatable():
+    """A HotPathRunner warps through sorted contributor lists from its first temporal frame on (the carried
+    transposition from the third): two runs over the same frames give identical bits, which the reference's atomic
+    scatter does not."""
+    import tcs_b200
+    from tcs_b200 import sequence
+    dev = torch.device("cuda")
+    B, C, H, W, iters, frames = 2, 128, 40, 96, 2, 5
+    K, K_inv = sequence.synthetic_intrinsics(B, 4 * H, 4 * W, dev)
+    baseline = torch.full((B, 1), 0.25, device=dev)
+    xs = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+
+    def run():
+        g = torch.Generator().manual_seed(99)
+        runner = tcs_b200.HotPathRunner()
+        outs, prev_T = [], None
+        for t in range(frames):
+            f1 = torch.randn(B, C, H, W, generator=g).to(dev)
+            f2 = torch.randn(B, C, H, W, generator=g).to(dev)
+            coords = (xs - 8.0 * torch.rand(iters, B, 1, H, W, generator=g)).to(dev)      # i.i.d. disparities: long, irregular lists
+            nets = [torch.randn(B, 8, H >> i, W >> i, generator=g).to(dev) for i in range(3)]
+            T = torch.stack([sequence.synthetic_pose(t, s) for s in range(B)])
+            kw = {}
+            if prev_T is not None:
+                fwd, inv = sequence.relative_pose(prev_T, T)
+                kw = dict(rel_T=fwd.to(dev), rel_T_inv=inv.to(dev), K=K, K_inv=K_inv, baseline=baseline)
+            out = runner.frame(f1, f2, coords, net_list=nets, **kw)
+            outs.append([out[k].clone() for k in ("corr", "sparse_disp", "cost", "mask")] + [n.clone() for n in (out["warped_net"] or [])])
+            prev_T = T
+        return outs
+
+    a, b = run(), run()
+    for fa, fb in zip(a, b):
+        for x, y in zip(fa, fb):
+            assert torch.equal(x, y)
