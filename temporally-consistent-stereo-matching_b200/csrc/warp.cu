@@ -15,6 +15,12 @@
 // (position 128*j + 4*lane + i  <->  channel lane + 32*(4*j + i)) chosen so that both the splat's
 // shared-memory reads and the normalise kernel's shared-memory writes are bank-conflict free.
 //
+// A second formulation (TCS_WARP_DETERMINISTIC) collects the same sums from the target's side through exact,
+// sorted per-target contributor lists and a transposed copy of the source features: no accumulator, no
+// floating-point atomics, a fixed summation order.  The transposed copy of a frame's features can be produced
+// by that frame's own cost kernel (cur_t_out) and consumed by the next frame's call (fmap_t), which is how a
+// sequence runs (see the "list formulation" section below).
+//
 // Geometry is evaluated with explicit round-to-nearest intrinsics (no compiler-chosen contraction) in a
 // fixed order so that the validity masks and the integer splat targets are reproducible bit for bit by the
 // CPU oracle.
@@ -307,8 +313,9 @@ __device__ __forceinline__ void cost_pixel(const float4 (&a)[kGroups], float2 ta
             sw = fmaf(v, v, sw);
         }
         // the current features are next frame's source: hand them on already transposed (pixel-major, permuted)
-        if (cur_t_out != nullptr && live)
-            *reinterpret_cast<float4*>(cur_t_out + tpix * C + j * 128 + 4 * lane) = make_float4(fq[0], fq[1], fq[2], fq[3]);
+        if (cur_t_out != nullptr && live)     // not read again before the next frame: cache-streaming store
+            asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(cur_t_out + tpix * C + j * 128 + 4 * lane),
+                         "f"(fq[0]), "f"(fq[1]), "f"(fq[2]), "f"(fq[3]) : "memory");
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
