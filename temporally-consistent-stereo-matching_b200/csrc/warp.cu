@@ -239,7 +239,7 @@ __device__ __forceinline__ void gather_target(const ListArgs& la, size_t sample_
             const float* row = la.src_t + (sample_px0 + en[u].x) * C + 4 * lane;
 #pragma unroll
             for (int j = 0; j < kGroups; ++j)
-                v[u][j] = live ? ldg_stream_f4(reinterpret_cast<const float4*>(row + j * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u][j] = live ? __ldg(reinterpret_cast<const float4*>(row + j * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
             d1[u] = live ? __ldg(la.disp1 + sample_px0 + en[u].x) : 0.0f;
         }
 #pragma unroll
