@@ -43,6 +43,14 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert n >= 2 * 136 * 240 * 260 * 4 and n % 256 == 0
     with pytest.raises(tcs_b200._lib.TcsError):
         tcs_b200._lib.call("tcs_grid_halve", None, None, 1, 4, 4, None)
+    # tcs_warp_forward: the carried transposition is produced by the cost-only call and consumed by the list formulation
+    P = ctypes.c_void_p(4096)                          # never dereferenced: the checks come first
+    warp_args = lambda out_fmap, fmap_t, cur_t, flags: (P, P, P, P, P, P, P, P, out_fmap, P, P, fmap_t, cur_t, P, 1, 128, 4, 4, flags, None)
+    assert lib.tcs_warp_forward(*warp_args(P, None, P, 0)) == -1 and b"cur_t_out" in lib.tcs_last_error()
+    assert lib.tcs_warp_forward(*warp_args(None, P, None, 0)) == -1 and b"fmap_t" in lib.tcs_last_error()
+    assert lib.tcs_warp_forward(*warp_args(None, ctypes.c_void_p(4100), None, 2)) == -3        # TCS_E_ALIGN
+    assert lib.tcs_disp_grad_candidates(P, P, 1, 4, 4, 5, None) == -2 and b"level" in lib.tcs_last_error()
+    assert lib.tcs_convex_upsample(P, P, P, 1, 1, 4, 4, 3, 1, None) == -2 and b"factor" in lib.tcs_last_error()
 
 
 def test_no_cpu_fallback():
