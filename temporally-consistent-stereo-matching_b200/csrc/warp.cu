@@ -698,7 +698,7 @@ backward_grid_kernel(const float* __restrict__ disp, const float* __restrict__ r
 // ATen's un-normalise round trip.  One thread per (output pixel, group of 8 channels): the four weights are
 // computed once, then the 32 corner loads of the group are issued back to back (memory-level parallelism),
 // lanes being consecutive output pixels so that loads and stores of one channel plane coalesce.
-constexpr int kSampleCh = 8;
+constexpr int kSampleCh = 16;
 
 template <bool kFull>   // kFull: C is a multiple of kSampleCh, no per-channel guards (keeps the loads batched)
 __global__ void __launch_bounds__(256)
