@@ -220,42 +220,49 @@ struct ListArgs {
 // Sum of the contributions to one target (the whole warp works on it; n is warp-uniform).  tail = (sum w * disp', sum w).
 // (Staging the block's offsets and entries in shared memory first was measured: 482 us instead of 355 -- the extra
 // barrier behind the current-feature loads and 20 more registers cost more than the index round trips.)
+// One round: kE consecutive entries of the list, all their rows in flight before the first is used.
+template <int kGroups, int kE>
+__device__ __forceinline__ void gather_round(const ListArgs& la, size_t sample_px0, int s0, int n, int j0, int lane,
+                                             float4 (&a)[kGroups], float& norm, float& dsum) {
+    constexpr int C = kGroups * 128;
+    int2 en[kE];
+    float4 v[kE][kGroups];
+    float d1[kE];
+#pragma unroll
+    for (int u = 0; u < kE; ++u) {
+        const bool live = j0 + u < n;
+        en[u] = live ? __ldg(la.entries + s0 + j0 + u) : make_int2(0, 0);   // weight 0: contributes nothing
+        const float* row = la.src_t + (sample_px0 + en[u].x) * C + 4 * lane;
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j)
+            v[u][j] = live ? __ldg(reinterpret_cast<const float4*>(row + j * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d1[u] = live ? __ldg(la.disp1 + sample_px0 + en[u].x) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kE; ++u) {
+        const float w = __int_as_float(en[u].y);
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j) {
+            a[j].x = fmaf(v[u][j].x, w, a[j].x);
+            a[j].y = fmaf(v[u][j].y, w, a[j].y);
+            a[j].z = fmaf(v[u][j].z, w, a[j].z);
+            a[j].w = fmaf(v[u][j].w, w, a[j].w);
+        }
+        norm = __fadd_rn(norm, w);
+        dsum = fmaf(d1[u], w, dsum);
+    }
+}
+
 template <int kGroups>
 __device__ __forceinline__ void gather_target(const ListArgs& la, size_t sample_px0, int s0, int n, int lane,
                                               float4 (&a)[kGroups], float2& tail) {
-    constexpr int C = kGroups * 128;
-    constexpr int kE = 4;                                       // entries per round: 4 * kGroups 16-byte loads in flight per lane
 #pragma unroll
     for (int j = 0; j < kGroups; ++j) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     float norm = 0.0f, dsum = 0.0f;
-    for (int j0 = 0; j0 < n; j0 += kE) {
-        int2 en[kE];
-        float4 v[kE][kGroups];
-        float d1[kE];
-#pragma unroll
-        for (int u = 0; u < kE; ++u) {
-            const bool live = j0 + u < n;
-            en[u] = live ? __ldg(la.entries + s0 + j0 + u) : make_int2(0, 0);   // weight 0: contributes nothing
-            const float* row = la.src_t + (sample_px0 + en[u].x) * C + 4 * lane;
-#pragma unroll
-            for (int j = 0; j < kGroups; ++j)
-                v[u][j] = live ? __ldg(reinterpret_cast<const float4*>(row + j * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            d1[u] = live ? __ldg(la.disp1 + sample_px0 + en[u].x) : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < kE; ++u) {
-            const float w = __int_as_float(en[u].y);
-#pragma unroll
-            for (int j = 0; j < kGroups; ++j) {
-                a[j].x = fmaf(v[u][j].x, w, a[j].x);
-                a[j].y = fmaf(v[u][j].y, w, a[j].y);
-                a[j].z = fmaf(v[u][j].z, w, a[j].z);
-                a[j].w = fmaf(v[u][j].w, w, a[j].w);
-            }
-            norm = __fadd_rn(norm, w);
-            dsum = fmaf(d1[u], w, dsum);
-        }
-    }
+    // a list holds 4 entries on average: one round of four (4 * kGroups 16-byte loads in flight per lane), then
+    // rounds of two so that a fifth or sixth entry does not pay for four predicated slots
+    if (n > 0) gather_round<kGroups, 4>(la, sample_px0, s0, n, 0, lane, a, norm, dsum);
+    for (int j0 = 4; j0 < n; j0 += 2) gather_round<kGroups, 2>(la, sample_px0, s0, n, j0, lane, a, norm, dsum);
     tail = make_float2(dsum, norm);
 }
 
