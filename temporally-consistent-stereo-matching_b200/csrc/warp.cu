@@ -670,7 +670,25 @@ warp_sort_kernel(const int* __restrict__ start, int2* __restrict__ entries, long
     if (t >= npix) return;
     const int s0 = start[t], n = start[t + 1] - s0;
     int2* e = entries + s0;
-    for (int i = 1; i < n; ++i) {                               // insertion sort: lists are a handful of entries
+    if (n <= 1) return;
+    if (n <= 8) {                                               // the usual case: in registers, 19-comparator network
+        int2 r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = (i < n) ? e[i] : make_int2(0x7fffffff, 0);   // padding sinks to the end
+        constexpr int kNet[19][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 2}, {1, 3}, {4, 6}, {5, 7}, {1, 2}, {5, 6},
+                                     {0, 4}, {1, 5}, {2, 6}, {3, 7}, {2, 4}, {3, 5}, {1, 2}, {3, 4}, {5, 6}};
+#pragma unroll
+        for (int c = 0; c < 19; ++c) {
+            int2& a = r[kNet[c][0]];
+            int2& b = r[kNet[c][1]];
+            if (a.x > b.x) { const int2 tmp = a; a = b; b = tmp; }     // source pixels of a list are distinct: no ties
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < n) e[i] = r[i];
+        return;
+    }
+    for (int i = 1; i < n; ++i) {                               // insertion sort for the rare long list
         const int2 key = e[i];
         int j = i - 1;
         while (j >= 0 && e[j].x > key.x) { e[j + 1] = e[j]; --j; }
