@@ -128,15 +128,18 @@ class ClockSampler:
             return
 
         def loop():
+            n = 0
             while not self._stop.is_set():
                 try:
                     self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
                     self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+                    if n % 8 == 0:                         # the power query is the slow one: keep the clock samples dense
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
                 except Exception as e:  # noqa: BLE001
                     self.err = str(e)
                     return
-                time.sleep(0.002)
+                n += 1
+                time.sleep(0.0005)
 
         self.t = threading.Thread(target=loop, daemon=True)
         self.t.start()
