@@ -118,6 +118,7 @@ def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, pe
         if fmap_t is not None and carry_out.rows.data_ptr() == fmap_t.data_ptr():
             raise ValueError("carry_in and carry_out must be different WarpCarry objects")
         cur_t = carry_out.rows
+        carry_out.tensor = None                               # the rows are about to be overwritten: valid again only on success
     with torch.cuda.device(dev):
         scratch = _warp_scratch(B, C, H, W, dev)
         _lib.call("tcs_warp_forward", disp.data_ptr(), fmap.data_ptr(), relative_T.data_ptr(), K.data_ptr(),
