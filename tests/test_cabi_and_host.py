@@ -175,6 +175,25 @@ def test_dropin_patches_the_iteration_stencils():
     assert DispRefine.propagate_disparity is orig_prop and TCStereo.upsample_flow is orig_up
 
 
+def test_warp_carry_is_keyed_on_the_tensor_and_its_version():
+    """The carried transposition may only be used for the very tensor it was made from, unmodified (host logic only)."""
+    import tcs_b200
+    c = tcs_b200.WarpCarry()
+    f = torch.zeros(1, 8, 2, 4)
+    assert not c.matches(f)                                  # empty
+    c.reserve(f)
+    assert tuple(c.rows.shape) == (8, 8) and not c.matches(f)   # reserved, nothing recorded yet
+    c.tensor, c.version = f, f._version
+    assert c.matches(f)
+    assert not c.matches(f.clone())                          # another tensor with the same contents
+    f.add_(1.0)                                              # modified in place: the rows are stale
+    assert not c.matches(f)
+    c.version = f._version
+    assert c.matches(f) and not c.matches(f.double()) and not c.matches(f.permute(0, 1, 3, 2))
+    c.reserve(torch.zeros(2, 8, 2, 4))                       # another shape: reallocated and invalidated
+    assert tuple(c.rows.shape) == (16, 8) and not c.matches(f)
+
+
 GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, %r)
