@@ -2,7 +2,8 @@
 """Throughput of the TC-Stereo cost-volume hot path on B200: stereo frames/s at 540x960, 32 GRU iterations.
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun by the driver)
-    python bench.py --impl reference ...                      (the CPU port of the reference's path)
+    python bench.py --impl reference ...                      (the reference's own code for the path on the host cores)
+    python [-O] bench.py --impl reference-gpu ...             (the reference's own PyTorch code for the path on the B200)
 
 A step = the hot path's share of ONE temporal frame for every sequence this GPU owns (B sequences batched
 along the batch axis): 2 normalise pre-passes + tcgen05 correlation build of all 4 levels, forward warp of the
@@ -15,7 +16,9 @@ max-over-ranks of the timings.  One JSON line is printed by rank 0.
 """
 import argparse
 import json
+import math
 import os
+import subprocess
 import statistics
 import sys
 import threading
@@ -39,7 +42,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
     ap.add_argument("--seqs-per-gpu", type=int, default=8)
     ap.add_argument("--height", type=int, default=540)
     ap.add_argument("--width", type=int, default=960)
@@ -51,6 +54,8 @@ def parse():
                     help="do not hand each frame's transposed features to the next frame's warp (atomic scatter instead)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-gpu-reference", action="store_true", help="do not time the reference's own PyTorch path on the GPU")
+    ap.add_argument("--want-fmap", action="store_true", help="plain drop-in warp: materialise the 256-channel warped features")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     return ap.parse_args()
 
@@ -90,13 +95,32 @@ def make_slot(B, H, W, iters, seed, device, pin=False):
     return host, dev
 
 
+def synthetic_intrinsics(batch, height, width, device, scale=0.25):
+    """TartanAir-style pinhole camera scaled to feature resolution (evaluate_stereo.py:138-142, tc_stereo.py:121-123).
+    The workload definition lives here, not in the product package: the reference arms must not load libtcs_b200.so."""
+    f = 0.5 * width
+    K = torch.tensor([[f, 0.0, 0.5 * width], [0.0, f, 0.5 * height], [0.0, 0.0, 1.0]], dtype=torch.float64)
+    Ks = K * torch.tensor([scale, scale, 1.0], dtype=torch.float64).view(3, 1)
+    rep = lambda m: m.to(torch.float32).unsqueeze(0).repeat(batch, 1, 1).contiguous().to(device)
+    return rep(Ks), rep(torch.linalg.inv(Ks))
+
+
+def synthetic_pose(frame, seq_id=0):
+    """world2cam 4x4: 0.05 m per frame along +z, 0.2 degrees of yaw per frame, a per-sequence lateral offset."""
+    yaw = math.radians(0.2 * frame)
+    c, s = math.cos(yaw), math.sin(yaw)
+    cam2world = torch.tensor([[c, 0.0, s, 0.002 * (seq_id % 7) * frame], [0.0, 1.0, 0.0, 0.0], [-s, 0.0, c, 0.05 * frame],
+                              [0.0, 0.0, 0.0, 1.0]], dtype=torch.float64)
+    return torch.linalg.inv(cam2world).to(torch.float32)
+
+
 def camera(B, H, W, device, frame):
-    from tcs_b200 import sequence
-    K, K_inv = sequence.synthetic_intrinsics(B, 4 * H, 4 * W, device)
-    prev = torch.stack([sequence.synthetic_pose(frame - 1, s) for s in range(B)])
-    cur = torch.stack([sequence.synthetic_pose(frame, s) for s in range(B)])
-    fwd, inv = sequence.relative_pose(prev, cur)
-    return {"K": K, "K_inv": K_inv, "rel_T": fwd.to(device), "rel_T_inv": inv.to(device),
+    K, K_inv = synthetic_intrinsics(B, 4 * H, 4 * W, device)
+    prev = torch.stack([synthetic_pose(frame - 1, s) for s in range(B)]).double()
+    cur = torch.stack([synthetic_pose(frame, s) for s in range(B)]).double()
+    fwd = cur @ torch.linalg.inv(prev)                                   # geo_utils.py:148-155
+    inv = torch.linalg.inv(fwd)
+    return {"K": K, "K_inv": K_inv, "rel_T": fwd.float().contiguous().to(device), "rel_T_inv": inv.float().contiguous().to(device),
             "baseline": torch.full((B, 1), 0.25, device=device)}
 
 
@@ -156,30 +180,43 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arms (the reference's path on the host cores)
+# reference arms: the reference's own code for the path (baseline/_ref through oracle/ref_model.py), or, when the
+# reference did not travel, the torch-CPU port of its call sequence (oracle/torch_port.py).  None of the product.
 # ------------------------------------------------------------------------------------------------------------
 
-def cpu_frames_per_second(H, W, iters, budget_s, steps=None, warmup=1):
-    """torch-CPU port of the reference's call sequence (oracle/torch_port.py), one sequence per step."""
-    from oracle import torch_port as tp
-    from tcs_b200 import sequence
+def workload_text(args, B):
+    return "%dx%d temporal frames, %d lookup iters, 4-level pyramid r=4, C=256, %d sequences per GPU batched" % (
+        args.height, args.width, args.iters, B)
+
+
+def cpu_frames_per_second(B, H, W, iters, budget_s, steps=None, warmup=1):
+    """One step = the hot path's share of one temporal frame for B batched sequences, on the host cores."""
+    from oracle import ref_model
     try:   # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
         torch.set_num_threads(len(os.sched_getaffinity(0)))
     except (AttributeError, RuntimeError):
         pass
-    g = torch.Generator().manual_seed(7)
-    f = [torch.randn(1, C, H, W, generator=g) for _ in range(2)]
-    xs = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
-    disp = 0.5 + torch.rand(1, 1, H, W, generator=g) * (W / 16.0)
-    coords = xs - (disp[None] + torch.cumsum(0.05 * torch.randn(iters, 1, 1, H, W, generator=g), 0))
-    nets = [torch.tanh(torch.randn(1, 128, H >> i, W >> i, generator=g)) for i in range(3)]
-    K, K_inv = sequence.synthetic_intrinsics(1, 4 * H, 4 * W, "cpu")
-    fwd, inv = sequence.relative_pose(sequence.synthetic_pose(0)[None], sequence.synthetic_pose(1)[None])
-    base = torch.full((1, 1), 0.25)
+    _, dev = make_slot(B, H, W, iters, 7, "cpu")
+    _, prev = make_slot(B, H, W, 1, 24, "cpu")
+    cam = camera(B, H, W, "cpu", 1)
+    state = (prev["last_disp"], prev["f1"], prev["nets"])
+    kind = "port"
+    if ref_model.reference_root() is not None:
+        ref = ref_model.load()
+        ref_model.use_cpu_splat(ref, threaded=True)
+        kind = "reference"
 
-    def one():
-        with torch.no_grad():
-            tp.frame(f[0], f[1], coords, state=(disp, f[1], nets), rel_T=fwd, rel_T_inv=inv, K=K, K_inv=K_inv, baseline=base)
+        def one():
+            with torch.no_grad():
+                ref_model.hot_path_frame(ref, dev["f1"], dev["f2"], dev["coords"], state, cam["rel_T"], cam["rel_T_inv"],
+                                         cam["K"], cam["K_inv"], cam["baseline"])
+    else:
+        from oracle import torch_port as tp
+
+        def one():
+            with torch.no_grad():
+                tp.frame(dev["f1"], dev["f2"], dev["coords"], state=state, rel_T=cam["rel_T"], rel_T_inv=cam["rel_T_inv"],
+                         K=cam["K"], K_inv=cam["K_inv"], baseline=cam["baseline"])
 
     for _ in range(warmup):
         one()
@@ -190,27 +227,114 @@ def cpu_frames_per_second(H, W, iters, budget_s, steps=None, warmup=1):
         el = time.perf_counter() - t0
         if (steps is not None and n >= steps) or (steps is None and (el >= budget_s or n >= 50)):
             break
-    return n / el, n, el
+    return B * n / el, n, el, kind
+
+
+CPU_NOTE = {"reference": "the reference's own core/corr.py, geo_utils.py, utils.py calls (baseline/_ref) in TCStereo.forward's order; "
+                         "its cupy splat kernel cannot run on a CPU and is replaced by index_add_ (oracle/torch_port.py)",
+            "port": "oracle/torch_port.py (torch-CPU restatement of the reference's call sequence; baseline/_ref absent)"}
+
+
+def product_so_loaded():
+    """Names of this repository's native libraries mapped into the process (the reference arms must report none)."""
+    try:
+        with open("/proc/self/maps") as f:
+            return sorted({os.path.basename(l.split()[-1]) for l in f if "libtcs_b200" in l})
+    except OSError:
+        return None
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    B = args.seqs_per_gpu
     H, W = feature_hw(args.height, args.width)
-    fps, n, el = cpu_frames_per_second(H, W, args.iters, 0, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    fps, n, el, kind = cpu_frames_per_second(B, H, W, args.iters, 0, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
     cores = torch.get_num_threads()
-    sample = "1 sequence per step (%d temporal frames of %dx%d, %d lookups each) on %d host threads" % (n, args.height, args.width, args.iters, cores)
+    sample = "%d steps of %d batched sequences (%dx%d, %d lookups each) on %d host threads; %s" % (
+        n, B, args.height, args.width, args.iters, cores, CPU_NOTE[kind])
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%dx%d temporal frames, %d lookup iters, 4-level pyramid r=4, C=256" % (args.height, args.width, args.iters),
-                   "feature_hw": [H, W]},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_text(args, B), "feature_hw": [H, W], "seqs_per_gpu": B},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "product_so_loaded": product_so_loaded(),
     }))
+
+
+def run_reference_gpu(args):
+    """the reference's own PyTorch code for the path on the B200 (cuBLAS SGEMM behind einsum,
+    4 avg_pool2d, 4 grid_sample per lookup, ~40 elementwise launches + its own NVRTC-compiled splat kernel in warp) on the
+    same batched inputs as the B200 arm, eager (it cannot be graph-captured: host syncs), CUDA-event timed per phase.
+    Run under `python -O` to strip its assert-induced host syncs."""
+    from oracle import ref_model
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if ref_model.reference_root() is None or not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "baseline/_ref not installed or no CUDA device"}))
+        return
+    ref = ref_model.load()
+    device = torch.device("cuda", 0)
+    B, iters = args.seqs_per_gpu, args.iters
+    H, W = feature_hw(args.height, args.width)
+    slots = [make_slot(B, H, W, iters, 1234 + 17 * s, device)[1] for s in range(2)]
+    cam = camera(B, H, W, device, 1)
+    marks = []
+
+    def step(k, timed):
+        s, o = slots[k % 2], slots[1 - k % 2]
+        ev = {}
+
+        def tick(label):
+            if timed:
+                ev[label] = torch.cuda.Event(enable_timing=True)
+                ev[label].record()
+        with torch.no_grad():
+            out = ref_model.hot_path_frame(ref, s["f1"], s["f2"], s["coords"], (o["last_disp"], o["f1"], o["nets"]), cam["rel_T"],
+                                           cam["rel_T_inv"], cam["K"], cam["K_inv"], cam["baseline"], timers=tick)
+        if timed:
+            marks.append(ev)
+        return out
+
+    for k in range(max(args.warmup, 2)):
+        step(k, False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        out = step(k, True)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ph = {n: sum(m[a].elapsed_time(m[b]) for m in marks) / len(marks)
+          for n, a, b in (("build_ms", "start", "build"), ("warp_ms", "build", "warp"), ("lookups_ms", "warp", "lookups"))}
+    total_ms = sum(m["start"].elapsed_time(m["lookups"]) for m in marks)
+    fps = B * args.steps / wall
+    print(json.dumps({
+        "impl": "reference-gpu", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 2), "ms_per_step": 1e3 * wall / args.steps, "device_ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "dtype": "f32", "data": "synthetic", "asserts": bool(__debug__),
+        "config": {"workload": workload_text(args, B), "feature_hw": [H, W], "seqs_per_gpu": B,
+                   "what": "reference core/corr.py + geo_utils.py + utils.py + softsplat.py (own CUDA kernel via NVRTC) on cuda:0, eager"},
+        "phases": ph, "checksum": float(out["corr"].double().sum().item()), "product_so_loaded": product_so_loaded(),
+    }))
+
+
+def gpu_reference_legs(args):
+    """Both modes of the reference-on-GPU leg as subprocesses (the -O mode needs its own interpreter)."""
+    res = {}
+    base = [os.path.join(ROOT, "bench.py"), "--impl", "reference-gpu", "--steps", "5", "--warmup", "2",
+            "--seqs-per-gpu", str(args.seqs_per_gpu), "--height", str(args.height), "--width", str(args.width), "--iters", str(args.iters)]
+    for name, flags in (("as_is", []), ("python_O", ["-O"])):
+        try:
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+            r = subprocess.run([sys.executable] + flags + base, capture_output=True, text=True, timeout=600, env=env)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            res[name] = json.loads(line[-1]) if line else {"unavailable": (r.stderr or "no output")[-300:]}
+        except Exception as e:  # noqa: BLE001
+            res[name] = {"unavailable": str(e)[:300]}
+    return res
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -253,10 +377,11 @@ def run_b200(args):
 
     def phase_warp(s):
         o = slots[1 - s]
+        carry = args.warp_carry and not args.want_fmap
         d, _, m, c = tcs_b200.warp_with_cost(o["last_disp"], o["f1"], cam["rel_T"], cam["K"], cam["K_inv"], cam["baseline"],
-                                             cur_fmap=slots[s]["f1"], per_sample_mean=True, want_fmap=False,
-                                             carry_in=carries[1 - s] if args.warp_carry else None,
-                                             carry_out=carries[s] if args.warp_carry else None)
+                                             cur_fmap=slots[s]["f1"], per_sample_mean=True, want_fmap=args.want_fmap,
+                                             carry_in=carries[1 - s] if carry else None,
+                                             carry_out=carries[s] if carry else None)
         grid = tcs_b200.get_backward_grid(d, cam["rel_T_inv"], cam["K"], cam["K_inv"], cam["baseline"])
         live[s]["init"] = (d, c, m)
         live[s]["nets"] = tcs_b200.warp_hidden_states(o["nets"], grid)
@@ -370,6 +495,21 @@ def run_b200(args):
 
         e2e_carry = [tcs_b200.WarpCarry().reserve(slots[0]["f1"]) for _ in range(3)]    # one per staging buffer
         stage[2]["f1"].copy_(slots[1]["f1"])                    # "frame -1" features for the first warp
+        # copy-only probe: what the host -> device link gives this rank with nothing else going on (all ranks at once)
+        barrier()
+        pe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        pe[0].record(main)
+        for cs in copy_streams:
+            cs.wait_event(pe[0])
+        for rep in range(4):
+            for j, name in enumerate(("f1", "f2")):
+                with torch.cuda.stream(copy_streams[j]):
+                    stage[rep % 2][name].copy_(slots_host[rep % 2][name], non_blocking=True)
+        for cs in copy_streams:
+            main.wait_stream(cs)
+        pe[1].record(main)
+        barrier()
+        probe_gbs = 4 * h2d / (pe[0].elapsed_time(pe[1]) * 1e-3) / 1e9
         upload(0)
         for k in range(2):                                       # warm-up of the e2e loop itself
             e2e_step(k)
@@ -382,20 +522,36 @@ def run_b200(args):
         tt = torch.tensor([el], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        rates = torch.tensor([K_steps * h2d / el / 1e9, probe_gbs], dtype=torch.float64, device=device)
+        allr = [torch.zeros_like(rates) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allr, rates)
+        else:
+            allr = [rates]
         e2e = {"value": frames / tt.item(), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "note": "pinned host fmaps -> H2D (two copy streams, triple-buffered staging) -> hot_path_frame (eager public API) -> D2H of lookup + init; PCIe-bound"}
+               "h2d_gbs_per_rank_in_loop": [round(r[0].item(), 2) for r in allr],
+               "h2d_gbs_per_rank_copy_only": [round(r[1].item(), 2) for r in allr],
+               "h2d_gbs_total_copy_only": round(sum(r[1].item() for r in allr), 1),
+               "device_ms_per_step_without_copies": total_ms / K_steps,
+               "note": "pinned host fmaps -> H2D (two copy streams, triple-buffered staging) -> hot_path_frame (eager public API) -> D2H "
+                       "of lookup + init.  Bound by the host->device link: compare h2d_gbs_per_rank_in_loop with the copy-only probe "
+                       "(all ranks copying at once, no kernels); the kernels need device_ms_per_step_without_copies"}
 
     # ---- rooflines
     npix = B * H * W
     lookup_bytes = 308 * npix                                   # 4 coord + 4*10*4 taps + 4*9*4 out per pixel
     lookup_ms = phase_ms[2] / iters
-    traffic = None
+    traffic, traffic_src = None, None
     tp_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp_path):
-        traffic = json.load(open(tp_path)).get("corr_lookup_bytes_per_launch_B%d" % B)
+    if os.path.exists(tp_path) and (H, W) == (136, 240):
+        tj = json.load(open(tp_path))
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from an `ncu --set full` capture of THIS command's
+        # lookups in the middle of a step (other phases' data and earlier calls' output planes in L2), not of an isolated launch
+        traffic = tj.get("corr_lookup_in_step_bytes_per_launch_B%d" % B, tj.get("corr_lookup_bytes_per_launch_B%d" % B))
+        traffic_src = tj.get("source")
     roofline = {"kernel": "corr_lookup_r4x4o_kernel", "bound": "hbm", "achieved": lookup_bytes / (lookup_ms * 1e-3) / 1e9,
                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": lookup_bytes / (lookup_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                "traffic": traffic, "peak_source": pk["source"], "launches_per_step": iters,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["source"], "launches_per_step": iters,
                 "algorithmic_bytes_per_launch": lookup_bytes}
     build_flops = 2.0 * npix * W * C
     build_bytes = 2 * npix * C * 4 + npix * W * 4 * (1 + 0.5 + 0.25 + 0.125)
@@ -409,11 +565,17 @@ def run_b200(args):
                  "hbm_frac": warp_bytes / (phase_ms[1] * 1e-3) / 1e9 / pk["hbm_gbs"]},
     }
 
-    cpu = None
+    used_graphs = graphs is not None
+    cpu, gpu_ref = None, None
+    if rank == 0 and world == 1 and not args.skip_gpu_reference:
+        live.clear()
+        graphs = None
+        torch.cuda.empty_cache()
+        gpu_ref = gpu_reference_legs(args)
     if rank == 0 and world == 1 and not args.skip_cpu:
-        fps, n, el = cpu_frames_per_second(H, W, iters, args.cpu_seconds)
-        cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "%d temporal frames of 1 sequence (%dx%d, %d lookups) in %.1f s, oracle/torch_port.py" % (n, args.height, args.width, iters, el)}
+        fps, n, el, kind = cpu_frames_per_second(B, H, W, iters, args.cpu_seconds)
+        cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind,
+               "sample": "%d steps of %d batched sequences (%dx%d, %d lookups) in %.1f s; %s" % (n, B, args.height, args.width, iters, el, CPU_NOTE[kind])}
 
     if rank == 0:
         print(json.dumps({
@@ -421,14 +583,13 @@ def run_b200(args):
             "ms_per_step": total_ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp16x3": "f16x3->f32", "bf16x3": "bf16x3->f32", "bf16": "bf16->f32", "fp16": "f16->f32", "fp32": "f32"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "%dx%d temporal frames, %d lookup iters, 4-level pyramid r=4, C=256, %d sequences per GPU batched"
-                                   % (args.height, args.width, iters, B),
+            "config": {"workload": workload_text(args, B),
                        "feature_hw": [H, W], "seqs_per_gpu": B, "precision": args.precision, "mode": args.mode,
-                       "cuda_graphs": graphs is not None, "fused_build": fused_build, "warp": "lists on carried transposition" if args.warp_carry else "scatter", "l2": "inputs larger than L2 (%.0f MB of feature maps per step, 2 alternating slots)" % (2 * npix * C * 4 / 1e6),
+                       "cuda_graphs": used_graphs, "fused_build": fused_build, "warp": ("scatter + warped-feature store (plain drop-in)" if args.want_fmap else "lists on carried transposition" if args.warp_carry else "scatter, cost only"), "l2": "inputs larger than L2 (%.0f MB of feature maps per step, 2 alternating slots)" % (2 * npix * C * 4 / 1e6),
                        "parallelism": "sequences sharded per GPU, no data-path collective"},
             "e2e": e2e, "gpu_launches": K_steps * sequence.launches_per_frame(iters, False, mode=args.mode, fused_build=fused_build,
-                                                                                    warp_lists=args.warp_carry),
-            "clocks": clocks, "roofline": roofline, "phases": phases_out, "cpu_baseline": cpu, "checksum": checksum,
+                                                                                    warp_lists=args.warp_carry and not args.want_fmap),
+            "clocks": clocks, "roofline": roofline, "phases": phases_out, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "checksum": checksum,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -438,6 +599,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_b200(args)
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCS_ABI_VERSION 2
+#define TCS_ABI_VERSION 3
 
 /* argument errors (negative); CUDA launch errors are returned as positive cudaError_t values */
 #define TCS_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported combination */
@@ -171,6 +171,11 @@ int tcs_warp_forward(const float* disp, const float* fmap, const float* rel_T, c
                      float* out_disp, float* out_fmap, float* out_mask, float* out_cost,
                      const float* fmap_t, float* cur_t_out,
                      void* scratch, int B, int C, int H, int W, int flags, void* stream);
+
+/* ref: core/utils/geo_utils.py:148-155 (cal_relative_transformation): out = T2 * inv(T1), batched 4x4 world2cam
+ * poses, computed in fp64 and rounded once (the reference: fp32 LU with a host sync on `info`, fp32 matmul).
+ *   T1, T2, out  [B,4,4] fp32 row-major. */
+int tcs_relative_pose(const float* T1, const float* T2, float* out, int B, void* stream);
 
 /* ref: core/utils/geo_utils.py:201-236 (get_backward_grid).  disp [B,1,H,W] -> grid [B,2,H,W] (x,y). */
 int tcs_backward_grid(const float* disp, const float* rel_T, const float* K, const float* K_inv,

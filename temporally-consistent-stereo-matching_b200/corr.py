@@ -11,6 +11,7 @@ import os
 import torch
 
 from . import _lib
+from .lazy import LazyTensorOps
 
 _DEFAULT_PRECISION = os.environ.get("TCS_B200_PRECISION", "fp16x3")
 _DEFAULT_MODE = os.environ.get("TCS_B200_CORR_MODE", "pyramid")
@@ -25,6 +26,11 @@ def _check_fmap(name, t):
         raise TypeError("%s must be a CUDA tensor (libtcs_b200 has no CPU path)" % name)
     if t.dim() != 4:
         raise ValueError("%s must be [B, C, H, W], got %s" % (name, tuple(t.shape)))
+    if t.requires_grad and torch.is_grad_enabled():
+        # in the reference, gradients flow through the volume into fnet (corr.py:60) and get_cost_volume feeds the
+        # training loss (train_stereo.py:385): a training run on these kernels would silently train with them cut
+        raise RuntimeError("%s requires grad, but libtcs_b200 is inference only (no backward kernels): run under "
+                           "torch.no_grad() with test_mode=True, or uninstall() the drop-in for training" % name)
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
@@ -127,7 +133,7 @@ def _coords_plane(coords, B, H, W1):
     return c, c.data_ptr(), (c.stride(0) if B > 1 else H * W1)
 
 
-class LazyLookup:
+class LazyLookup(LazyTensorOps):
     """corr_fn(coords) not yet evaluated.  BasicMotionEncoder's patched forward calls .encode(convc1) and never
     materialises the 36 tap planes; every other use (torch functions, the reference's isnan asserts) goes through
     __torch_function__ and sees the ordinary lookup result."""
@@ -141,6 +147,11 @@ class LazyLookup:
         return self._value
 
     def encode(self, conv, relu=True):
+        if self._value is not None:
+            # something already forced the 36 tap planes (without `python -O` the reference's isnan/isinf assert at
+            # update.py:155 does, every iteration): finish with the ordinary 1x1 instead of looking everything up twice
+            out = conv(self._value)
+            return torch.relu_(out) if relu else out
         return self.block.lookup_encoded(self.coords, conv.weight, conv.bias, relu=relu)
 
     @classmethod
@@ -174,6 +185,7 @@ class CorrBlock1D:
         self.B, self.C, self.H, self.W1 = fmap1.shape
         self.W2 = fmap2.shape[3]
         self.device = fmap1.device
+        self.fmap1 = fmap1          # what the build read (the model's fmap1 itself when it is fp32 and contiguous)
         self._cost_volume = None
         if self.mode == "pyramid":
             self._flat, self._levels = build_pyramid(fmap1, fmap2, num_levels, self.precision)
@@ -198,7 +210,7 @@ class CorrBlock1D:
         self = cls.__new__(cls)
         lv0 = levels[0]
         self.B, self.H, self.W1, self.W2 = lv0.shape
-        self.C = None
+        self.C, self.fmap1 = None, None
         self.num_levels, self.radius, self.thres = len(levels), radius, 0.2
         self.precision, self.mode, self.device = "external", "pyramid", lv0.device
         self._flat, self._levels = alloc_pyramid(self.B, self.H, self.W1, self.W2, self.num_levels, self.device)

@@ -251,13 +251,9 @@ extern "C" int tcs_corr_build(const void* a_hi, const void* a_lo, const void* b_
         tb_lo = tb_hi;
     }
 
-    static bool attr_done[64] = {};
-    int dev = 0;
-    TCS_CHECK_CUDA(cudaGetDevice(&dev));
-    if (!attr_done[dev & 63]) {
+    TCS_ONCE_PER_DEVICE(
         TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBuildSmemBytes));
-        attr_done[dev & 63] = true;
-    }
+    );
     const int grid = (int)((total < (long long)num_sms()) ? total : (long long)num_sms());
     corr_build_kernel<<<grid, kBuildThreads, kBuildSmemBytes, static_cast<cudaStream_t>(stream)>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
     TCS_CHECK_LAUNCH("tcs_corr_build");

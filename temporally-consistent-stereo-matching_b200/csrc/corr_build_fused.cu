@@ -563,12 +563,10 @@ extern "C" int tcs_corr_build_fused(const float* fmap1, const float* fmap2,
         if (num_levels > 1 && (rc = make_level_map(&tml1, lv[1], B * H, W1, W2 >> 1, 16, CU_TENSOR_MAP_SWIZZLE_64B)) != 0) return rc;
     }
 
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[fp16 ? 1 : 0]) {
-        if (fp16) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_build_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        else TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_build_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_done[fp16 ? 1 : 0] = true;
-    }
+    TCS_ONCE_PER_DEVICE(
+        TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_build_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_build_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    );
     const int units = p.num_rows * p.num_m;
     const int grid = units < num_sms() ? units : num_sms();
     cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -732,12 +732,10 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
     if (radius == 4) {
         TCS_REQUIRE(B <= 65535, TCS_E_SHAPE, "tcs_corr_lookup: B must be <= 65535");
         dim3 grid((unsigned)ceil_div(H * W1, kLookThreads), 1, B);
-        static bool attr_done = false;
-        if (!attr_done) {   // leave most of the unified array to L1: the loads stream through it (27 vs 68 us)
+        TCS_ONCE_PER_DEVICE(   // leave most of the unified array to L1: the loads stream through it (27 vs 68 us)
             const int carve = carveout_percent("TCS_CARVE_LOOKUP", 25);
             if (carve >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_r4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            attr_done = true;
-        }
+        );
         // W2 % 16 == 0: the rows of levels 0 and 2 start on 16-byte boundaries (no bounds predicates); with a 32-byte
         // aligned level 0 its span comes as 32-byte loads
         const dim3 grid2(grid.x, 2, B);            // 4 levels: one thread per (pixel, level pair)
@@ -772,16 +770,14 @@ extern "C" int tcs_corr_lookup_encode(const float* lvl0, const float* lvl1, cons
     LevelPtrs lp;
     for (int l = 0; l < 4; ++l) lp.p[l] = lv[l];
     dim3 grid((unsigned)ceil_div(H * W1, kLookThreads), 1, B);
-    static bool attr_done = false;
-    if (!attr_done) {
+    TCS_ONCE_PER_DEVICE(
         const int carve = carveout_percent("TCS_CARVE_LOOKUP_ENC", 25);
         if (carve >= 0) {
             TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         }
-        attr_done = true;
-    }
+    );
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (W2 % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
         corr_lookup_encode_kernel<2><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, weight, bias, out, H * W1, W2, Cout, relu);

@@ -145,20 +145,16 @@ extern "C" int tcs_corr_prepass(const float* fmap, void* hi, void* lo, float* n3
     dim3 grid(ceil_div(W, kPreTileW), H, B);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (fp16) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        TCS_ONCE_PER_DEVICE(
             TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 513 * 4));
             { const int cv = carveout_percent("TCS_CARVE_PREPASS", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); }
-            attr_done = true;
-        }
+        );
         corr_prepass_kernel<true><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W);
     } else {
-        static bool attr_done = false;
-        if (!attr_done) {
+        TCS_ONCE_PER_DEVICE(
             TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 513 * 4));
             { const int cv = carveout_percent("TCS_CARVE_PREPASS", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); }
-            attr_done = true;
-        }
+        );
         corr_prepass_kernel<false><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W);
     }
     TCS_CHECK_LAUNCH("tcs_corr_prepass");

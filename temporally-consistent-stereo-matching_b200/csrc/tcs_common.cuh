@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 
@@ -38,6 +39,19 @@ void set_error(const char* fmt, ...);
         if (e__ != cudaSuccess) {                                                   \
             ::tcs::set_error("%s: %s", #expr, cudaGetErrorString(e__));             \
             return static_cast<int>(e__);                                           \
+        }                                                                           \
+    } while (0)
+
+// Function attributes (dynamic shared memory opt-in, carve-out hints) apply per DEVICE: run `body` the first time the
+// enclosing call site is reached on each device of the process.  Two racing threads may both run it (idempotent).
+#define TCS_ONCE_PER_DEVICE(...)                                                    \
+    do {                                                                            \
+        static std::atomic<bool> done__[64];                                        \
+        int dev__ = 0;                                                              \
+        TCS_CHECK_CUDA(cudaGetDevice(&dev__));                                      \
+        if (!done__[dev__ & 63].load(std::memory_order_acquire)) {                  \
+            __VA_ARGS__                                                             \
+            done__[dev__ & 63].store(true, std::memory_order_release);              \
         }                                                                           \
     } while (0)
 

@@ -5,6 +5,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 namespace tcs {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -13,15 +15,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 inline EncodeTiledFn get_encode_fn() {
     static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         void* ptr = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
             fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
+    });
     return fn;
 }
 

@@ -900,8 +900,7 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
     const size_t smem_cost = (size_t)C * 33 * sizeof(float);
 #define TCS_WARP_CASE(G)                                                                                              \
     case G: {                                                                                                         \
-        static bool attr_done = false;                                                                                \
-        if (!attr_done) {                                                                                             \
+        TCS_ONCE_PER_DEVICE(                                                                                          \
             TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_splat_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_splat)); \
             TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_transpose_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_splat)); \
             TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_finalize_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin)); \
@@ -909,8 +908,7 @@ extern "C" int tcs_warp_forward(const float* disp, const float* fmap, const floa
             TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_cost_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cost)); \
             TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_cost_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cost)); \
             { const int cv = carveout_percent("TCS_CARVE_SPLAT", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(warp_splat_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); } \
-            attr_done = true;                                                                                         \
-        }                                                                                                             \
+        );                                                                                                            \
         const bool cost_only = out_fmap == nullptr && out_cost != nullptr && cur_fmap != nullptr;                     \
         if (lists) {                                                                                                  \
             if (fmap_t == nullptr) {                                                                                  \

@@ -2,14 +2,115 @@
 
 core/tc_stereo.py imports CorrBlock1D, warp, get_backward_grid, cal_relative_transformation and
 bilinear_sampler by name (tc_stereo.py:6-8), so the drop-in is an assignment into that module's namespace;
-TCStereo.forward (tc_stereo.py:114-116,137,142,159-163,177) then runs unmodified on libtcs_b200.
+TCStereo.forward (tc_stereo.py:114-116,127,137,142,159-163,177) then runs unmodified on libtcs_b200.
 """
+import torch
+import torch.nn.functional as F
+
+from .lazy import LazyTensorOps
+
 _saved = {}
-_NAMES = ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler")
+_NAMES = ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler", "cal_relative_transformation")
 
 
-def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=None, stencils=None):
+class _FrameContext:
+    """What one TCStereo.forward leaves behind for the next call of the patched `warp` (fuse_cost=True): the current
+    frame's fmap1 (seen by the CorrBlock1D constructor, tc_stereo.py:116, one statement before the warp, :137) and two
+    alternating WarpCarry buffers (each frame's fmap1 transposed by its own cost kernel for the next frame's warp)."""
+
+    def __init__(self):
+        self.cur_fmap1 = None
+        self.carries = None
+        self.fused_calls = 0
+        self.carried_calls = 0
+
+
+_ctx = _FrameContext()
+
+
+class LazyWarpedFmap(LazyTensorOps):
+    """warp()'s second output under install(..., fuse_cost=True): the warped features, not materialised.
+
+    TCStereo.forward uses them for exactly one expression (tc_stereo.py:139-140),
+
+        cost = torch.sum(F.normalize(fmap1, dim=1) * F.normalize(warped_fmap1, dim=1), dim=1, keepdim=True) * sparse_mask
+
+    which the cost kernel of tcs_warp_forward already evaluated against the current frame's fmap1 while it
+    normalised the splat (the 256-channel warped map is never stored).  F.normalize(self, dim=1) -> a marker;
+    normalised_fmap1 * marker -> a marker that remembers the other factor's shape; torch.sum(marker, dim=1,
+    keepdim=True) -> the fused cost (already times the mask, and the mask is 0/1, so the reference's second
+    multiplication changes nothing).  Any other use of the object materialises the warped features with the
+    ordinary warp kernels and continues as a tensor."""
+
+    _NORMALIZED, _PRODUCT = 1, 2
+
+    def __init__(self, cost, shape, rerun, stage=0):
+        self._cost, self._shape, self._rerun, self._stage, self._value = cost, torch.Size(shape), rerun, stage, None
+
+    @property
+    def shape(self):
+        return self._shape
+
+    def materialize(self):
+        if self._stage != 0:
+            raise RuntimeError("the fused matching cost was used outside the expression of tc_stereo.py:139-140; "
+                               "install the drop-in without fuse_cost=True for this model")
+        if self._value is None:
+            self._value = self._rerun()
+        return self._value
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        me = next((a for a in args if isinstance(a, LazyWarpedFmap)), None)
+        name = getattr(func, "__name__", "")
+        if me is not None and me._value is None:
+            if me._stage == 0 and func is F.normalize and args[0] is me and \
+                    (kwargs.get("dim", args[2] if len(args) > 2 else 1) == 1) and kwargs.get("p", 2.0) in (2, 2.0):
+                return LazyWarpedFmap(me._cost, me._shape, None, cls._NORMALIZED)
+            if me._stage == cls._NORMALIZED and name in ("mul", "__mul__", "__rmul__") and len(args) == 2:
+                other = args[1] if args[0] is me else args[0]
+                if isinstance(other, torch.Tensor) and other.shape == me._shape:
+                    return LazyWarpedFmap(me._cost, me._shape, None, cls._PRODUCT)
+            if me._stage == cls._PRODUCT and name == "sum" and args[0] is me and \
+                    (kwargs.get("dim", args[1] if len(args) > 1 else None) in (1, [1], (1,))) and \
+                    kwargs.get("keepdim", args[2] if len(args) > 2 else False):
+                return me._cost
+        unwrap = lambda a: a.materialize() if isinstance(a, LazyWarpedFmap) else a
+        return func(*[unwrap(a) for a in args], **{k: unwrap(v) for k, v in kwargs.items()})
+
+
+def _fused_warp(disp, fmap, relative_T, K, K_inv, baseline):
+    """geo.warp for TCStereo.forward with the matching cost fused (ref: geo_utils.py:158-198 + tc_stereo.py:139-140)."""
+    from . import geo
+
+    cur = _ctx.cur_fmap1
+    if cur is None or not isinstance(fmap, torch.Tensor) or cur.shape != fmap.shape or cur.device != fmap.device:
+        return geo.warp(disp, fmap, relative_T, K, K_inv, baseline)
+    if _ctx.carries is None:
+        _ctx.carries = [geo.WarpCarry(), geo.WarpCarry()]
+    fm = fmap if (fmap.dtype == torch.float32 and fmap.is_contiguous()) else None
+    cin = next((c for c in _ctx.carries if fm is not None and c.matches(fm)), None)
+    cout = next(c for c in _ctx.carries if c is not cin)
+    d, _, m, cost = geo.warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=cur, per_sample_mean=False,
+                                       want_fmap=False, deterministic=True, carry_in=cin, carry_out=cout)
+    _ctx.fused_calls += 1
+    _ctx.carried_calls += cin is not None
+    _ctx.cur_fmap1 = None
+
+    def rerun():
+        return geo.warp(disp, fmap, relative_T, K, K_inv, baseline)[1]
+
+    return d, LazyWarpedFmap(cost, fmap.shape, rerun), m
+
+
+def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=None, stencils=None, fuse_cost=False):
     """tc_stereo_module: the imported `core.tc_stereo`.  Returns the dict of names that were replaced.
+
+    fuse_cost: `warp` also evaluates the matching cost of tc_stereo.py:139-140 in its normalise kernel (against the
+    fmap1 the CorrBlock1D constructor saw one statement earlier), never stores the 256-channel warped features, runs
+    the deterministic list formulation, and hands each frame's transposed fmap1 to the next frame's call (WarpCarry).
+    The second return value is then a LazyWarpedFmap (see there) instead of a tensor.
 
     stencils: the imported `core.update`.  When given, the three per-iteration 3x3 stencils also run as single kernels
     (SURVEY.md section 8f rank 2): `disp2disp_gradient_xy` (tc_stereo.py:192), `disp2disp_grad_candidates`
@@ -22,12 +123,14 @@ def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=Non
     from . import corr, geo
 
     block = corr.CorrBlock1D
-    if precision is not None or mode is not None or fuse_motion_encoder is not None:
+    if precision is not None or mode is not None or fuse_motion_encoder is not None or fuse_cost:
         lazy = fuse_motion_encoder is not None
 
         class _Configured(corr.CorrBlock1D):
             def __init__(self, fmap1, fmap2, num_levels=4, radius=4, thres=0.2):
                 super().__init__(fmap1, fmap2, num_levels, radius, thres, precision=precision, mode=mode)
+                if fuse_cost:
+                    _ctx.cur_fmap1 = self.fmap1          # the fp32 contiguous tensor the build read
 
             def __call__(self, coords):
                 if lazy and self.mode == "pyramid" and self.num_levels == 4 and self.radius == 4:
@@ -39,8 +142,8 @@ def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=Non
         _patch_motion_encoder(fuse_motion_encoder)
     if stencils is not None:
         _patch_stencils(tc_stereo_module, stencils)
-    new = {"CorrBlock1D": block, "warp": geo.warp, "get_backward_grid": geo.get_backward_grid,
-           "bilinear_sampler": geo.bilinear_sampler}
+    new = {"CorrBlock1D": block, "warp": _fused_warp if fuse_cost else geo.warp, "get_backward_grid": geo.get_backward_grid,
+           "bilinear_sampler": geo.bilinear_sampler, "cal_relative_transformation": geo.cal_relative_transformation}
     for name in _NAMES:
         if not hasattr(tc_stereo_module, name):
             raise AttributeError("%s has no attribute %r; is it the reference's core.tc_stereo?" % (tc_stereo_module, name))
@@ -116,3 +219,4 @@ def uninstall(tc_stereo_module, update_module=None):
         old = _saved.pop((id(tc_stereo_module), name), None)
         if old is not None:
             setattr(tc_stereo_module, name, old)
+    _ctx.cur_fmap1, _ctx.carries = None, None

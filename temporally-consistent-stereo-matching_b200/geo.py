@@ -8,16 +8,24 @@ import torch
 
 from . import _lib
 
-_scratch = {}
-
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _no_grad_path(name, t):
+    """The kernels have no backward (inference only).  In the reference, gradients flow through
+    these calls (corr -> fnet, propagate_disparity -> disp_grad, upsample_flow -> up_mask), so a training run on
+    the drop-in would silently train with them cut: refuse instead."""
+    if t.requires_grad and torch.is_grad_enabled():
+        raise RuntimeError("%s requires grad, but libtcs_b200 is inference only (no backward kernels): run under "
+                           "torch.no_grad() / model.eval() with test_mode=True, or uninstall() the drop-in for training" % name)
+
+
 def _f32c(name, t, shape=None):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise TypeError("%s must be a CUDA tensor (libtcs_b200 has no CPU path)" % name)
+    _no_grad_path(name, t)
     if t.dtype != torch.float32:
         t = t.float()
     t = t.contiguous()
@@ -27,17 +35,12 @@ def _f32c(name, t, shape=None):
 
 
 def _warp_scratch(B, C, H, W, device):
-    """Scratch of tcs_warp_forward, cached per shape and stream-ordered like any torch buffer."""
-    key = (device.index, B, C, H, W)
-    buf = _scratch.get(key)
-    if buf is None:
-        n = _lib.warp_scratch_bytes(B, C, H, W)
-        if n <= 0:
-            raise ValueError("bad warp shape B=%d C=%d H=%d W=%d" % (B, C, H, W))
-        buf = torch.empty(n, dtype=torch.uint8, device=device)
-        _scratch.clear()          # one shape at a time is the common case; do not hoard HBM
-        _scratch[key] = buf
-    return buf
+    """Scratch of tcs_warp_forward, taken from torch's caching allocator on every call: stream-ordered (two streams
+    never share a block), owned by the graph's pool when the call is captured into a CUDA graph, and free once warm."""
+    n = _lib.warp_scratch_bytes(B, C, H, W)
+    if n <= 0:
+        raise ValueError("bad warp shape B=%d C=%d H=%d W=%d" % (B, C, H, W))
+    return torch.empty(n, dtype=torch.uint8, device=device)
 
 
 def _camera_args(relative_T, K, K_inv, baseline, B):
@@ -56,13 +59,19 @@ class WarpCarry:
     The cost-only call of warp_with_cost has cur_fmap in shared memory anyway and writes it out as pixel-major rows
     (`rows`, [B*H*W, C] in the library's private channel order).  TC-Stereo hands fmap1 to the next frame as
     last_fmap1 (core/tc_stereo.py:137, evaluate_stereo.py:192-197); when that next call receives this object as
-    `carry_in` and its `fmap` is the very tensor recorded here, unchanged, the list formulation skips its
-    transposition pass.  The tensor is kept referenced so that its storage cannot be reused in between."""
+    `carry_in` and its `fmap` is the memory recorded here, unchanged, the list formulation skips its
+    transposition pass.  The key is (storage pointer, shape, strides, version counter), not object identity: the model
+    hands back `fmap1.detach()` (tc_stereo.py:227,242), a new Python object over the same storage and version counter.
+    The tensor is kept referenced so that its storage cannot be freed and reused in between."""
 
     def __init__(self):
         self.tensor = None
         self.version = -1
         self.rows = None
+
+    def record(self, fmap):
+        self.tensor = fmap
+        self.version = fmap._version
 
     def reserve(self, like):
         """Allocate the row buffer for feature maps shaped like `like` [B,C,H,W] now (e.g. outside a timed loop)."""
@@ -73,8 +82,10 @@ class WarpCarry:
         return self
 
     def matches(self, fmap):
-        return (self.tensor is not None and self.rows is not None and fmap is self.tensor
-                and fmap._version == self.version and fmap.is_contiguous() and fmap.dtype == torch.float32)
+        t = self.tensor
+        return (t is not None and self.rows is not None and fmap.dtype == torch.float32 and fmap.is_contiguous()
+                and fmap.device == t.device and fmap.data_ptr() == t.data_ptr() and fmap.shape == t.shape
+                and fmap.stride() == t.stride() and fmap._version == self.version and t._version == self.version)
 
 
 def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, per_sample_mean=False, want_fmap=True,
@@ -87,7 +98,6 @@ def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, pe
     repeatable, no accumulator, as fast as the default atomic scatter).
     carry_out (a WarpCarry; cost-only calls) receives cur_fmap transposed for the next frame; carry_in (the
     WarpCarry filled when `fmap` was the current frame) selects the list formulation and saves its transposition."""
-    fmap_in, cur_in = fmap, cur_fmap                          # the caller's own tensors: what a WarpCarry is keyed on
     disp = _f32c("disp", disp)
     fmap = _f32c("fmap", fmap)
     if disp.dim() != 4 or disp.shape[1] != 1:
@@ -107,7 +117,7 @@ def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, pe
     out_mask = torch.empty_like(disp)
     out_cost = torch.empty_like(disp) if cur_fmap is not None else None
     fmap_t = None
-    if carry_in is not None and carry_in.matches(fmap_in) and tuple(carry_in.rows.shape) == (B * H * W, C):
+    if carry_in is not None and carry_in.matches(fmap) and tuple(carry_in.rows.shape) == (B * H * W, C):
         fmap_t = carry_in.rows
         deterministic = True                                  # the list formulation is the one that reads rows
     cur_t = None
@@ -129,8 +139,7 @@ def warp_with_cost(disp, fmap, relative_T, K, K_inv, baseline, cur_fmap=None, pe
                   scratch.data_ptr(),
                   B, C, H, W, (1 if per_sample_mean else 0) | (2 if deterministic else 0), _stream())
     if carry_out is not None:
-        carry_out.tensor = cur_in
-        carry_out.version = cur_in._version
+        carry_out.record(cur_fmap)                            # the fp32 contiguous tensor the kernel read
     return out_disp, out_fmap, out_mask, out_cost
 
 
@@ -208,8 +217,17 @@ def warp_hidden_states(net_list, backward_grid):
 
 
 def cal_relative_transformation(T1, T2):
-    """ref: geo_utils.py:148-155.  T2 @ inv(T1) for world2cam poses.  4x4 bookkeeping, stays in torch."""
-    return torch.matmul(T2, torch.linalg.inv(T1))
+    """ref: geo_utils.py:148-155.  T2 @ inv(T1) for world2cam poses [B,4,4] (or [4,4]), one launch, no host sync
+    (torch.linalg.inv reads its LU `info` back on the host: two syncs per temporal frame in tc_stereo.py:127,159)."""
+    single = T1.dim() == 2
+    a = _f32c("T1", T1.reshape(-1, 4, 4))
+    b = _f32c("T2", T2.reshape(-1, 4, 4))
+    if a.shape != b.shape or tuple(a.shape[1:]) != (4, 4):
+        raise ValueError("T1 and T2 must both be [B,4,4], got %s and %s" % (tuple(T1.shape), tuple(T2.shape)))
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.call("tcs_relative_pose", a.data_ptr(), b.data_ptr(), out.data_ptr(), a.shape[0], _stream())
+    return out[0] if single else out
 
 
 # ---- "next" row (SURVEY.md section 8f rank 2): the per-GRU-iteration 3x3 stencils on the disparity ------------------

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libtcs_b200.so does not export %s" % n
     assert sorted(tcs_b200._lib.SIGNATURES) == names, "ctypes signatures and header disagree"
-    assert lib.tcs_abi_version() == tcs_b200._lib.ABI_VERSION == 2
+    assert lib.tcs_abi_version() == tcs_b200._lib.ABI_VERSION == 3
 
 
 def test_argument_errors_are_reported_without_a_gpu():
@@ -112,12 +112,12 @@ def test_dropin_rebinds_and_restores_names():
     import tcs_b200
     fake = types.ModuleType("core.tc_stereo")
     sentinel = object()
-    for n in ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler"):
+    for n in ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler", "cal_relative_transformation"):
         setattr(fake, n, sentinel)
     new = tcs_b200.install(fake, precision="bf16")
     assert fake.warp is tcs_b200.warp and fake.get_backward_grid is tcs_b200.get_backward_grid
     assert issubclass(fake.CorrBlock1D, tcs_b200.CorrBlock1D) and fake.CorrBlock1D.__name__ == "CorrBlock1D"
-    assert set(new) == {"CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler"}
+    assert set(new) == {"CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler", "cal_relative_transformation"}
     tcs_b200.uninstall(fake)
     assert fake.warp is sentinel and fake.CorrBlock1D is sentinel
     with pytest.raises(AttributeError):
@@ -127,7 +127,7 @@ def test_dropin_rebinds_and_restores_names():
 def test_dropin_patches_motion_encoder():
     import tcs_b200
     tcs_mod = types.ModuleType("core.tc_stereo")
-    for n in ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler"):
+    for n in ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler", "cal_relative_transformation"):
         setattr(tcs_mod, n, object())
     upd = types.ModuleType("core.update")
 
@@ -146,7 +146,7 @@ def test_dropin_patches_motion_encoder():
 def test_dropin_patches_the_iteration_stencils():
     import tcs_b200
     tcs_mod = types.ModuleType("core.tc_stereo")
-    for n in ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler"):
+    for n in ("CorrBlock1D", "warp", "get_backward_grid", "bilinear_sampler", "cal_relative_transformation"):
         setattr(tcs_mod, n, object())
     orig_grad = tcs_mod.disp2disp_gradient_xy = lambda disp: "gradient"
     upd = types.ModuleType("core.update")
@@ -175,16 +175,18 @@ def test_dropin_patches_the_iteration_stencils():
     assert DispRefine.propagate_disparity is orig_prop and TCStereo.upsample_flow is orig_up
 
 
-def test_warp_carry_is_keyed_on_the_tensor_and_its_version():
-    """The carried transposition may only be used for the very tensor it was made from, unmodified (host logic only)."""
+def test_warp_carry_is_keyed_on_the_storage_and_its_version():
+    """The carried transposition may only be used for the very memory it was made from, unmodified (host logic only);
+    the model hands the tensor back as `fmap1.detach()` (tc_stereo.py:227,242): a new object, same storage and version."""
     import tcs_b200
     c = tcs_b200.WarpCarry()
     f = torch.zeros(1, 8, 2, 4)
     assert not c.matches(f)                                  # empty
     c.reserve(f)
     assert tuple(c.rows.shape) == (8, 8) and not c.matches(f)   # reserved, nothing recorded yet
-    c.tensor, c.version = f, f._version
-    assert c.matches(f)
+    c.record(f)
+    assert c.matches(f) and c.matches(f.detach()) and c.matches(f.view(1, 8, 2, 4))
+    assert not c.matches(f[:, :4]) and not c.matches(f.view(1, 4, 4, 4))   # same pointer, another shape
     assert not c.matches(f.clone())                          # another tensor with the same contents
     f.add_(1.0)                                              # modified in place: the rows are stale
     assert not c.matches(f)
@@ -229,7 +231,7 @@ def test_bench_reference_arm_contract():
     """`bench.py --impl reference` prints ONE JSON line with the contract's keys (CPU port of the path)."""
     import json
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--height", "128", "--width", "192", "--iters", "2"], capture_output=True, text=True, timeout=600)
+                        "--height", "128", "--width", "192", "--iters", "2", "--seqs-per-gpu", "2"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -237,7 +239,9 @@ def test_bench_reference_arm_contract():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["product_so_loaded"] == [], "the reference arm must not load the product library"
+    assert d["config"]["seqs_per_gpu"] == 2                      # same batch per step as the B200 arm's --seqs-per-gpu
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 

@@ -1,0 +1,302 @@
+"""The UNMODIFIED reference model (baseline/_ref: core/tc_stereo.py TCStereo.forward and everything it imports) on the
+B200, with and without `tcs_b200.install()` — SURVEY.md section 8d(ii) and north_star's end-to-end gate.
+
+The reference side runs its own PyTorch code on the GPU, including its own soft-splat CUDA kernel string compiled
+with NVRTC (oracle/cupy_shim.py stands in for the five cupy names softsplat.py uses).  Random-init weights, synthetic
+images U(0,255), synthetic poses (no datasets or checkpoints exist offline).
+
+Gates
+  * the reference's splat kernel pins the oracle's restatement of it (row a8): same non-zero pattern, floats within
+    1e-5 rel + 1e-6 abs (its own atomics are unordered);
+  * on identical temporal state the warp's masks are bit-exact against the reference's warp() on the GPU;
+  * end-to-end drift after 32 iterations: mean |d flow_q| (1/4 res) and mean |d flow| (full res) against the reference
+    on the same GPU, reported next to the fp32-reordering noise floor measured in the same run (the reference with
+    N(0, 1e-7) added to its own volume).  The random-init network amplifies any perturbation ~5x per 8
+    iterations, so the gate is drift <= max(1e-3 px, 3 x floor).
+Numbers are written to gpurun_out/real_model.json for profiles/.
+"""
+import contextlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, assert_close, assert_exact
+from oracle import ref_model
+from oracle import tcs_oracle as orc
+
+pytestmark = pytest.mark.gpu
+ITERS = 32
+REPORT = {}
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_model.load()
+
+
+@pytest.fixture(scope="module")
+def tcs():
+    import tcs_b200
+    return tcs_b200
+
+
+@pytest.fixture(scope="module")
+def model(ref):
+    return ref_model.make_model("cuda")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def write_report():
+    yield
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "real_model.json"), "w") as f:
+            json.dump(REPORT, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@contextlib.contextmanager
+def installed(tcs, ref, **kw):
+    update = ref.update if (kw.get("fuse_motion_encoder") or kw.get("stencils")) else None
+    if kw.get("fuse_motion_encoder"):
+        kw["fuse_motion_encoder"] = ref.update
+    if kw.get("stencils"):
+        kw["stencils"] = ref.update
+    tcs.install(ref.tc_stereo, **kw)
+    try:
+        yield
+    finally:
+        tcs.uninstall(ref.tc_stereo, update)
+
+
+@contextlib.contextmanager
+def volume_noise(ref, sigma=1e-7, seed=99):
+    """The reference with N(0, sigma) added to its own correlation volume: what a bit-different but correct fp32
+    summation order does to the output (the floor any re-implementation sits on)."""
+    cls = ref.corr.CorrBlock1D
+    orig = cls.__dict__["corr"]
+    g = torch.Generator(device="cuda").manual_seed(seed)
+
+    def noisy(fmap1, fmap2):
+        c = orig.__func__(fmap1, fmap2)
+        return c + sigma * torch.randn(c.shape, device=c.device, generator=g)
+
+    cls.corr = staticmethod(noisy)
+    try:
+        yield
+    finally:
+        cls.corr = orig
+
+
+def drift(a, b):
+    return {"flow_q": (a["flow_q"] - b["flow_q"]).abs().mean().item(), "flow": (a["flow"] - b["flow"]).abs().mean().item()}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a8: the reference's own splat kernel pins the oracle and the kernels
+# ---------------------------------------------------------------------------------------------------------
+
+def test_reference_splat_kernel_pins_oracle(ref):
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 2, 19, 23, 31
+    ten_in = torch.randn(B, C, H, W, generator=g)
+    flow = torch.randn(B, 2, H, W, generator=g) * 4
+    flow[0, 0, 3, 4] = float("nan")                   # skipped sources (softsplat.py:300-301)
+    flow[1, 1, 7, 9] = float("inf")
+    flow[0, :, 0, 0] = torch.tensor([-40.0, 2.0])     # all four corners out of range
+    flow[1, :, 5, 5] = torch.tensor([2.0, -3.0])      # exact integers: three zero weights
+    got = host(ref.softsplat.softsplat_func.apply(ten_in.cuda(), flow.cuda()))
+    xs = torch.arange(W, dtype=torch.float32).view(1, 1, W)
+    ys = torch.arange(H, dtype=torch.float32).view(1, H, 1)
+    want = orc.softsplat_scatter(ten_in.numpy(), (xs + flow[:, 0]).numpy(), (ys + flow[:, 1]).numpy())
+    assert_exact(got != 0, want != 0, what="non-zero pattern of the reference's splat kernel vs the oracle")
+    assert_close(got, want, rtol=1e-5, atol=1e-6, what="reference splat kernel vs oracle restatement")
+
+
+def _camera(B, H, W, device):
+    K = torch.zeros(B, 3, 3)
+    K[:, 0, 0] = K[:, 1, 1] = 0.5 * W
+    K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = 0.5 * W - 0.5, 0.5 * H - 0.5, 1.0
+    Kinv = torch.linalg.inv(K.double()).float()
+    T = []
+    for b in range(B):
+        yaw = np.deg2rad(0.6 + 0.3 * b)
+        c, s = np.cos(yaw), np.sin(yaw)
+        cam2world = np.array([[c, 0, s, 0.02 * (b + 1)], [0, 1, 0, 0.01], [-s, 0, c, 0.12 + 0.05 * b], [0, 0, 0, 1.0]])
+        T.append(torch.from_numpy(np.linalg.inv(cam2world)).float())
+    T = torch.stack(T)
+    return K.to(device), Kinv.contiguous().to(device), T.contiguous().to(device), torch.full((B, 1), 0.25, device=device)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 136, 240), (1, 120, 160), (1, 96, 312)])
+def test_warp_against_reference_kernel_full_size(ref, tcs, B, H, W):
+    """tcs_warp_forward (atomic scatter and deterministic lists) against the reference's warp() running its own
+    geometry ops and splat kernel on the same GPU.  Masks bit-exact.  Floats: both sides compute the target
+    coordinates in fp32 but torch's batched matmul on the GPU (cuBLAS) need not round like the kernel's FMA chain, and
+    a bilinear weight (x - floor x) moves by one ulp(x) ~ 1.5e-5 at x ~ 200, so the float gate here is 5e-5 rel +
+    5e-5 abs on O(1) features; the bit-identical-geometry comparison at 1e-5 is test_gpu_parity.py::test_warp_full_size."""
+    g = torch.Generator().manual_seed(7 + H)
+    C = 256
+    disp = (0.5 + torch.rand(B, 1, H, W, generator=g) * (W / 16)).cuda()
+    disp.view(-1)[::41] = 0.0
+    fmap = torch.randn(B, C, H, W, generator=g).cuda()
+    K, Kinv, T, base = _camera(B, H, W, "cuda")
+    rd, rf, rm = ref.geo.warp(disp, fmap, T, K, Kinv, base)
+    rd2, rf2, rm2 = ref.geo.warp(disp, fmap, T, K, Kinv, base)          # the reference against itself: its own atomics noise
+    self_noise = (rf - rf2).abs().max().item()
+    for det in (False, True):
+        d, f, m, _ = tcs.warp_with_cost(disp, fmap, T, K, Kinv, base, deterministic=det)
+        assert_exact(host(m), host(rm), what="splat mask (deterministic=%s)" % det)
+        assert_close(host(d), host(rd), rtol=5e-5, atol=5e-5, what="warped disparity (deterministic=%s)" % det)
+        assert_close(host(f), host(rf), rtol=5e-5, atol=5e-5, what="warped features (deterministic=%s)" % det)
+        REPORT["warp_vs_reference_kernel_%dx%d_det%d" % (H, W, det)] = {
+            "max_abs_fmap": (f - rf).abs().max().item(), "max_abs_disp": (d - rd).abs().max().item(),
+            "reference_vs_itself_max_abs_fmap": self_noise, "mask_density": rm.mean().item()}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the real model
+# ---------------------------------------------------------------------------------------------------------
+
+CONFIGS = {
+    "dropin": {},
+    "dropin_fused": {"fuse_cost": True, "fuse_motion_encoder": True, "stencils": True},
+    "dropin_fp32": {"precision": "fp32"},
+}
+
+
+def test_real_model_temporal_frame_on_identical_state(ref, tcs, model):
+    """Frame 0 by the reference; frame 1 by the reference and by every drop-in configuration from the SAME state:
+    the warp's integer/mask outputs must be bit-exact, the flows within the drift gate."""
+    imgs, K, poses, base = ref_model.synthetic_sequence(2, 480, 640, device="cuda")
+    with torch.no_grad():
+        o0 = model(imgs[0][0], imgs[0][1], iters=ITERS, test_mode=True)
+        params = {"K": K, "T": poses[1], "previous_T": poses[0], "last_disp": o0["flow_q"], "last_net_list": o0["net_list"],
+                  "fmap1": o0["fmap1"], "baseline": base}
+        run = lambda: model(imgs[1][0], imgs[1][1], iters=ITERS, test_mode=True, params=dict(params))
+        r1 = run()
+        with volume_noise(ref):
+            floor = drift(run(), r1)
+        rerun = drift(run(), r1)
+        # the warp on the model's own state (tiny disparities with many exact zeros: the clip(disp, 1e-3) branch)
+        Ks = K * torch.tensor([0.25, 0.25, 1]).view(1, 3, 1).cuda()
+        Ksi = torch.linalg.inv(Ks)
+        relT = ref.geo.cal_relative_transformation(poses[0], poses[1])
+        rd, rf, rm = ref.geo.warp(-o0["flow_q"], o0["fmap1"], relT, Ks, Ksi, base)
+        for det in (False, True):
+            d, f, m, _ = tcs.warp_with_cost(-o0["flow_q"], o0["fmap1"], relT, Ks, Ksi, base, deterministic=det)
+            assert_exact(host(m), host(rm), what="splat mask on model state (deterministic=%s)" % det)
+            assert_close(host(d), host(rd), rtol=5e-5, atol=5e-5, what="warped disparity on model state")
+        assert_close(host(tcs.cal_relative_transformation(poses[0], poses[1])), host(relT), rtol=1e-6, atol=1e-7, what="relative pose")
+        rep = {"floor_noise_1e-7": floor, "reference_rerun": rerun, "mask_density": rm.mean().item()}
+        for name, kw in CONFIGS.items():
+            with installed(tcs, ref, **kw):
+                rep[name] = drift(run(), r1)
+    REPORT["frame1_480x640_identical_state"] = rep
+    print("\nframe 1 (480x640, %d iters) drift vs reference-on-GPU:" % ITERS, json.dumps(rep))
+    for name in CONFIGS:
+        for k in ("flow_q", "flow"):
+            assert rep[name][k] <= max(1e-3, 3 * floor[k]), "%s %s drift %.3g vs floor %.3g" % (name, k, rep[name][k], floor[k])
+
+
+def test_real_model_sequence_drift(ref, tcs, model):
+    """BASELINE config 2 in small: a 3-frame 480x640 temporal sequence, 32 iterations, each arm carrying its own state
+    (evaluate_stereo.py:170-197).  The fused configuration must take the list/carry path from the second warp on."""
+    from tcs_b200 import dropin
+    imgs, K, poses, base = ref_model.synthetic_sequence(3, 480, 640, device="cuda")
+    want = ref_model.run_sequence(model, imgs, K, poses, base, ITERS)
+    with volume_noise(ref):
+        noisy = ref_model.run_sequence(model, imgs, K, poses, base, ITERS)
+    rep = {"floor_noise_1e-7": [drift(a, b) for a, b in zip(noisy, want)]}
+    for name, kw in CONFIGS.items():
+        fused0, carried0 = dropin._ctx.fused_calls, dropin._ctx.carried_calls
+        with installed(tcs, ref, **kw):
+            got = ref_model.run_sequence(model, imgs, K, poses, base, ITERS)
+        rep[name] = [drift(a, b) for a, b in zip(got, want)]
+        if kw.get("fuse_cost"):
+            assert dropin._ctx.fused_calls - fused0 == 2, "both temporal frames must take the fused cost path"
+            assert dropin._ctx.carried_calls - carried0 == 1, "the third frame's warp must read the carried transposition"
+    REPORT["sequence_3x480x640"] = rep
+    print("\n3-frame 480x640 sequence drift per frame:", json.dumps(rep))
+    for name in CONFIGS:
+        for t in range(3):
+            for k in ("flow_q", "flow"):
+                fl = max(f[k] for f in rep["floor_noise_1e-7"][:t + 1])
+                assert rep[name][t][k] <= max(1e-3, 3 * fl), "%s frame %d %s drift %.3g vs floor %.3g" % (name, t, k, rep[name][t][k], fl)
+
+
+def test_real_model_single_pair_540x960(ref, tcs, model):
+    """BASELINE config 1: one 540x960 pair (padded to 544x960 as evaluate_stereo.py:179 does), 32 iterations, first
+    frame (argmax initialisation).  fp32 build: argmax masks bit-exact; fp16x3 (default): a confidence threshold on
+    main - sub > 0.3 may flip where the two differ by an ulp, so it is counted and bounded."""
+    g = torch.Generator().manual_seed(4321)
+    im1 = (torch.rand(1, 3, 544, 960, generator=g) * 255).cuda()
+    im2 = (torch.rand(1, 3, 544, 960, generator=g) * 255).cuda()
+    seen = {}
+    orig = ref.corr.CorrBlock1D.argmax_disp
+
+    def spy(self):
+        out = orig(self)
+        seen["ref"] = [host(x) for x in out]
+        return out
+
+    with torch.no_grad():
+        ref.corr.CorrBlock1D.argmax_disp = spy
+        try:
+            want = model(im1, im2, iters=ITERS, test_mode=True)
+        finally:
+            ref.corr.CorrBlock1D.argmax_disp = orig
+        with volume_noise(ref):
+            floor = drift(model(im1, im2, iters=ITERS, test_mode=True), want)
+        rep = {"floor_noise_1e-7": floor}
+        for name, kw in CONFIGS.items():
+            with installed(tcs, ref, **kw):
+                blk_cls = ref.tc_stereo.CorrBlock1D
+                o_arg = blk_cls.argmax_disp
+
+                def spy2(self, *a, **k):
+                    out = o_arg(self, *a, **k)
+                    seen[name] = [host(x) for x in out]
+                    return out
+
+                blk_cls.argmax_disp = spy2
+                try:
+                    rep[name] = drift(model(im1, im2, iters=ITERS, test_mode=True), want)
+                finally:
+                    blk_cls.argmax_disp = o_arg
+            flips = int((seen[name][2] != seen["ref"][2]).sum())
+            rep[name]["argmax_mask_flips"] = flips
+            rep[name]["argmax_mask_density"] = float(seen["ref"][2].mean())
+            if kw.get("precision") == "fp32":
+                same = seen[name][2] == seen["ref"][2]
+                # the reference's volume on the GPU is cuBLAS SGEMM, the kernel's an FMA chain: a threshold test on their
+                # difference can flip on an ulp; everything else (indices where both agree on the mask) must be exact
+                assert flips <= 1e-4 * same.size, "fp32 argmax mask flips: %d" % flips
+                agree = same & (seen["ref"][2] != 0)
+                assert np.array_equal(seen[name][0][agree], seen["ref"][0][agree]), "argmax disparity differs where the masks agree"
+            else:
+                assert flips <= 1e-3 * seen["ref"][2].size
+    REPORT["pair_544x960"] = rep
+    print("\n544x960 pair (%d iters) drift vs reference-on-GPU:" % ITERS, json.dumps(rep))
+    for name in CONFIGS:
+        for k in ("flow_q", "flow"):
+            assert rep[name][k] <= max(1e-3, 3 * floor[k]), "%s %s drift %.3g vs floor %.3g" % (name, k, rep[name][k], floor[k])
+
+
+def test_dropin_refuses_training(ref, tcs):
+    """Gradients flow through corr / warp in the reference; the kernels have no backward, so the drop-in must refuse
+    rather than silently cut them."""
+    f = torch.randn(1, 64, 4, 32, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError, match="inference only"):
+        tcs.CorrBlock1D(f, f)
+    with torch.no_grad():
+        tcs.CorrBlock1D(f, f)

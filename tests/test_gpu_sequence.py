@@ -17,7 +17,7 @@ def test_fifty_frame_sequence_480x640():
     dev = torch.device("cuda")
     H, W = sequence.feature_shape(480, 640)
     assert (H, W) == (120, 160)
-    B, C, iters, frames = 1, 256, 3, 50
+    B, C, iters, frames = 1, 256, 32, 50                # BASELINE config 2: 32 GRU iterations, 128-channel hidden states
     check = {0, 1, 24, 49}
     g = torch.Generator().manual_seed(1234)
     runner = tcs_b200.HotPathRunner()
@@ -30,7 +30,7 @@ def test_fifty_frame_sequence_480x640():
         f1 = (base_f[..., t:t + W] + 0.05 * torch.randn(B, C, H, W, generator=g)).contiguous()
         f2 = torch.roll(f1, -4, dims=3) + 0.3 * torch.randn(B, C, H, W, generator=g)
         coords = xs - (2.0 + 6.0 * torch.rand(iters, B, 1, H, W, generator=g))
-        nets = [torch.tanh(torch.randn(B, 16, H >> i, W >> i, generator=g)) for i in range(3)]
+        nets = [torch.tanh(torch.randn(B, 128, H >> i, W >> i, generator=g)) for i in range(3)]
         T = torch.stack([sequence.synthetic_pose(t, s) for s in range(B)])
         kw = {}
         if prev_T is not None:
@@ -54,10 +54,10 @@ def test_fifty_frame_sequence_480x640():
                 Kn, Kin, bn = K.cpu().numpy(), K_inv.cpu().numpy(), baseline.cpu().numpy()
                 rd, rf, rm = orc.warp(st[0], st[1], fwd.numpy(), Kn, Kin, bn, per_sample_mean=True)
                 assert_exact(out["mask"].cpu().numpy(), rm, what="frame %d splat mask" % t)
-                assert_close(out["sparse_disp"].cpu().numpy(), rd, rtol=1e-4, atol=1e-4, what="frame %d warped disparity" % t)
+                assert_close(out["sparse_disp"].cpu().numpy(), rd, rtol=1e-5, atol=2e-6, what="frame %d warped disparity" % t)
                 grid = orc.backward_grid(out["sparse_disp"].cpu().numpy(), inv.numpy(), Kn, Kin, bn)
                 for a, r in zip(out["warped_net"], orc.warp_hidden_states(st[2], grid)):
-                    assert_close(a.cpu().numpy(), r, rtol=1e-4, atol=1e-4, what="frame %d hidden state" % t)
+                    assert_close(a.cpu().numpy(), r, rtol=1e-5, atol=2e-6, what="frame %d hidden state" % t)
         prev_T = T
 
 

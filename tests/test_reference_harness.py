@@ -1,0 +1,99 @@
+"""CPU-side checks of the harness that runs the UNMODIFIED reference beside the kernels (oracle/ref_model.py,
+oracle/cupy_shim.py, baseline/install_ref.py) and of the drop-in's deferred results.  No GPU needed: NVRTC compiles for
+sm_100 without a device."""
+import filecmp
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_model  # noqa: E402
+
+needs_ref = pytest.mark.skipif(ref_model.reference_root() is None, reason="reference not installed (baseline/install_ref.py)")
+
+
+@needs_ref
+def test_installed_reference_is_unmodified():
+    src = "/root/reference"
+    if not os.path.isdir(src):
+        pytest.skip("no reference checkout on this machine")
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import install_ref
+    dest = install_ref.install(src, quiet=True)
+    for rel in install_ref.FILES:
+        assert filecmp.cmp(os.path.join(src, rel), os.path.join(dest, rel), shallow=False), rel
+
+
+@needs_ref
+def test_reference_splat_kernel_compiles_through_the_cupy_shim():
+    """The reference's own preprocessing (softsplat.py:27-216) + NVRTC on its own kernel string, for sm_100."""
+    from oracle import cupy_shim
+    ref = ref_model.load()
+    ss = ref.softsplat
+    ss.objCudacache.setdefault("device", "NVIDIA B200")          # cuda_kernel() asks torch for the device name otherwise
+    text = open(os.path.join(ref.root, "core", "utils", "splatting", "softsplat.py")).read()
+    kernel = text.split("cuda_kernel('softsplat_out', '''")[1].split("''', {")[0]
+    t = torch.zeros(2, 258, 12, 16)
+    key = ss.cuda_kernel("softsplat_out", kernel, {"tenIn": t, "tenFlow": torch.zeros(2, 2, 12, 16), "tenOut": torch.zeros_like(t)})
+    src = ss.objCudacache[key]["strKernel"]
+    assert "atomicAdd" in src and "SIZE_" not in src and "VALUE_" not in src and "OFFSET_" not in src
+    cubin = cupy_shim.compile_source(src, ["-I /usr/local/cuda", "-I /usr/local/cuda/include"], arch="sm_100")
+    assert len(cubin) > 1000 and b"softsplat_out" in cubin
+
+
+@needs_ref
+def test_reference_model_runs_a_temporal_sequence_on_cpu():
+    ref = ref_model.load()
+    ref_model.use_cpu_splat(ref)
+    model = ref_model.make_model()
+    imgs, K, poses, base = ref_model.synthetic_sequence(2, 64, 96)
+    outs = ref_model.run_sequence(model, imgs, K, poses, base, iters=2)
+    assert outs[1]["flow"].shape == (1, 1, 64, 96) and torch.isfinite(outs[1]["flow"]).all()
+    # and the same frame through the reference's hot-path call sequence alone
+    f = outs[0]["fmap1"]
+    xs = torch.arange(24, dtype=torch.float32).view(1, 1, 1, 24)
+    coords = (xs - 2.0).expand(1, 1, 16, 24)[None].contiguous()
+    Ks = K * torch.tensor([0.25, 0.25, 1]).view(1, 3, 1)
+    rel = ref.geo.cal_relative_transformation(poses[0], poses[1])
+    out = ref_model.hot_path_frame(ref, f, f, coords, (-outs[0]["flow_q"], f, outs[0]["net_list"]), rel, torch.linalg.inv(rel), Ks,
+                                   torch.linalg.inv(Ks), base)
+    assert out["corr"].shape == (1, 36, 16, 24) and len(out["warped_net"]) == 3
+
+
+def test_fused_cost_marker_resolves_only_the_models_expression():
+    """dropin.LazyWarpedFmap (install(..., fuse_cost=True)): tc_stereo.py:139-140 resolves to the fused cost without
+    materialising; anything else sees the materialised tensor; a half-used marker refuses."""
+    from tcs_b200 import dropin
+    cost = torch.full((2, 1, 3, 4), 7.0)
+    f = torch.randn(2, 8, 3, 4)
+    calls = []
+
+    def mk():
+        return dropin.LazyWarpedFmap(cost, (2, 8, 3, 4), lambda: calls.append(1) or torch.ones(2, 8, 3, 4))
+
+    assert torch.sum(F.normalize(f, dim=1) * F.normalize(mk(), dim=1), dim=1, keepdim=True) is cost
+    assert torch.sum(F.normalize(mk(), dim=1) * F.normalize(f, dim=1), dim=1, keepdim=True) is cost
+    assert (F.normalize(mk(), dim=1) * F.normalize(f, dim=1)).sum(dim=1, keepdim=True) is cost
+    assert not calls
+    lz = mk()
+    assert lz.shape == (2, 8, 3, 4) and not calls
+    assert torch.equal(lz + 1, torch.full((2, 8, 3, 4), 2.0)) and len(calls) == 1
+    assert float(lz.mean()) == 1.0 and len(calls) == 1                 # materialised once
+    assert torch.equal(F.normalize(lz, dim=1), F.normalize(torch.ones(2, 8, 3, 4), dim=1))   # now an ordinary tensor
+    with pytest.raises(RuntimeError, match="139-140"):
+        torch.sum(F.normalize(mk(), dim=1))                             # not the model's expression
+    with pytest.raises(RuntimeError, match="139-140"):
+        F.normalize(mk(), dim=1) * torch.ones(2, 8, 3, 5)               # another shape
+
+
+def test_kernels_refuse_tensors_that_require_grad():
+    from tcs_b200 import corr, geo
+    t = torch.zeros(1, 8, 2, 16, requires_grad=True)
+    for check in (lambda: corr._check_fmap("fmap1", t), lambda: geo._f32c("disp", t)):
+        with pytest.raises((RuntimeError, TypeError)):                  # TypeError: CPU tensor is refused first
+            check()
