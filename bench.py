@@ -324,7 +324,7 @@ def run_reference_gpu(args):
 def gpu_reference_legs(args):
     """Both modes of the reference-on-GPU leg as subprocesses (the -O mode needs its own interpreter)."""
     res = {}
-    base = [os.path.join(ROOT, "bench.py"), "--impl", "reference-gpu", "--steps", "5", "--warmup", "2",
+    base = [os.path.join(ROOT, "bench.py"), "--impl", "reference-gpu", "--steps", "6", "--warmup", "2",
             "--seqs-per-gpu", str(args.seqs_per_gpu), "--height", str(args.height), "--width", str(args.width), "--iters", str(args.iters)]
     for name, flags in (("as_is", []), ("python_O", ["-O"])):
         try:

@@ -143,7 +143,8 @@ class LazyLookup(LazyTensorOps):
 
     def materialize(self):
         if self._value is None:
-            self._value = self.block(self.coords)
+            # the base class's lookup: a configured block's own __call__ is what returned this deferred object
+            self._value = CorrBlock1D.__call__(self.block, self.coords)
         return self._value
 
     def encode(self, conv, relu=True):

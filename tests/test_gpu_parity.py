@@ -643,3 +643,31 @@ def test_convex_upsample_golden_and_full_size(tcs):
         assert_close(host(out), ref, rtol=1e-5, atol=2e-5, what="upsample %dx%dx%dx%d f=%d" % (N, D, H, W, f))
     with pytest.raises(ValueError):
         tcs.convex_upsample(torch.zeros(1, 1, 4, 4, device="cuda"), torch.zeros(1, 9 * 9, 4, 4, device="cuda"), 3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a6: relative pose (geo_utils.py:148-155)
+# ---------------------------------------------------------------------------------------------------------
+
+def test_relative_pose_matches_torch(tcs):
+    """T2 @ inv(T1) in one launch with no host sync, against the reference's expression evaluated in fp64 (the yardstick)
+    and in fp32 on the GPU (what the reference runs): rigid world2cam poses, a general affine matrix that needs pivoting,
+    a single [4,4] pair."""
+    g = torch.Generator().manual_seed(3)
+    B = 5
+    T1 = torch.eye(4).repeat(B, 1, 1)
+    T2 = torch.eye(4).repeat(B, 1, 1)
+    for T in (T1, T2):
+        q, _ = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))
+        T[:, :3, :3] = q
+        T[:, :3, 3] = torch.randn(B, 3, generator=g) * 2
+    T1[4] = torch.tensor([[0.0, 2.0, 0.0, 1.0], [1.0, 0.0, 0.5, 0.0], [0.0, 0.0, 3.0, -1.0], [0.0, 0.0, 0.0, 1.0]])   # zero leading pivot
+    got = tcs.cal_relative_transformation(T1.cuda(), T2.cuda())
+    want64 = (T2.double() @ torch.linalg.inv(T1.double())).numpy()
+    assert_close(host(got), want64, rtol=1e-6, atol=1e-6, what="relative pose vs fp64")
+    want32 = torch.matmul(T2.cuda(), torch.linalg.inv(T1.cuda()))
+    assert_close(host(got), host(want32), rtol=1e-5, atol=2e-6, what="relative pose vs torch fp32 on the GPU")
+    one = tcs.cal_relative_transformation(T1[0].cuda(), T2[0].cuda())
+    assert one.shape == (4, 4) and torch.equal(one, got[0])
+    with pytest.raises(ValueError):
+        tcs.cal_relative_transformation(T1.cuda(), T2[:2].cuda())

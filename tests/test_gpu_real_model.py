@@ -48,6 +48,20 @@ def model(ref):
     return ref_model.make_model("cuda")
 
 
+@pytest.fixture(autouse=True)
+def fp32_convolutions():
+    """BASELINE config 1 is fp32.  cuDNN's default TF32 convolutions quantise their inputs to 10 mantissa bits, which
+    turns a 1e-7 perturbation into a 2^-11 jump whenever a value crosses a rounding boundary: measured on this model,
+    the reference then differs from ITSELF (two identical runs, its own atomic splat the only non-determinism) by 0.18 px
+    after 32 iterations, and every drift number drowns in that.  With true fp32 convolutions the floor is the fp32
+    re-ordering floor SURVEY.md section 0 measured on the CPU."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 @pytest.fixture(scope="module", autouse=True)
 def write_report():
     yield
@@ -97,6 +111,28 @@ def volume_noise(ref, sigma=1e-7, seed=99):
         cls.corr = orig
 
 
+@contextlib.contextmanager
+def reference_splat_on_gpu_for_cpu_tensors(ref):
+    """The reference's warp() on CPU tensors (torch CPU geometry: the arithmetic the oracle and the kernels reproduce
+    bit for bit) with its scatter still done by the reference's OWN CUDA kernel: what isolates the splat."""
+    ss = ref.softsplat.softsplat_func
+    orig = ss.apply
+
+    def apply(ten_in, ten_flow):
+        return ref._gpu_apply(ten_in.cuda(), ten_flow.cuda()).cpu()
+
+    ss.apply = staticmethod(apply)
+    try:
+        yield
+    finally:
+        ss.apply = orig
+
+
+def outlier_fraction(got, want, rtol, atol):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return float((np.abs(got - want) > atol + rtol * np.abs(want)).mean())
+
+
 def drift(a, b):
     return {"flow_q": (a["flow_q"] - b["flow_q"]).abs().mean().item(), "flow": (a["flow"] - b["flow"]).abs().mean().item()}
 
@@ -139,28 +175,40 @@ def _camera(B, H, W, device):
 
 @pytest.mark.parametrize("B,H,W", [(2, 136, 240), (1, 120, 160), (1, 96, 312)])
 def test_warp_against_reference_kernel_full_size(ref, tcs, B, H, W):
-    """tcs_warp_forward (atomic scatter and deterministic lists) against the reference's warp() running its own
-    geometry ops and splat kernel on the same GPU.  Masks bit-exact.  Floats: both sides compute the target
-    coordinates in fp32 but torch's batched matmul on the GPU (cuBLAS) need not round like the kernel's FMA chain, and
-    a bilinear weight (x - floor x) moves by one ulp(x) ~ 1.5e-5 at x ~ 200, so the float gate here is 5e-5 rel +
-    5e-5 abs on O(1) features; the bit-identical-geometry comparison at 1e-5 is test_gpu_parity.py::test_warp_full_size."""
+    """Row a8 at full size: tcs_warp_forward (atomic scatter and deterministic lists) against the reference's warp()
+    with its OWN CUDA splat kernel.
+
+    (i) Geometry by torch on the CPU (the arithmetic the kernels reproduce bit for bit), scatter by the reference's
+        kernel on the GPU: masks bit-exact, floats at north_star's fp32 gate 1e-5 rel (+ 2e-6 abs for cancellation in
+        sums of O(1) features).  What differs is only the order of the <= ~10 atomic adds per target and expf's last ulp.
+    (ii) Everything of the reference on the GPU: torch's batched matmul there (cuBLAS) does not round like an FMA chain,
+        so target coordinates move by an ulp, a bilinear weight (x - floor x) by ~1.5e-5, and a target whose whole
+        weight is of that size (i.i.d. random depths leave a few) changes arbitrarily - in the reference against itself
+        just as much.  Gate: mask flips <= 1e-3 of the pixels, >= 99 % of the floats within 1e-4."""
     g = torch.Generator().manual_seed(7 + H)
     C = 256
-    disp = (0.5 + torch.rand(B, 1, H, W, generator=g) * (W / 16)).cuda()
+    disp = 0.5 + torch.rand(B, 1, H, W, generator=g) * (W / 16)
     disp.view(-1)[::41] = 0.0
-    fmap = torch.randn(B, C, H, W, generator=g).cuda()
-    K, Kinv, T, base = _camera(B, H, W, "cuda")
-    rd, rf, rm = ref.geo.warp(disp, fmap, T, K, Kinv, base)
-    rd2, rf2, rm2 = ref.geo.warp(disp, fmap, T, K, Kinv, base)          # the reference against itself: its own atomics noise
-    self_noise = (rf - rf2).abs().max().item()
+    fmap = torch.randn(B, C, H, W, generator=g)
+    K, Kinv, T, base = _camera(B, H, W, "cpu")
+    with reference_splat_on_gpu_for_cpu_tensors(ref):
+        rd, rf, rm = ref.geo.warp(disp, fmap, T, K, Kinv, base)
+    gd, gf, gm = ref.geo.warp(disp.cuda(), fmap.cuda(), T.cuda(), K.cuda(), Kinv.cuda(), base.cuda())
     for det in (False, True):
-        d, f, m, _ = tcs.warp_with_cost(disp, fmap, T, K, Kinv, base, deterministic=det)
+        d, f, m, _ = tcs.warp_with_cost(disp.cuda(), fmap.cuda(), T.cuda(), K.cuda(), Kinv.cuda(), base.cuda(), deterministic=det)
         assert_exact(host(m), host(rm), what="splat mask (deterministic=%s)" % det)
-        assert_close(host(d), host(rd), rtol=5e-5, atol=5e-5, what="warped disparity (deterministic=%s)" % det)
-        assert_close(host(f), host(rf), rtol=5e-5, atol=5e-5, what="warped features (deterministic=%s)" % det)
+        assert_close(host(d), host(rd), rtol=1e-5, atol=2e-6, what="warped disparity (deterministic=%s)" % det)
+        assert_close(host(f), host(rf), rtol=1e-5, atol=2e-6, what="warped features (deterministic=%s)" % det)
+        flips = float((m != gm).float().mean().item())
+        out_d = outlier_fraction(host(d), host(gd), 1e-4, 1e-4)
+        out_f = outlier_fraction(host(f), host(gf), 1e-4, 1e-4)
+        assert flips <= 1e-3 and out_d <= 1e-2 and out_f <= 1e-2, (flips, out_d, out_f)
         REPORT["warp_vs_reference_kernel_%dx%d_det%d" % (H, W, det)] = {
-            "max_abs_fmap": (f - rf).abs().max().item(), "max_abs_disp": (d - rd).abs().max().item(),
-            "reference_vs_itself_max_abs_fmap": self_noise, "mask_density": rm.mean().item()}
+            "cpu_geometry_gpu_reference_splat": {"max_abs_fmap": (f.cpu() - rf).abs().max().item(), "max_abs_disp": (d.cpu() - rd).abs().max().item(),
+                                                 "mask_mismatches": 0},
+            "all_reference_on_gpu": {"mask_flip_fraction": flips, "disp_outlier_fraction_1e-4": out_d, "fmap_outlier_fraction_1e-4": out_f,
+                                     "reference_gpu_vs_reference_cpu_geometry_disp_outliers": outlier_fraction(host(gd), host(rd), 1e-4, 1e-4)},
+            "mask_density": rm.mean().item()}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -191,12 +239,18 @@ def test_real_model_temporal_frame_on_identical_state(ref, tcs, model):
         Ks = K * torch.tensor([0.25, 0.25, 1]).view(1, 3, 1).cuda()
         Ksi = torch.linalg.inv(Ks)
         relT = ref.geo.cal_relative_transformation(poses[0], poses[1])
-        rd, rf, rm = ref.geo.warp(-o0["flow_q"], o0["fmap1"], relT, Ks, Ksi, base)
+        with reference_splat_on_gpu_for_cpu_tensors(ref):       # torch-CPU geometry + the reference's own CUDA splat kernel
+            rd, rf, rm = ref.geo.warp(-o0["flow_q"].cpu(), o0["fmap1"].cpu(), relT.cpu(), Ks.cpu(), Ksi.cpu(), base.cpu())
+        gd, gf, gm = ref.geo.warp(-o0["flow_q"], o0["fmap1"], relT, Ks, Ksi, base)
         for det in (False, True):
             d, f, m, _ = tcs.warp_with_cost(-o0["flow_q"], o0["fmap1"], relT, Ks, Ksi, base, deterministic=det)
             assert_exact(host(m), host(rm), what="splat mask on model state (deterministic=%s)" % det)
-            assert_close(host(d), host(rd), rtol=5e-5, atol=5e-5, what="warped disparity on model state")
-        assert_close(host(tcs.cal_relative_transformation(poses[0], poses[1])), host(relT), rtol=1e-6, atol=1e-7, what="relative pose")
+            assert_close(host(d), host(rd), rtol=1e-5, atol=2e-6, what="warped disparity on model state")
+            assert float((m != gm).float().mean().item()) <= 1e-3           # cuBLAS-rounded geometry: an ulp can flip a target
+        # a6: the relative pose, one launch and no host sync against torch.linalg.inv + matmul
+        assert_close(host(tcs.cal_relative_transformation(poses[0], poses[1])), host(relT), rtol=1e-5, atol=1e-6, what="relative pose")
+        assert_close(host(tcs.cal_relative_transformation(poses[1], poses[0])), host(ref.geo.cal_relative_transformation(poses[1], poses[0])),
+                     rtol=1e-5, atol=1e-6, what="inverse relative pose")
         rep = {"floor_noise_1e-7": floor, "reference_rerun": rerun, "mask_density": rm.mean().item()}
         for name, kw in CONFIGS.items():
             with installed(tcs, ref, **kw):
@@ -208,30 +262,38 @@ def test_real_model_temporal_frame_on_identical_state(ref, tcs, model):
             assert rep[name][k] <= max(1e-3, 3 * floor[k]), "%s %s drift %.3g vs floor %.3g" % (name, k, rep[name][k], floor[k])
 
 
-def test_real_model_sequence_drift(ref, tcs, model):
-    """BASELINE config 2 in small: a 3-frame 480x640 temporal sequence, 32 iterations, each arm carrying its own state
-    (evaluate_stereo.py:170-197).  The fused configuration must take the list/carry path from the second warp on."""
+@pytest.mark.parametrize("iters", [8, ITERS])
+def test_real_model_sequence_drift(ref, tcs, model, iters):
+    """BASELINE config 2 in small: a 3-frame 480x640 temporal sequence, each arm carrying its own state
+    (evaluate_stereo.py:170-197).  The fused configuration must take the list/carry path from the second warp on.
+    With random-init weights the recurrent state is expansive: at 32 iterations the reference's own disparities reach
+    1e9 px by the second frame (its own noise floor is then of that size too), so beyond frame 0 the 32-iteration run is
+    gated only against the floor measured in the same run (x10: two chaotic trajectories) and on staying finite; the
+    8-iteration run keeps every frame in a sane range and carries the 3 x floor gate on all three frames."""
     from tcs_b200 import dropin
     imgs, K, poses, base = ref_model.synthetic_sequence(3, 480, 640, device="cuda")
-    want = ref_model.run_sequence(model, imgs, K, poses, base, ITERS)
+    want = ref_model.run_sequence(model, imgs, K, poses, base, iters)
     with volume_noise(ref):
-        noisy = ref_model.run_sequence(model, imgs, K, poses, base, ITERS)
-    rep = {"floor_noise_1e-7": [drift(a, b) for a, b in zip(noisy, want)]}
+        noisy = ref_model.run_sequence(model, imgs, K, poses, base, iters)
+    rep = {"floor_noise_1e-7": [drift(a, b) for a, b in zip(noisy, want)],
+           "reference_mean_abs_flow": [o["flow"].abs().mean().item() for o in want]}
     for name, kw in CONFIGS.items():
         fused0, carried0 = dropin._ctx.fused_calls, dropin._ctx.carried_calls
         with installed(tcs, ref, **kw):
-            got = ref_model.run_sequence(model, imgs, K, poses, base, ITERS)
+            got = ref_model.run_sequence(model, imgs, K, poses, base, iters)
         rep[name] = [drift(a, b) for a, b in zip(got, want)]
+        assert all(torch.isfinite(o["flow"]).all() for o in got)
         if kw.get("fuse_cost"):
             assert dropin._ctx.fused_calls - fused0 == 2, "both temporal frames must take the fused cost path"
             assert dropin._ctx.carried_calls - carried0 == 1, "the third frame's warp must read the carried transposition"
-    REPORT["sequence_3x480x640"] = rep
-    print("\n3-frame 480x640 sequence drift per frame:", json.dumps(rep))
+    REPORT["sequence_3x480x640_%diters" % iters] = rep
+    print("\n3-frame 480x640 sequence, %d iters, drift per frame:" % iters, json.dumps(rep))
     for name in CONFIGS:
         for t in range(3):
             for k in ("flow_q", "flow"):
                 fl = max(f[k] for f in rep["floor_noise_1e-7"][:t + 1])
-                assert rep[name][t][k] <= max(1e-3, 3 * fl), "%s frame %d %s drift %.3g vs floor %.3g" % (name, t, k, rep[name][t][k], fl)
+                factor = 3 if (iters <= 8 or t == 0) else 10
+                assert rep[name][t][k] <= max(1e-3, factor * fl), "%s frame %d %s drift %.3g vs floor %.3g" % (name, t, k, rep[name][t][k], fl)
 
 
 def test_real_model_single_pair_540x960(ref, tcs, model):
