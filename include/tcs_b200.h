@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCS_ABI_VERSION 3
+#define TCS_ABI_VERSION 4
 
 /* argument errors (negative); CUDA launch errors are returned as positive cudaError_t values */
 #define TCS_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported combination */
@@ -129,6 +129,16 @@ int tcs_corr_lookup_alt(const float* a_n32,
                         const float* b0_n32, const float* b1_n32, const float* b2_n32, const float* b3_n32,
                         const float* coords, long long coords_bstride, float* out,
                         int B, int H, int W1, int W2, int C, int num_levels, int radius, void* stream);
+
+/* The same on the tensor cores (tcgen05 + TMEM + TMA), 4 levels, radius 4: per 128-pixel tile the band of the row's
+ * correlation block that the tile's coordinates can touch is built into TMEM from the 16-bit operands of
+ * tcs_corr_prepass and the 36 taps are sampled in the epilogue; nothing of the volume is written.  Bit-identical to
+ * tcs_corr_build (same precision) + tcs_corr_lookup.  Contract: ref core/corr.py:33-52.
+ *   a_hi,a_lo [B,H,W1,C], b_hi,b_lo [B,H,W2,C] operands (lo nullable unless prec is *X3); out [B,36,H,W1].
+ * Requires C % 64 == 0, W2 >= 16. */
+int tcs_corr_lookup_alt_tc(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                           const float* coords, long long coords_bstride, float* out,
+                           int B, int H, int W1, int W2, int C, int prec, void* stream);
 
 /* ---- first-frame initialisation ------------------------------------------------------------------ */
 

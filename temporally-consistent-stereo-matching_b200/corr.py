@@ -193,16 +193,24 @@ class CorrBlock1D:
             self._fmaps = None
         else:
             self._flat, self._levels = None, None
-            _, _, self._a32 = normalized_operands(fmap1, want_hi=False, want_n32=True)
-            _, _, b32 = normalized_operands(fmap2, want_hi=False, want_n32=True)
-            self._b32 = [b32]
-            with torch.cuda.device(self.device):
-                for l in range(1, num_levels):
-                    prev = self._b32[-1]
-                    nxt = torch.empty((self.B, self.H, prev.shape[2] // 2, self.C), dtype=torch.float32, device=self.device)
-                    _lib.call("tcs_fmap_pool_w", prev.data_ptr(), nxt.data_ptr(), self.B, self.H, prev.shape[2], self.C, _stream())
-                    self._b32.append(nxt)
             self._fmaps = (fmap1, fmap2)   # argmax_disp / get_cost_volume need level 0 on demand
+            # tensor-core formulation (4 levels, radius 4): the 16-bit operands once per frame, the band of each row's
+            # block rebuilt in TMEM by every call; anything else: dot products at the taps on the CUDA cores
+            self._alt_tc = (num_levels == 4 and radius == 4 and self.C % 64 == 0 and self.W2 >= 16
+                            and self.precision in _lib.PRECISIONS and os.environ.get("TCS_B200_ALT_TC", "1") != "0")
+            if self._alt_tc:
+                self._a_hi, self._a_lo, _ = normalized_operands(fmap1, self.precision)
+                self._b_hi, self._b_lo, _ = normalized_operands(fmap2, self.precision)
+            else:
+                _, _, self._a32 = normalized_operands(fmap1, want_hi=False, want_n32=True)
+                _, _, b32 = normalized_operands(fmap2, want_hi=False, want_n32=True)
+                self._b32 = [b32]
+                with torch.cuda.device(self.device):
+                    for l in range(1, num_levels):
+                        prev = self._b32[-1]
+                        nxt = torch.empty((self.B, self.H, prev.shape[2] // 2, self.C), dtype=torch.float32, device=self.device)
+                        _lib.call("tcs_fmap_pool_w", prev.data_ptr(), nxt.data_ptr(), self.B, self.H, prev.shape[2], self.C, _stream())
+                        self._b32.append(nxt)
 
     @classmethod
     def from_levels(cls, levels, radius=4):
@@ -251,6 +259,10 @@ class CorrBlock1D:
                 ptrs = [self._levels[l].data_ptr() if l < self.num_levels else None for l in range(4)]
                 _lib.call("tcs_corr_lookup", *ptrs, cptr, cstride, out.data_ptr(),
                           self.B, self.H, self.W1, self.W2, self.num_levels, self.radius, _stream())
+            elif self._alt_tc:
+                _lib.call("tcs_corr_lookup_alt_tc", self._a_hi.data_ptr(), self._a_lo.data_ptr() if self._a_lo is not None else None,
+                          self._b_hi.data_ptr(), self._b_lo.data_ptr() if self._b_lo is not None else None, cptr, cstride,
+                          out.data_ptr(), self.B, self.H, self.W1, self.W2, self.C, _lib.PRECISIONS[self.precision], _stream())
             else:
                 ptrs = [self._b32[l].data_ptr() if l < self.num_levels else None for l in range(4)]
                 _lib.call("tcs_corr_lookup_alt", self._a32.data_ptr(), *ptrs, cptr, cstride, out.data_ptr(),

@@ -112,10 +112,12 @@ def hot_path_frame(fmap1, fmap2, coords_seq, state=None, disp_init=None, rel_T=N
             "corr_fn": corr_fn}
 
 
-def launches_per_frame(iters, first_frame, hidden_levels=3, mode="pyramid", num_levels=4, fused_build=True, warp_lists=False):
+def launches_per_frame(iters, first_frame, hidden_levels=3, mode="pyramid", num_levels=4, fused_build=True, warp_lists=False,
+                       alt_tc=True):
     """Number of libtcs_b200 kernel launches hot_path_frame issues (memset nodes not counted).  warp_lists: the warp
     runs its list formulation on a carried transposition (a HotPathRunner's frames after the second)."""
-    n = (1 if fused_build else 3) if mode == "pyramid" else 2 + (num_levels - 1)   # fused build | prepass x2 + build | prepass x2 + pools
+    # fused build | prepass x2 + build | alternate: prepass x2 (tensor-core lookups) or prepass x2 + pools (CUDA-core lookups)
+    n = (1 if fused_build else 3) if mode == "pyramid" else (2 if alt_tc else 2 + (num_levels - 1))
     if first_frame:
         n += 1 if mode == "pyramid" else 2                         # argmax (+ an on-demand level-0 build)
         if mode != "pyramid":

@@ -304,6 +304,58 @@ def test_alternate_equals_pyramid(tcs, B, H, W):
     assert_close(host(a), host(p), rtol=1e-5, atol=2e-6, what="alternate vs pyramid")
 
 
+@pytest.mark.parametrize("B,H,W1,W2", [(1, 136, 240, 240), (2, 9, 312, 312), (1, 7, 480, 480), (1, 5, 78, 78), (1, 6, 200, 72), (1, 3, 130, 300)])
+@pytest.mark.parametrize("precision", ["fp16x3", "bf16"])
+def test_alternate_tensor_core_is_bit_identical_to_the_pyramid_path(tcs, B, H, W1, W2, precision):
+    """tcs_corr_lookup_alt_tc builds each tile's band with the MMA sequence of tcs_corr_build and pools / samples with the
+    expressions of its epilogue and of tcs_corr_lookup, so the two paths agree BIT FOR BIT — for coordinates spread over
+    a quarter of the width (bands wider than 256 columns: several chunks per tile), out-of-range, exact-integer and
+    non-finite ones, odd level widths, W1 != W2 and partial M tiles."""
+    g = torch.Generator().manual_seed(W1 + W2)
+    f1 = torch.randn(B, 256, H, W1, generator=g).cuda()
+    f2 = torch.randn(B, 256, H, W2, generator=g).cuda()
+    coords = make_coords(B, H, W1, 11)
+    coords.view(-1)[5] = float("nan")
+    coords.view(-1)[17] = float("inf")
+    coords = coords.cuda()
+    alt = tcs.CorrBlock1D(f1, f2, mode="alternate", precision=precision)
+    assert alt._alt_tc and alt._levels is None
+    _, levels = tcs.build_pyramid(f1, f2, 4, precision, fused=False)
+    pyr = tcs.CorrBlock1D.from_levels(levels)
+    a, p = alt(coords), pyr(coords)
+    assert_exact(host(a), host(p), what="tensor-core alternate vs pyramid (%s)" % precision)
+    smooth = (torch.arange(W1, dtype=torch.float32).view(1, 1, 1, W1) - 3.25).expand(B, 1, H, W1).contiguous().cuda()
+    assert_exact(host(alt(smooth)), host(pyr(smooth)), what="constant disparity: one chunk per tile")
+    far = torch.full((B, 1, H, W1), -1000.0).cuda()
+    assert float(alt(far).abs().max()) == 0.0                      # no tile touches the row: zero chunks, zero output
+
+
+def test_alternate_tensor_core_full_size_1080p(tcs):
+    """BASELINE config 5's shape (1088x1920 -> 272x480): against the pyramid path bit for bit on the whole frame, and
+    against the oracle's fp64 volume on a band of rows (the oracle takes ~1 s per 10 rows at this width)."""
+    B, H, W = 1, 272, 480
+    f1, f2 = make_fmaps(B, 256, H, W, 31, shift=11)
+    coords = make_coords(B, H, W, 13)
+    alt = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), mode="alternate")
+    pyr = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), mode="pyramid")           # two-step build at this width
+    a = alt(coords.cuda())
+    assert_exact(host(a), host(pyr(coords.cuda())), what="1080p alternate vs pyramid")
+    rows = slice(100, 124)
+    vol = orc.corr_volume(f1[:, :, rows].numpy(), f2[:, :, rows].numpy(), np.float64)
+    want = orc.corr_lookup(orc.corr_pyramid(vol.astype(np.float32), 4), coords[:, :, rows].numpy(), 4)
+    assert_close(host(a)[:, :, rows], want, rtol=1e-5, atol=2e-6, what="1080p alternate vs oracle")
+
+
+def test_alternate_cuda_core_fallback_still_matches(tcs):
+    """Radius != 4 (or TCS_B200_ALT_TC=0) keeps the dot-per-tap kernel."""
+    f1, f2 = make_fmaps(1, 128, 6, 64, 3)
+    coords = make_coords(1, 6, 64, 4).cuda()
+    alt = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), mode="alternate", radius=3)
+    assert not alt._alt_tc
+    pyr = tcs.CorrBlock1D(f1.cuda(), f2.cuda(), mode="pyramid", precision="fp32", radius=3)
+    assert_close(host(alt(coords)), host(pyr(coords)), rtol=1e-5, atol=2e-6, what="CUDA-core alternate, radius 3")
+
+
 # ---------------------------------------------------------------------------------------------------------
 # first frame: argmax_disp, cost volume
 # ---------------------------------------------------------------------------------------------------------
