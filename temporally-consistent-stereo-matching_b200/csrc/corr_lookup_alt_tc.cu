@@ -7,10 +7,12 @@
 // the union of the rows' level-3 windows, which contain the windows of every finer level — is built into TMEM exactly
 // as the correlation build does it (TMA-fed K-major 16-bit operands, tcgen05.mma kind::f16, fp32 accumulators, the
 // hi/lo split precisions as three passes), and the 4 x 9 taps are sampled in the epilogue.  The volume never exists:
-//   warp 0      TMA producer: [128 x 64] A boxes and [256 | 64 x 64] B boxes (SWIZZLE_128B), 4-stage ring
+//   warp 0      TMA producer: per 32-channel K block the [128 x 32] A and [256 | 64 x 32] B boxes of the hi and lo operands
+//               (SWIZZLE_64B) into one stage of a 4-stage ring
 //   warp 1      MMA issuer: UMMA 128 x N x 16 with N = the band width (multiple of 16, <= 256 per chunk; a band wider
 //               than 256 columns is covered by several chunks whose tap contributions add), two accumulator stages
-//   warps 2..5  epilogue, one per TMEM lane quarter: thread = one pixel.  tcgen05.ld 32 columns at a time (only the
+//   warps 2..9  epilogue, two per TMEM lane quarter (even / odd 32-column blocks; afterwards two levels' taps each):
+//               thread = one pixel.  tcgen05.ld 32 columns at a time (only the
 //               blocks the warp's own pixels can touch), avg-pool cascade (a+b)*0.5 along w2 in registers (the
 //               expression of corr.py:21-23 and of the build epilogue, so the levels are bit-identical to the pyramid's),
 //               each value is dropped into the pixel's private 12-entry window of its level in shared memory when it
@@ -31,23 +33,26 @@ namespace tcs {
 namespace alt {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;
+constexpr int kBlockK = 32;                          // 32 x 16 bit = 64 B: one SWIZZLE_64B row
 constexpr int kUmmaK = 16;
 constexpr int kMaxN = 256;
 constexpr int kSmallN = 64;
 constexpr int kStages = 4;
-constexpr int kABytes = kBlockM * kBlockK * 2;       // 16 KB
-constexpr int kBBytes = kMaxN * kBlockK * 2;         // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;       // 48 KB
+constexpr int kABytes = kBlockM * kBlockK * 2;       // 8 KB
+constexpr int kBBytes = kMaxN * kBlockK * 2;         // 16 KB
+// one stage = one K block of ALL operands (A hi, A lo, B hi, B lo): the three passes of the split precisions read them
+// from shared memory instead of fetching the hi parts twice (a third less L2 -> shared traffic than a stage per pass)
+constexpr int kOffAlo = kABytes, kOffBhi = 2 * kABytes, kOffBlo = 2 * kABytes + kBBytes;
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // 48 KB
 constexpr int kAccStages = 2;
 constexpr int kAccCols = 256;
 constexpr int kTmemCols = kAccStages * kAccCols;     // 512
-constexpr int kEpiWarps = 4;
-constexpr int kThreads = 64 + 32 * kEpiWarps;        // 192
+constexpr int kEpiWarps = 8;                         // two per TMEM lane quarter: even / odd 32-column blocks, then two levels each
+constexpr int kThreads = 64 + 32 * kEpiWarps;        // 320
 constexpr int kWinEntries = 12;                      // per level: entries f_l - 5 .. f_l + 6
-constexpr int kWinBytes = 4 * kWinEntries * 32 * 4;  // per epilogue warp: [4 levels][12][32 lanes] fp32 = 6 KB
+constexpr int kWinBytes = 4 * kWinEntries * 32 * 4;  // per lane quarter: [4 levels][12][32 pixels] fp32 = 6 KB
 constexpr int kBarrierBytes = 256;
-constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiWarps * kWinBytes + kBarrierBytes;
+constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 4 * kWinBytes + kBarrierBytes;
 
 struct Params {
     const float* coords;
@@ -74,11 +79,19 @@ __device__ __forceinline__ int level_floor(float c, int l, int Wl) {
     return (int)fminf(fmaxf(floorf(cl), -16.0f), (float)(Wl + 16));
 }
 
-// Level-0 column range a pixel can touch (its level-3 window), or an empty range when every tap is zero padding.
+// Level-0 column range a pixel can touch (its level-3 window, which contains the windows of the finer levels), or an
+// empty range when every tap is zero padding.  grid_sample's normalise / un-normalise round trip moves a tap by less
+// than 2e-4 px on levels up to 1024 wide, so unless the fractional part of coords/8 comes within 2^-9 of 0 or 1 the
+// level-3 taps' floors are f3 - 4 .. f3 + 4 and the entries f3 - 4 .. f3 + 5 suffice (80 columns); otherwise one more
+// entry on that side may be read (96 columns).  80 instead of 96 is what lets a 128-pixel tile with up to ~40 px of
+// disparity spread fit ONE 256-column chunk.
 __device__ __forceinline__ void pixel_range(float c, int W2, int& lo, int& hi) {
-    const int f3 = level_floor(c, 3, W2 >> 3);
-    lo = 8 * (f3 - 5);
-    hi = 8 * (f3 + 7);
+    const float c3 = c * 0.125f;
+    const float fl = floorf(c3), frac = c3 - fl;
+    const int f3 = (int)fminf(fmaxf(fl, -16.0f), (float)((W2 >> 3) + 16));
+    const bool wide = W2 > 8192;
+    lo = 8 * (f3 - ((wide || !(frac >= 1.0f / 512.0f)) ? 5 : 4));
+    hi = 8 * (f3 + ((wide || !(frac <= 1.0f - 1.0f / 512.0f)) ? 7 : 6));
     if (hi <= 0 || lo >= W2) { lo = INT_MAX; hi = INT_MIN; }
 }
 
@@ -126,7 +139,7 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* win_base = smem + kStages * kStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(win_base + kEpiWarps * kWinBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(win_base + 4 * kWinBytes);
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * kStages;
     const uint32_t bar_tfull = bar_empty + 8 * kStages;
@@ -162,7 +175,6 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const int steps_per_chunk = p.kblocks * p.passes;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -176,19 +188,20 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
                 for (int k = 0; k < bd.nchunks; ++k) {
                     const int n = chunk_cols(bd, k);
                     const bool small = n <= kSmallN;
-                    const uint32_t tx = kABytes + (small ? kSmallN : kMaxN) * (kBlockK * 2);
+                    const uint32_t tx = (kABytes + (small ? kSmallN : kMaxN) * (kBlockK * 2)) * (p.passes == 3 ? 2 : 1);
                     const int col0 = bd.lo + kMaxN * k;
                     for (int kb = 0; kb < p.kblocks; ++kb) {
-                        for (int pass = 0; pass < p.passes; ++pass) {
-                            ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                            const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-                            const uint32_t full = bar_full + 8 * stage;
-                            ptx::mbar_arrive_expect_tx(full, tx);
-                            ptx::tma_load_3d(sa, pass == 2 ? &tm_a_lo : &tm_a_hi, full, kb * kBlockK, m_t * kBlockM, bh);
-                            const CUtensorMap* tb = small ? (pass == 1 ? &tm_bs_lo : &tm_bs_hi) : (pass == 1 ? &tm_b_lo : &tm_b_hi);
-                            ptx::tma_load_3d(sa + kABytes, tb, full, kb * kBlockK, col0, bh);
-                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                        const uint32_t full = bar_full + 8 * stage;
+                        ptx::mbar_arrive_expect_tx(full, tx);
+                        ptx::tma_load_3d(sa, &tm_a_hi, full, kb * kBlockK, m_t * kBlockM, bh);
+                        ptx::tma_load_3d(sa + kOffBhi, small ? &tm_bs_hi : &tm_b_hi, full, kb * kBlockK, col0, bh);
+                        if (p.passes == 3) {
+                            ptx::tma_load_3d(sa + kOffAlo, &tm_a_lo, full, kb * kBlockK, m_t * kBlockM, bh);
+                            ptx::tma_load_3d(sa + kOffBlo, small ? &tm_bs_lo : &tm_b_lo, full, kb * kBlockK, col0, bh);
                         }
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -211,17 +224,19 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
                     ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                     ptx::tc_fence_after_sync();
                     const uint32_t tmem_d = tmem_base + acc * kAccCols;
-                    for (int s = 0; s < steps_per_chunk; ++s) {
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
                         ptx::mbar_wait(bar_full + 8 * stage, phase);
                         ptx::tc_fence_after_sync();
                         const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-                        const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
-                        const uint64_t db = ptx::make_kmajor_sw128_desc(sa + kABytes);
+                        for (int pass = 0; pass < p.passes; ++pass) {      // hi*hi, hi*lo, lo*hi: the order of tcs_corr_build
+                            const uint64_t da = ptx::make_kmajor_sw64_desc(sa + (pass == 2 ? kOffAlo : 0));
+                            const uint64_t db = ptx::make_kmajor_sw64_desc(sa + (pass == 1 ? kOffBlo : kOffBhi));
 #pragma unroll
-                        for (int kk = 0; kk < kBlockK / kUmmaK; ++kk)
-                            ptx::umma_f16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (s | kk) != 0 ? 1u : 0u);
+                            for (int kk = 0; kk < kBlockK / kUmmaK; ++kk)
+                                ptx::umma_f16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | pass | kk) != 0 ? 1u : 0u);
+                        }
                         ptx::umma_commit(bar_empty + 8 * stage);
-                        if (s == steps_per_chunk - 1) ptx::umma_commit(bar_tfull + 8 * acc);
+                        if (kb == p.kblocks - 1) ptx::umma_commit(bar_tfull + 8 * acc);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -232,9 +247,10 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
         }
     } else {
         // ================= epilogue: thread = pixel =================
-        const int ew = warp - 2;
         const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
-        const uint32_t win = smem_u32(win_base + ew * kWinBytes) + 4u * lane;   // entry (l, i): win + 128 * (12 l + i)
+        const int half = (warp - 2) >> 2;                     // which of the quarter's two warps: block parity, then level pair
+        const uint32_t win = smem_u32(win_base + quarter * kWinBytes) + 4u * lane;   // entry (l, i): win + 128 * (12 l + i)
+        const uint32_t pair_bar = 1 + quarter;                // named barrier of the quarter's two warps
         const int W2 = p.W2;
         int iter = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -261,7 +277,7 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
                 ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 ptx::tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols;
-                for (int blk = 0; blk < nblk; ++blk) {
+                for (int blk = half; blk < nblk; blk += 2) {
                     const int cg = col0 + 32 * blk;           // first level-0 column of the block (multiple of 8)
                     if (!__any_sync(0xffffffffu, my_lo < cg + 32 && my_hi > cg)) continue;   // nobody here touches it
                     float v[32];
@@ -320,11 +336,13 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
                 ptx::mbar_arrive(bar_tempty + 8 * acc);
             }
 
-            // ---- the 36 taps from the pixel's own windows (its shared-memory column: no other thread touches it)
+            // ---- the taps from the pixel's windows, filled by both warps of the quarter: this warp takes two levels
+            asm volatile("bar.sync %0, 64;" :: "r"(pair_bar) : "memory");
             if (in_row) {
-                float* o = p.out + ((long long)b * 36) * p.HW + (long long)h * p.W1 + row;
+                float* o = p.out + ((long long)b * 36 + 18 * half) * p.HW + (long long)h * p.W1 + row;
 #pragma unroll
-                for (int l = 0; l < 4; ++l) {
+                for (int ll = 0; ll < 2; ++ll) {
+                    const int l = 2 * half + ll;
                     const int Wl = W2 >> l;
                     const float wm1 = (float)(Wl - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
                     const float cl = c0 * (1.0f / (float)(1 << l));            // coords / 2^l (exact), corr.py:43
@@ -349,6 +367,7 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
                     }
                 }
             }
+            asm volatile("bar.sync %0, 64;" :: "r"(pair_bar) : "memory");   // the partner is done reading before the next tile's values land
         }
     }
 
@@ -361,7 +380,7 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
     }
 }
 
-// Operand [BH, W, C] 16-bit, channels contiguous; box = [1, box_w, 64], 128 B swizzle, zero fill outside.
+// Operand [BH, W, C] 16-bit, channels contiguous; box = [1, box_w, 32], 64 B swizzle, zero fill outside.
 static int make_operand_map(CUtensorMap* tm, const void* base, int BH, int W, int C, int box_w, bool fp16) {
     EncodeTiledFn enc = get_encode_fn();
     TCS_REQUIRE(enc != nullptr, TCS_E_DRIVER, "tcs_corr_lookup_alt_tc: cuTensorMapEncodeTiled not available from the driver");
@@ -371,7 +390,7 @@ static int make_operand_map(CUtensorMap* tm, const void* base, int BH, int W, in
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TCS_REQUIRE(r == CUDA_SUCCESS, TCS_E_DRIVER, "tcs_corr_lookup_alt_tc: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return 0;
 }
@@ -392,7 +411,7 @@ extern "C" int tcs_corr_lookup_alt_tc(const void* a_hi, const void* a_lo, const 
     TCS_REQUIRE(!x3 || (a_lo != nullptr && b_lo != nullptr), TCS_E_BADARG, "tcs_corr_lookup_alt_tc: the X3 modes need the lo operands");
     TCS_REQUIRE(B > 0 && H > 0 && W1 > 0 && C > 0, TCS_E_BADARG, "tcs_corr_lookup_alt_tc: bad sizes");
     TCS_REQUIRE(W2 >= 16, TCS_E_SHAPE, "tcs_corr_lookup_alt_tc: W2=%d must be >= 16 (4 levels, each at least 2 wide)", W2);
-    TCS_REQUIRE(C % kBlockK == 0, TCS_E_SHAPE, "tcs_corr_lookup_alt_tc: C=%d must be a multiple of 64", C);
+    TCS_REQUIRE(C % kBlockK == 0, TCS_E_SHAPE, "tcs_corr_lookup_alt_tc: C=%d must be a multiple of 32", C);
     TCS_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo), TCS_E_ALIGN,
                 "tcs_corr_lookup_alt_tc: operands must be 16-byte aligned");
     TCS_REQUIRE((long long)B * H <= 0x7fffffffLL / 1024, TCS_E_SHAPE, "tcs_corr_lookup_alt_tc: B*H too large");

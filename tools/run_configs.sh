@@ -3,7 +3,7 @@
 set -u
 out=gpurun_out/configs_r02.jsonl
 : > $out
-run() { echo "== $*" >&2; python bench.py --steps 10 --warmup 3 --skip-cpu "$@" 2>/dev/null | tail -1 >> $out; }
+run() { echo "== $*" >&2; python bench.py --steps 10 --warmup 3 --skip-cpu --skip-gpu-reference "$@" 2>/dev/null | tail -1 >> $out; }
 run --height 540 --width 960 --seqs-per-gpu 8
 run --height 540 --width 960 --seqs-per-gpu 1 --skip-e2e
 run --height 480 --width 640 --seqs-per-gpu 8
