@@ -553,6 +553,20 @@ def run_b200(args):
                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": lookup_bytes / (lookup_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["source"], "launches_per_step": iters,
                 "algorithmic_bytes_per_launch": lookup_bytes}
+    if args.mode == "alternate":
+        # alternate mode: the dominant kernel is the tensor-core on-the-fly lookup.  Algorithmic work: per pixel and
+        # call 4 levels x 10 distinct taps x a 256-long dot product = 20.5 kFLOP; the kernel issues the whole band of the row block
+        # (128 x ~256 x 256 MACs per tile and pass) to get them, which is what `executed_tflops_estimate` counts for a 256-column band
+        passes = 3 if args.precision.endswith("x3") else 1
+        alg_flops = npix * LEVELS * 10 * 2.0 * C
+        exe_flops = 2.0 * npix * min(W, 256) * C * passes
+        operand_bytes = 2.0 * npix * C * 2 * (2 if passes == 3 else 1)
+        roofline = {"kernel": "corr_lookup_alt_tc_kernel", "bound": "tensor", "achieved": alg_flops / (lookup_ms * 1e-3) / 1e12,
+                    "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": alg_flops / (lookup_ms * 1e-3) / 1e12 / pk["bf16_tflops"],
+                    "traffic": None, "peak_source": pk["source"], "launches_per_step": iters, "algorithmic_flops_per_launch": alg_flops,
+                    "executed_tflops_estimate": exe_flops / (lookup_ms * 1e-3) / 1e12,
+                    "operand_stream_gbs": operand_bytes / (lookup_ms * 1e-3) / 1e9,
+                    "note": "each call re-streams the 16-bit operands from HBM (operand_stream_gbs) and rebuilds every tile's band in TMEM"}
     build_flops = 2.0 * npix * W * C
     build_bytes = 2 * npix * C * 4 + npix * W * 4 * (1 + 0.5 + 0.25 + 0.125)
     warp_bytes = npix * (4 + 1024 + 1024 + 4 + 4 + 4 + 1344)   # disp + prev fmap + cur fmap in; disp', mask, cost out; hidden gather

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCS_ABI_VERSION 4
+#define TCS_ABI_VERSION 5
 
 /* argument errors (negative); CUDA launch errors are returned as positive cudaError_t values */
 #define TCS_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported combination */
@@ -60,6 +60,12 @@ const char* tcs_last_error(void);
  * prec selects bf16 vs fp16 rounding.  Requires C % 64 == 0, C <= 512. */
 int tcs_corr_prepass(const float* fmap, void* hi, void* lo, float* n32,
                      int B, int C, int H, int W, int prec, void* stream);
+
+/* The same 16-bit operands K-BLOCK-MAJOR, [B,H,C/64,W,64]: every 64-channel block of an image row is one contiguous
+ * run of 128-byte pixel rows, so the TMA boxes of tcs_corr_lookup_alt_tc are whole contiguous lines.
+ * ref: core/corr.py:58-59.  Same requirements as tcs_corr_prepass. */
+int tcs_corr_prepass_kblocked(const float* fmap, void* hi, void* lo,
+                              int B, int C, int H, int W, int prec, void* stream);
 
 /* All-pairs 1-D correlation of one frame, all pyramid levels in one pass (tcgen05 + TMEM + TMA).
  * ref: core/corr.py:54-62 (CorrBlock1D.corr: einsum 'aijk,aijh->ajkh') and core/corr.py:15-23
@@ -134,7 +140,8 @@ int tcs_corr_lookup_alt(const float* a_n32,
  * correlation block that the tile's coordinates can touch is built into TMEM from the 16-bit operands of
  * tcs_corr_prepass and the 36 taps are sampled in the epilogue; nothing of the volume is written.  Bit-identical to
  * tcs_corr_build (same precision) + tcs_corr_lookup.  Contract: ref core/corr.py:33-52.
- *   a_hi,a_lo [B,H,W1,C], b_hi,b_lo [B,H,W2,C] operands (lo nullable unless prec is *X3); out [B,36,H,W1].
+ *   a_hi,a_lo [B,H,C/64,W1,64], b_hi,b_lo [B,H,C/64,W2,64] K-block-major operands of tcs_corr_prepass_kblocked
+ *   (lo nullable unless prec is *X3); out [B,36,H,W1].
  * Requires C % 64 == 0, W2 >= 16. */
 int tcs_corr_lookup_alt_tc(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                            const float* coords, long long coords_bstride, float* out,

@@ -40,22 +40,30 @@ def _pad16(n_floats):
     return (n_floats + 3) & ~3
 
 
-def normalized_operands(fmap, precision="bf16x3", want_hi=True, want_lo=None, want_n32=False):
+def normalized_operands(fmap, precision="bf16x3", want_hi=True, want_lo=None, want_n32=False, kblocked=False):
     """L2-normalise [B,C,H,W] fp32 features over C and re-lay them out channels-last (ref: corr.py:58-59).
 
     Returns (hi, lo, n32): 16-bit [B,H,W,C] operands of the tensor-core build (lo only for the x3 modes)
-    and/or the fp32 normalised features."""
+    and/or the fp32 normalised features.  kblocked: the 16-bit operands K-block-major, [B,H,C/64,W,64] (what the
+    tensor-core alternate lookup streams)."""
     fmap = _check_fmap("fmap", fmap)
     B, C, H, W = fmap.shape
     fp16 = precision in ("fp16", "fp16x3")
     if want_lo is None:
         want_lo = precision in ("bf16x3", "fp16x3")
     dt = torch.float16 if fp16 else torch.bfloat16
-    hi = torch.empty((B, H, W, C), dtype=dt, device=fmap.device) if want_hi else None
-    lo = torch.empty((B, H, W, C), dtype=dt, device=fmap.device) if (want_hi and want_lo) else None
+    shape = (B, H, C // 64, W, 64) if kblocked else (B, H, W, C)
+    hi = torch.empty(shape, dtype=dt, device=fmap.device) if want_hi else None
+    lo = torch.empty(shape, dtype=dt, device=fmap.device) if (want_hi and want_lo) else None
     n32 = torch.empty((B, H, W, C), dtype=torch.float32, device=fmap.device) if want_n32 else None
     prec = _lib.PRECISIONS["fp16" if fp16 else "bf16"]
     with torch.cuda.device(fmap.device):
+        if kblocked:
+            if want_n32 or not want_hi:
+                raise ValueError("kblocked operands are the 16-bit ones")
+            _lib.call("tcs_corr_prepass_kblocked", fmap.data_ptr(), hi.data_ptr(), lo.data_ptr() if lo is not None else None,
+                      B, C, H, W, prec, _stream())
+            return hi, lo, None
         _lib.call("tcs_corr_prepass", fmap.data_ptr(), hi.data_ptr() if hi is not None else None,
                   lo.data_ptr() if lo is not None else None, n32.data_ptr() if n32 is not None else None,
                   B, C, H, W, prec, _stream())
@@ -199,8 +207,8 @@ class CorrBlock1D:
             self._alt_tc = (num_levels == 4 and radius == 4 and self.C % 64 == 0 and self.W2 >= 16
                             and self.precision in _lib.PRECISIONS and os.environ.get("TCS_B200_ALT_TC", "1") != "0")
             if self._alt_tc:
-                self._a_hi, self._a_lo, _ = normalized_operands(fmap1, self.precision)
-                self._b_hi, self._b_lo, _ = normalized_operands(fmap2, self.precision)
+                self._a_hi, self._a_lo, _ = normalized_operands(fmap1, self.precision, kblocked=True)
+                self._b_hi, self._b_lo, _ = normalized_operands(fmap2, self.precision, kblocked=True)
             else:
                 _, _, self._a32 = normalized_operands(fmap1, want_hi=False, want_n32=True)
                 _, _, b32 = normalized_operands(fmap2, want_hi=False, want_n32=True)

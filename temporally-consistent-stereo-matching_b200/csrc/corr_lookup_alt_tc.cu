@@ -7,8 +7,8 @@
 // the union of the rows' level-3 windows, which contain the windows of every finer level — is built into TMEM exactly
 // as the correlation build does it (TMA-fed K-major 16-bit operands, tcgen05.mma kind::f16, fp32 accumulators, the
 // hi/lo split precisions as three passes), and the 4 x 9 taps are sampled in the epilogue.  The volume never exists:
-//   warp 0      TMA producer: per 32-channel K block the [128 x 32] A and [256 | 64 x 32] B boxes of the hi and lo operands
-//               (SWIZZLE_64B) into one stage of a 4-stage ring
+//   warp 0      TMA producer: per 64-channel K block the [128 x 64] A and [256 | 64 x 64] B boxes (SWIZZLE_128B, contiguous
+//               in the K-block-major operands) of the hi part, then of the lo part, each into one slot of a 4-slot ring
 //   warp 1      MMA issuer: UMMA 128 x N x 16 with N = the band width (multiple of 16, <= 256 per chunk; a band wider
 //               than 256 columns is covered by several chunks whose tap contributions add), two accumulator stages
 //   warps 2..9  epilogue, two per TMEM lane quarter (even / odd 32-column blocks; afterwards two levels' taps each):
@@ -28,22 +28,26 @@
 #include "tma_host.cuh"
 
 #include <climits>
+#include <cstdlib>
 
 namespace tcs {
 namespace alt {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 32;                          // 32 x 16 bit = 64 B: one SWIZZLE_64B row
+constexpr int kBlockK = 64;                          // 64 x 16 bit = 128 B: one SWIZZLE_128B row = one L2 line
 constexpr int kUmmaK = 16;
 constexpr int kMaxN = 256;
 constexpr int kSmallN = 64;
 constexpr int kStages = 4;
-constexpr int kABytes = kBlockM * kBlockK * 2;       // 8 KB
-constexpr int kBBytes = kMaxN * kBlockK * 2;         // 16 KB
-// one stage = one K block of ALL operands (A hi, A lo, B hi, B lo): the three passes of the split precisions read them
-// from shared memory instead of fetching the hi parts twice (a third less L2 -> shared traffic than a stage per pass)
-constexpr int kOffAlo = kABytes, kOffBhi = 2 * kABytes, kOffBlo = 2 * kABytes + kBBytes;
-constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // 48 KB
+constexpr int kABytes = kBlockM * kBlockK * 2;       // 16 KB
+constexpr int kBBytes = kMaxN * kBlockK * 2;         // 32 KB
+// One ring slot = one K block of the A and B tiles of ONE operand part (hi or lo).  The split precisions take two
+// consecutive slots per K block (hi, then lo) and run hi*hi, hi*lo, lo*hi from them, so every part is fetched once
+// (a stage per pass fetches the hi parts twice: a third more L2 -> shared traffic).  The operands are K-BLOCK-MAJOR,
+// [B,H,C/64,W,64] (tcs_corr_prepass_kblocked), so that each box is one contiguous run of whole 128-byte lines; boxes
+// cut out of pixel-major [B,H,W,C] rows (128 B out of every 512) left this kernel waiting on TMA at 27 % tensor-pipe
+// activity with DRAM at 43 %.
+constexpr int kStageBytes = kABytes + kBBytes;       // 48 KB
 constexpr int kAccStages = 2;
 constexpr int kAccCols = 256;
 constexpr int kTmemCols = kAccStages * kAccCols;     // 512
@@ -60,10 +64,17 @@ struct Params {
     float* out;
     int H, W1, W2, HW;
     int num_m, total_tiles;
+    uint32_t num_m_mul, num_m_shr, H_mul, H_shr;   // tile -> (bh, m_t) and bh -> (b, h) without integer division
     int kblocks, passes;
     uint32_t ab_format;   // 0 fp16, 1 bf16
     float scale;
+    int debug;            // development aid (TCS_ALT_DEBUG): 1 = epilogue only waits and releases, 2 = no MMAs are issued
 };
+
+// n / d for 0 <= n < 2^31 as one multiply-high and a shift (Granlund & Montgomery; constants from fast_divisor()).
+__device__ __forceinline__ int fast_div(int n, int d, uint32_t mul, uint32_t shr) {
+    return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr);
+}
 
 struct Band {
     int lo;        // first level-0 column (multiple of 8, >= 0)
@@ -95,18 +106,32 @@ __device__ __forceinline__ void pixel_range(float c, int W2, int& lo, int& hi) {
     if (hi <= 0 || lo >= W2) { lo = INT_MAX; hi = INT_MIN; }
 }
 
-// Warp-collective: the band of the tile whose first row is m0 (rows m0 .. m0+127 of this image row).
-__device__ __forceinline__ Band tile_band(const float* __restrict__ crow, int m0, int W1, int W2, int lane) {
+// The coordinates of a tile's 128 pixels, 4 per lane (rows m0 + lane + 32 j; a far-away value for rows past W1).  Every
+// role loads them ONE TILE AHEAD (the loads are issued in program order and only waited for when first used), so the
+// global-memory latency of the band computation is off every role's per-tile critical path.
+struct TileCoords { float c[4]; };
+__device__ __forceinline__ void load_tile_coords(const Params& p, int tile, int lane, TileCoords& tc) {
+    const int bh = fast_div(tile, p.num_m, p.num_m_mul, p.num_m_shr);
+    const int m_t = tile - bh * p.num_m;
+    const int b = fast_div(bh, p.H, p.H_mul, p.H_shr), h = bh - b * p.H;
+    const float* crow = p.coords + (long long)b * p.coords_bstride + (long long)h * p.W1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int row = m_t * kBlockM + lane + 32 * j;
+        tc.c[j] = 1.0e9f;
+        if (row < p.W1) tc.c[j] = ldg_ordered_f1(crow + row);
+    }
+}
+
+// Warp-collective: the band of a tile from its coordinates.
+__device__ __forceinline__ Band tile_band(const TileCoords& tc, int W2) {
     int lo = INT_MAX, hi = INT_MIN;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int row = m0 + lane + 32 * j;
-        if (row < W1) {
-            int l, h;
-            pixel_range(sane_coord(__ldg(crow + row)), W2, l, h);
-            lo = min(lo, l);
-            hi = max(hi, h);
-        }
+        int l, h;
+        pixel_range(sane_coord(tc.c[j]), W2, l, h);
+        lo = min(lo, l);
+        hi = max(hi, h);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -131,6 +156,7 @@ __device__ __forceinline__ float sample_pos_fast(float xk, float wm1, float rc, 
     return __fmul_rn(__fadd_rn(xg, 1.0f), hwm1);
 }
 
+template <bool kX3>
 __global__ void __launch_bounds__(kThreads, 1)
 corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -153,7 +179,7 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
         ptx::prefetch_tensormap(&tm_a_hi);
         ptx::prefetch_tensormap(&tm_b_hi);
         ptx::prefetch_tensormap(&tm_bs_hi);
-        if (p.passes == 3) {
+        if (kX3) {
             ptx::prefetch_tensormap(&tm_a_lo);
             ptx::prefetch_tensormap(&tm_b_lo);
             ptx::prefetch_tensormap(&tm_bs_lo);
@@ -178,30 +204,38 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
 
     if (warp == 0) {
         // ================= TMA producer =================
+        // (single-thread loops: every instruction here is on the critical path of the ring, so the per-slot work is an
+        // address add, the barrier handshake and the two bulk-tensor issues)
         uint32_t stage = 0, phase = 0;
+        const uint32_t smem0 = smem_u32(smem);
+        TileCoords cur, nxt;
+        if ((int)blockIdx.x < p.total_tiles) load_tile_coords(p, blockIdx.x, lane, cur);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int m_t = tile % p.num_m;
-            const int bh = tile / p.num_m;
-            const int b = bh / p.H, h = bh - b * p.H;
-            const Band bd = tile_band(p.coords + (long long)b * p.coords_bstride + (long long)h * p.W1, m_t * kBlockM, p.W1, p.W2, lane);
+            const int bh = fast_div(tile, p.num_m, p.num_m_mul, p.num_m_shr);
+            const int m0 = (tile - bh * p.num_m) * kBlockM;
+            nxt = cur;
+            if (tile + (int)gridDim.x < p.total_tiles) load_tile_coords(p, tile + gridDim.x, lane, nxt);
+            const Band bd = tile_band(cur, p.W2);
+            cur = nxt;
             if (lane == 0) {
                 for (int k = 0; k < bd.nchunks; ++k) {
-                    const int n = chunk_cols(bd, k);
-                    const bool small = n <= kSmallN;
-                    const uint32_t tx = (kABytes + (small ? kSmallN : kMaxN) * (kBlockK * 2)) * (p.passes == 3 ? 2 : 1);
+                    const bool small = chunk_cols(bd, k) <= kSmallN;
+                    const uint32_t tx = kABytes + (small ? kSmallN : kMaxN) * (kBlockK * 2);
                     const int col0 = bd.lo + kMaxN * k;
+                    const CUtensorMap* tb_hi = small ? &tm_bs_hi : &tm_b_hi;
+                    const CUtensorMap* tb_lo = small ? &tm_bs_lo : &tm_b_lo;
                     for (int kb = 0; kb < p.kblocks; ++kb) {
-                        ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-                        const uint32_t full = bar_full + 8 * stage;
-                        ptx::mbar_arrive_expect_tx(full, tx);
-                        ptx::tma_load_3d(sa, &tm_a_hi, full, kb * kBlockK, m_t * kBlockM, bh);
-                        ptx::tma_load_3d(sa + kOffBhi, small ? &tm_bs_hi : &tm_b_hi, full, kb * kBlockK, col0, bh);
-                        if (p.passes == 3) {
-                            ptx::tma_load_3d(sa + kOffAlo, &tm_a_lo, full, kb * kBlockK, m_t * kBlockM, bh);
-                            ptx::tma_load_3d(sa + kOffBlo, small ? &tm_bs_lo : &tm_b_lo, full, kb * kBlockK, col0, bh);
+#pragma unroll
+                        for (int part = 0; part < (kX3 ? 2 : 1); ++part) {           // hi, then lo
+                            ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            const uint32_t sa = smem0 + stage * kStageBytes;
+                            const uint32_t full = bar_full + 8 * stage;
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            if (p.debug & 8) { ptx::mbar_arrive(full); continue; }
+                            ptx::mbar_arrive_expect_tx(full, tx);
+                            ptx::tma_load_4d(sa, part ? &tm_a_lo : &tm_a_hi, full, 0, m0, kb, bh);
+                            ptx::tma_load_4d(sa + kABytes, part ? tb_lo : tb_hi, full, 0, col0, kb, bh);
                         }
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -211,11 +245,16 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
         // ================= MMA issuer =================
         uint32_t stage = 0, phase = 0;
         int iter = 0;
+        // descriptor of slot 0's A tile; slot s is + s * (kStageBytes >> 4), its B tile + (kABytes >> 4) more (the start
+        // address field holds (addr & 0x3ffff) >> 4 and shared addresses stay below 256 KB, so the adds never carry out)
+        const uint64_t desc0 = ptx::make_kmajor_sw128_desc(smem_u32(smem));
+        TileCoords cur, nxt;
+        if ((int)blockIdx.x < p.total_tiles) load_tile_coords(p, blockIdx.x, lane, cur);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int m_t = tile % p.num_m;
-            const int bh = tile / p.num_m;
-            const int b = bh / p.H, h = bh - b * p.H;
-            const Band bd = tile_band(p.coords + (long long)b * p.coords_bstride + (long long)h * p.W1, m_t * kBlockM, p.W1, p.W2, lane);
+            nxt = cur;
+            if (tile + (int)gridDim.x < p.total_tiles) load_tile_coords(p, tile + gridDim.x, lane, nxt);
+            const Band bd = tile_band(cur, p.W2);
+            cur = nxt;
             if (lane == 0) {
                 for (int k = 0; k < bd.nchunks; ++k, ++iter) {
                     const uint32_t acc = iter & 1;
@@ -225,19 +264,37 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
                     ptx::tc_fence_after_sync();
                     const uint32_t tmem_d = tmem_base + acc * kAccCols;
                     for (int kb = 0; kb < p.kblocks; ++kb) {
-                        ptx::mbar_wait(bar_full + 8 * stage, phase);
-                        ptx::tc_fence_after_sync();
-                        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-                        for (int pass = 0; pass < p.passes; ++pass) {      // hi*hi, hi*lo, lo*hi: the order of tcs_corr_build
-                            const uint64_t da = ptx::make_kmajor_sw64_desc(sa + (pass == 2 ? kOffAlo : 0));
-                            const uint64_t db = ptx::make_kmajor_sw64_desc(sa + (pass == 1 ? kOffBlo : kOffBhi));
-#pragma unroll
-                            for (int kk = 0; kk < kBlockK / kUmmaK; ++kk)
-                                ptx::umma_f16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | pass | kk) != 0 ? 1u : 0u);
-                        }
-                        ptx::umma_commit(bar_empty + 8 * stage);
-                        if (kb == p.kblocks - 1) ptx::umma_commit(bar_tfull + 8 * acc);
+                        // slot of the hi part, and (split precisions) the next slot with the lo part
+                        const uint32_t s_hi = stage, ph_hi = phase;
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        uint32_t s_lo = s_hi, ph_lo = ph_hi;
+                        if (kX3) {
+                            s_lo = stage; ph_lo = phase;
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+                        const uint64_t a_hi = desc0 + (uint64_t)(s_hi * (kStageBytes >> 4)), b_hi = a_hi + (kABytes >> 4);
+                        const uint64_t a_lo = desc0 + (uint64_t)(s_lo * (kStageBytes >> 4)), b_lo = a_lo + (kABytes >> 4);
+                        const uint32_t first = kb != 0 ? 1u : 0u;          // the chunk's very first MMA overwrites the accumulator
+                        ptx::mbar_wait(bar_full + 8 * s_hi, ph_hi);
+                        ptx::tc_fence_after_sync();
+                        if (!(p.debug & 2)) {                               // hi*hi, hi*lo, lo*hi: the order of tcs_corr_build
+                            ptx::umma_f16(tmem_d, a_hi, b_hi, idesc, first);
+#pragma unroll
+                            for (int kk = 1; kk < kBlockK / kUmmaK; ++kk) ptx::umma_f16(tmem_d, a_hi + 2 * kk, b_hi + 2 * kk, idesc, 1u);
+                        }
+                        if (kX3) {
+                            ptx::mbar_wait(bar_full + 8 * s_lo, ph_lo);
+                            ptx::tc_fence_after_sync();
+                            if (!(p.debug & 2)) {
+#pragma unroll
+                                for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) ptx::umma_f16(tmem_d, a_hi + 2 * kk, b_lo + 2 * kk, idesc, 1u);
+#pragma unroll
+                                for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) ptx::umma_f16(tmem_d, a_lo + 2 * kk, b_hi + 2 * kk, idesc, 1u);
+                            }
+                        }
+                        ptx::umma_commit(bar_empty + 8 * s_hi);
+                        if (kX3) ptx::umma_commit(bar_empty + 8 * s_lo);
+                        if (kb == p.kblocks - 1) ptx::umma_commit(bar_tfull + 8 * acc);
                     }
                 }
             } else {
@@ -253,15 +310,19 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
         const uint32_t pair_bar = 1 + quarter;                // named barrier of the quarter's two warps
         const int W2 = p.W2;
         int iter = 0;
+        TileCoords cur, nxt;
+        if ((int)blockIdx.x < p.total_tiles) load_tile_coords(p, blockIdx.x, lane, cur);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int m_t = tile % p.num_m;
-            const int bh = tile / p.num_m;
-            const int b = bh / p.H, h = bh - b * p.H;
-            const float* crow = p.coords + (long long)b * p.coords_bstride + (long long)h * p.W1;
-            const Band bd = tile_band(crow, m_t * kBlockM, p.W1, W2, lane);
+            const int bh = fast_div(tile, p.num_m, p.num_m_mul, p.num_m_shr);
+            const int m_t = tile - bh * p.num_m;
+            const int b = fast_div(bh, p.H, p.H_mul, p.H_shr), h = bh - b * p.H;
+            nxt = cur;
+            if (tile + (int)gridDim.x < p.total_tiles) load_tile_coords(p, tile + gridDim.x, lane, nxt);
+            const Band bd = tile_band(cur, W2);
             const int row = m_t * kBlockM + quarter * 32 + lane;
             const bool in_row = row < p.W1;
-            const float c0 = in_row ? sane_coord(__ldg(crow + row)) : 1.0e9f;
+            const float c0 = sane_coord(quarter == 0 ? cur.c[0] : quarter == 1 ? cur.c[1] : quarter == 2 ? cur.c[2] : cur.c[3]);   // 1e9 past W1
+            cur = nxt;
             int my_lo, my_hi;
             pixel_range(c0, W2, my_lo, my_hi);
             if (!in_row) { my_lo = INT_MAX; my_hi = INT_MIN; }
@@ -277,7 +338,7 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
                 ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 ptx::tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols;
-                for (int blk = half; blk < nblk; blk += 2) {
+                for (int blk = half; blk < ((p.debug & 1) ? 0 : nblk); blk += 2) {
                     const int cg = col0 + 32 * blk;           // first level-0 column of the block (multiple of 8)
                     if (!__any_sync(0xffffffffu, my_lo < cg + 32 && my_hi > cg)) continue;   // nobody here touches it
                     float v[32];
@@ -338,7 +399,7 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
 
             // ---- the taps from the pixel's windows, filled by both warps of the quarter: this warp takes two levels
             asm volatile("bar.sync %0, 64;" :: "r"(pair_bar) : "memory");
-            if (in_row) {
+            if (in_row && !(p.debug & 4)) {
                 float* o = p.out + ((long long)b * 36 + 18 * half) * p.HW + (long long)h * p.W1 + row;
 #pragma unroll
                 for (int ll = 0; ll < 2; ++ll) {
@@ -380,17 +441,27 @@ corr_lookup_alt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
     }
 }
 
-// Operand [BH, W, C] 16-bit, channels contiguous; box = [1, box_w, 32], 64 B swizzle, zero fill outside.
+// (mul, shr) with n / d == __umulhi(n, mul) >> shr for every 0 <= n < 2^31, d >= 2.
+static void fast_divisor(int d, uint32_t* mul, uint32_t* shr) {
+    if (d <= 1) { *mul = 0; *shr = 0; return; }
+    int lg = 0;
+    while ((1LL << lg) < d) ++lg;
+    const int pbits = 31 + lg;
+    *mul = (uint32_t)(((1ULL << pbits) + (unsigned long long)d - 1) / (unsigned long long)d);
+    *shr = (uint32_t)(pbits - 32);
+}
+
+// K-block-major operand [BH, C/64, W, 64] 16-bit; box = [1, 1, box_w, 64] (contiguous), 128 B swizzle, zero fill outside.
 static int make_operand_map(CUtensorMap* tm, const void* base, int BH, int W, int C, int box_w, bool fp16) {
     EncodeTiledFn enc = get_encode_fn();
     TCS_REQUIRE(enc != nullptr, TCS_E_DRIVER, "tcs_corr_lookup_alt_tc: cuTensorMapEncodeTiled not available from the driver");
-    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)BH};
-    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)box_w, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+    cuuint64_t dims[4] = {(cuuint64_t)kBlockK, (cuuint64_t)W, (cuuint64_t)(C / kBlockK), (cuuint64_t)BH};
+    cuuint64_t strides[3] = {(cuuint64_t)kBlockK * 2, (cuuint64_t)W * kBlockK * 2, (cuuint64_t)W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)box_w, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TCS_REQUIRE(r == CUDA_SUCCESS, TCS_E_DRIVER, "tcs_corr_lookup_alt_tc: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return 0;
 }
@@ -411,7 +482,7 @@ extern "C" int tcs_corr_lookup_alt_tc(const void* a_hi, const void* a_lo, const 
     TCS_REQUIRE(!x3 || (a_lo != nullptr && b_lo != nullptr), TCS_E_BADARG, "tcs_corr_lookup_alt_tc: the X3 modes need the lo operands");
     TCS_REQUIRE(B > 0 && H > 0 && W1 > 0 && C > 0, TCS_E_BADARG, "tcs_corr_lookup_alt_tc: bad sizes");
     TCS_REQUIRE(W2 >= 16, TCS_E_SHAPE, "tcs_corr_lookup_alt_tc: W2=%d must be >= 16 (4 levels, each at least 2 wide)", W2);
-    TCS_REQUIRE(C % kBlockK == 0, TCS_E_SHAPE, "tcs_corr_lookup_alt_tc: C=%d must be a multiple of 32", C);
+    TCS_REQUIRE(C % kBlockK == 0, TCS_E_SHAPE, "tcs_corr_lookup_alt_tc: C=%d must be a multiple of 64", C);
     TCS_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo), TCS_E_ALIGN,
                 "tcs_corr_lookup_alt_tc: operands must be 16-byte aligned");
     TCS_REQUIRE((long long)B * H <= 0x7fffffffLL / 1024, TCS_E_SHAPE, "tcs_corr_lookup_alt_tc: B*H too large");
@@ -423,10 +494,13 @@ extern "C" int tcs_corr_lookup_alt_tc(const void* a_hi, const void* a_lo, const 
     const long long total = (long long)B * H * p.num_m;
     TCS_REQUIRE(total < 0x7fffffffLL, TCS_E_SHAPE, "tcs_corr_lookup_alt_tc: too many tiles");
     p.total_tiles = (int)total;
+    fast_divisor(p.num_m, &p.num_m_mul, &p.num_m_shr);
+    fast_divisor(H, &p.H_mul, &p.H_shr);
     p.kblocks = C / kBlockK;
     p.passes = x3 ? 3 : 1;
     p.ab_format = fp16 ? 0u : 1u;
     p.scale = fp16 ? (1.0f / 65536.0f) : 1.0f;
+    { const char* e = getenv("TCS_ALT_DEBUG"); p.debug = e ? atoi(e) : 0; }
 
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tbs_hi, tbs_lo;
     int rc;
@@ -441,10 +515,13 @@ extern "C" int tcs_corr_lookup_alt_tc(const void* a_hi, const void* a_lo, const 
         ta_lo = ta_hi; tb_lo = tb_hi; tbs_lo = tbs_hi;
     }
     TCS_ONCE_PER_DEVICE(
-        TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_alt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_alt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_alt_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     );
     const int grid = (int)((total < (long long)num_sms()) ? total : (long long)num_sms());
-    corr_lookup_alt_tc_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ta_hi, ta_lo, tb_hi, tb_lo, tbs_hi, tbs_lo, p);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (x3) corr_lookup_alt_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tbs_hi, tbs_lo, p);
+    else corr_lookup_alt_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, tbs_hi, tbs_lo, p);
     TCS_CHECK_LAUNCH("tcs_corr_lookup_alt_tc");
     return 0;
 }

@@ -35,7 +35,7 @@ __device__ __forceinline__ uint32_t pack_hi_lo(float a, float b, uint32_t& lo_pa
 template <bool kFp16>
 __global__ void __launch_bounds__(kPreThreads)
 corr_prepass_kernel(const float* __restrict__ fmap, uint32_t* __restrict__ hi, uint32_t* __restrict__ lo,
-                    float* __restrict__ n32, int C, int H, int W) {
+                    float* __restrict__ n32, int C, int H, int W, int kblocked) {
     extern __shared__ float tile[];  // [32][C + 1]
     const int pitch = C + 1;
     const int w0 = blockIdx.x * kPreTileW;
@@ -105,8 +105,10 @@ corr_prepass_kernel(const float* __restrict__ fmap, uint32_t* __restrict__ hi, u
             if (hi != nullptr) {
                 uint32_t lo_pack;
                 const uint32_t hi_pack = pack_hi_lo<kFp16>(a, d, lo_pack);
-                hi[(pix * C + c) >> 1] = hi_pack;
-                if (lo != nullptr) lo[(pix * C + c) >> 1] = lo_pack;
+                // pixel-major [B,H,W,C] or K-block-major [B,H,C/64,W,64]: either way this warp store is one 128-byte line
+                const size_t e = kblocked ? ((((size_t)b * H + h) * pairs + k) * W + w) * 64 + 2 * lane : pix * C + c;
+                hi[e >> 1] = hi_pack;
+                if (lo != nullptr) lo[e >> 1] = lo_pack;
             }
         }
     }
@@ -128,8 +130,8 @@ __global__ void fmap_pool_w_kernel(const float4* __restrict__ in, float4* __rest
 
 }  // namespace tcs
 
-extern "C" int tcs_corr_prepass(const float* fmap, void* hi, void* lo, float* n32,
-                                int B, int C, int H, int W, int prec, void* stream) {
+static int launch_prepass(const float* fmap, void* hi, void* lo, float* n32, int B, int C, int H, int W, int prec, int kblocked,
+                          void* stream) {
     using namespace tcs;
     TCS_REQUIRE(fmap != nullptr && (hi != nullptr || n32 != nullptr), TCS_E_BADARG,
                 "tcs_corr_prepass: fmap and at least one of hi / n32 are required");
@@ -149,16 +151,27 @@ extern "C" int tcs_corr_prepass(const float* fmap, void* hi, void* lo, float* n3
             TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 513 * 4));
             { const int cv = carveout_percent("TCS_CARVE_PREPASS", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); }
         );
-        corr_prepass_kernel<true><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W);
+        corr_prepass_kernel<true><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W, kblocked);
     } else {
         TCS_ONCE_PER_DEVICE(
             TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 513 * 4));
             { const int cv = carveout_percent("TCS_CARVE_PREPASS", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); }
         );
-        corr_prepass_kernel<false><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W);
+        corr_prepass_kernel<false><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W, kblocked);
     }
     TCS_CHECK_LAUNCH("tcs_corr_prepass");
     return 0;
+}
+
+extern "C" int tcs_corr_prepass(const float* fmap, void* hi, void* lo, float* n32,
+                                int B, int C, int H, int W, int prec, void* stream) {
+    return launch_prepass(fmap, hi, lo, n32, B, C, H, W, prec, 0, stream);
+}
+
+extern "C" int tcs_corr_prepass_kblocked(const float* fmap, void* hi, void* lo,
+                                         int B, int C, int H, int W, int prec, void* stream) {
+    TCS_REQUIRE(hi != nullptr, TCS_E_BADARG, "tcs_corr_prepass_kblocked: hi is required");
+    return launch_prepass(fmap, hi, lo, nullptr, B, C, H, W, prec, 1, stream);
 }
 
 extern "C" int tcs_fmap_pool_w(const float* in, float* out, int B, int H, int W, int C, void* stream) {
