@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCS_ABI_VERSION 5
+#define TCS_ABI_VERSION 6
 
 /* argument errors (negative); CUDA launch errors are returned as positive cudaError_t values */
 #define TCS_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported combination */
@@ -207,6 +207,14 @@ int tcs_bilinear_sample(const float* img, const float* grid_xy, float* out,
 /* ref: core/tc_stereo.py:163: grid <- 0.5 * F.interpolate(grid, scale_factor=0.5, 'bilinear',
  * align_corners=True).  in [B,2,H,W] -> out [B,2,H/2,W/2]. */
 int tcs_grid_halve(const float* in, float* out, int B, int H, int W, void* stream);
+
+/* ref: core/tc_stereo.py:159-163, the whole loop in one launch: the three hidden-state maps net[l] [B,C_l,H>>l,W>>l] are
+ * sampled (tcs_bilinear_sample's arithmetic) at the backward grid [B,2,H,W] halved l times (tcs_grid_halve's arithmetic,
+ * evaluated on the fly), so the results are bit-identical to the chain of three samples and two halvings.
+ *   out[l] [B,C_l,H>>l,W>>l].  Requires H, W >= 4. */
+int tcs_warp_hidden_states(const float* net0, const float* net1, const float* net2, const float* grid,
+                           float* out0, float* out1, float* out2, int B, int C0, int C1, int C2, int H, int W,
+                           void* stream);
 
 /* ---- (5) "next" row: the per-GRU-iteration 3x3 stencils on the disparity ---------- */
 

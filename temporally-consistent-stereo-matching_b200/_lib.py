@@ -14,7 +14,7 @@ PREC_BF16, PREC_BF16X3, PREC_FP16, PREC_FP16X3 = 0, 1, 2, 3
 PRECISIONS = {"bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16, "fp16x3": PREC_FP16X3}
 MAX_LEVELS = 4
 MAX_RADIUS = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -43,6 +43,7 @@ SIGNATURES = {
     "tcs_backward_grid": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "tcs_bilinear_sample": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_grid_halve": (_i, [_p, _p, _i, _i, _i, _p]),
+    "tcs_warp_hidden_states": (_i, [_p] * 7 + [_i] * 6 + [_p]),
     "tcs_disp_gradient_xy": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "tcs_disp_grad_candidates": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tcs_disp_propagate": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),

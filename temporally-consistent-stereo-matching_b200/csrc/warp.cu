@@ -725,16 +725,10 @@ backward_grid_kernel(const float* __restrict__ disp, const float* __restrict__ r
 // lanes being consecutive output pixels so that loads and stores of one channel plane coalesce.
 constexpr int kSampleCh = 16;
 
+// One (output pixel, channel group) of the gather: img_b / out_b are the sample's [C,Hi,Wi] / [C,Ho*Wo] planes.
 template <bool kFull>   // kFull: C is a multiple of kSampleCh, no per-channel guards (keeps the loads batched)
-__global__ void __launch_bounds__(256)
-bilinear_sample_kernel(const float* __restrict__ img, const float* __restrict__ grid_xy, float* __restrict__ out,
-                       int C, int Hi, int Wi, int Ho, int Wo) {
-    const int b = blockIdx.z;
-    const int HWo = Ho * Wo;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= HWo) return;
-    const float gx = __ldg(grid_xy + ((size_t)b * 2 + 0) * HWo + i);
-    const float gy = __ldg(grid_xy + ((size_t)b * 2 + 1) * HWo + i);
+__device__ __forceinline__ void sample_group(const float* __restrict__ img_b, float gx, float gy, float* __restrict__ out_b,
+                                             int C, int Hi, int Wi, int HWo, int i, int c_begin) {
     const float wm1 = (float)(Wi - 1), hm1 = (float)(Hi - 1);
     const float xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, gx), wm1), 1.0f);                  // utils.py:86
     const float yn = (Hi > 1) ? __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, gy), hm1), 1.0f) : gy;  // utils.py:87-88
@@ -755,9 +749,8 @@ bilinear_sample_kernel(const float* __restrict__ img, const float* __restrict__ 
     const float w_se = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(iy, y0f));
     const int o_nw = y0 * Wi + x0, o_ne = y0 * Wi + x1, o_sw = y1 * Wi + x0, o_se = y1 * Wi + x1;
     const size_t plane_i = (size_t)Hi * Wi;
-    const int c_begin = blockIdx.y * kSampleCh;
-    const float* src = img + ((size_t)b * C + c_begin) * plane_i;
-    float* dst = out + ((size_t)b * C + c_begin) * HWo + i;
+    const float* src = img_b + (size_t)c_begin * plane_i;
+    float* dst = out_b + (size_t)c_begin * HWo + i;
     float v[kSampleCh][4];
 #pragma unroll
     for (int k = 0; k < kSampleCh; ++k) {
@@ -781,7 +774,50 @@ bilinear_sample_kernel(const float* __restrict__ img, const float* __restrict__ 
     }
 }
 
+template <bool kFull>
+__global__ void __launch_bounds__(256)
+bilinear_sample_kernel(const float* __restrict__ img, const float* __restrict__ grid_xy, float* __restrict__ out,
+                       int C, int Hi, int Wi, int Ho, int Wo) {
+    const int b = blockIdx.z;
+    const int HWo = Ho * Wo;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HWo) return;
+    const float gx = __ldg(grid_xy + ((size_t)b * 2 + 0) * HWo + i);
+    const float gy = __ldg(grid_xy + ((size_t)b * 2 + 1) * HWo + i);
+    sample_group<kFull>(img + (size_t)b * C * Hi * Wi, gx, gy, out + (size_t)b * C * HWo, C, Hi, Wi, HWo, i, blockIdx.y * kSampleCh);
+}
+
 // ---- 0.5 * interpolate(grid, 0.5, bilinear, align_corners=True) ------------------------------------------------------------
+// One element of 0.5 * F.interpolate(plane, scale_factor=0.5, 'bilinear', align_corners=True): the source position and
+// the four interpolation weights of output (yo, xo) ...
+struct HalvePos {
+    int y0, x0, yp, xp;
+    float ly0, ly1, lx0, lx1;
+};
+__device__ __forceinline__ HalvePos halve_pos(int H, int W, int Ho, int Wo, int yo, int xo) {
+    HalvePos q;
+    // ATen area_pixel_compute_scale with align_corners: (in - 1) / (out - 1), 0 when out == 1
+    const float sh = (Ho > 1) ? __fdiv_rn((float)(H - 1), (float)(Ho - 1)) : 0.0f;
+    const float sw = (Wo > 1) ? __fdiv_rn((float)(W - 1), (float)(Wo - 1)) : 0.0f;
+    const float ys = __fmul_rn(sh, (float)yo), xs = __fmul_rn(sw, (float)xo);
+    q.y0 = (int)ys; q.x0 = (int)xs;
+    q.yp = (q.y0 < H - 1) ? 1 : 0; q.xp = (q.x0 < W - 1) ? 1 : 0;
+    q.ly1 = __fsub_rn(ys, (float)q.y0); q.ly0 = __fsub_rn(1.0f, q.ly1);
+    q.lx1 = __fsub_rn(xs, (float)q.x0); q.lx0 = __fsub_rn(1.0f, q.lx1);
+    return q;
+}
+// ... and the value from the four source values.
+__device__ __forceinline__ float halve_mix(const HalvePos& q, float v00, float v01, float v10, float v11) {
+    const float top = __fadd_rn(__fmul_rn(q.lx0, v00), __fmul_rn(q.lx1, v01));
+    const float bot = __fadd_rn(__fmul_rn(q.lx0, v10), __fmul_rn(q.lx1, v11));
+    return __fmul_rn(0.5f, __fadd_rn(__fmul_rn(q.ly0, top), __fmul_rn(q.ly1, bot)));
+}
+__device__ __forceinline__ float halve_at(const float* __restrict__ plane, int H, int W, int Ho, int Wo, int yo, int xo) {
+    const HalvePos q = halve_pos(H, W, Ho, Wo, yo, xo);
+    const float* p = plane + (long long)q.y0 * W + q.x0;
+    return halve_mix(q, __ldg(p), __ldg(p + q.xp), __ldg(p + (long long)q.yp * W), __ldg(p + (long long)q.yp * W + q.xp));
+}
+
 __global__ void __launch_bounds__(256)
 grid_halve_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int Ho, int Wo, long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -789,19 +825,69 @@ grid_halve_kernel(const float* __restrict__ in, float* __restrict__ out, int H, 
     const int xo = (int)(i % Wo);
     const int yo = (int)((i / Wo) % Ho);
     const long long bc = i / ((long long)Wo * Ho);
-    // ATen area_pixel_compute_scale with align_corners: (in - 1) / (out - 1), 0 when out == 1
-    const float sh = (Ho > 1) ? __fdiv_rn((float)(H - 1), (float)(Ho - 1)) : 0.0f;
-    const float sw = (Wo > 1) ? __fdiv_rn((float)(W - 1), (float)(Wo - 1)) : 0.0f;
-    const float ys = __fmul_rn(sh, (float)yo), xs = __fmul_rn(sw, (float)xo);
-    const int y0 = (int)ys, x0 = (int)xs;
-    const int yp = (y0 < H - 1) ? 1 : 0, xp = (x0 < W - 1) ? 1 : 0;
-    const float ly1 = __fsub_rn(ys, (float)y0), ly0 = __fsub_rn(1.0f, ly1);
-    const float lx1 = __fsub_rn(xs, (float)x0), lx0 = __fsub_rn(1.0f, lx1);
-    const float* p = in + bc * (long long)H * W + (long long)y0 * W + x0;
-    const float v00 = __ldg(p), v01 = __ldg(p + xp), v10 = __ldg(p + (long long)yp * W), v11 = __ldg(p + (long long)yp * W + xp);
-    const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
-    const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
-    out[i] = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot)));
+    out[i] = halve_at(in + bc * (long long)H * W, H, W, Ho, Wo, yo, xo);
+}
+
+// ---- the whole hidden-state warp of tc_stereo.py:159-163 in ONE launch ---------------------------------------------
+// Three gathers with a grid halved between them were five launches, of which the two small levels ran at 50 % / 28 %
+// of the HBM rate (tails and launch gaps, not bytes).  Here the blocks of all three levels share one grid
+// (blockIdx.x runs over level 0's pixel blocks, then level 1's, then level 2's), and a thread of level 1 / 2 halves
+// the backward grid for its own pixel on the fly - the same operations in the same order as grid_halve_kernel, so
+// the sampled positions are bit-identical to the chained launches (level 2 re-derives the four level-1 values it
+// mixes: 16 grid reads per plane, from L1/L2).
+struct Hidden3Params {
+    const float* net[3];
+    float* out[3];
+    const float* grid;
+    int C[3];
+    int H[3], W[3];
+    int blocks[3];       // pixel blocks of each level
+};
+
+__global__ void __launch_bounds__(256)
+warp_hidden3_kernel(const Hidden3Params p) {
+    const int b = blockIdx.z;
+    int bx = blockIdx.x, l = 0;
+    if (bx >= p.blocks[0]) { bx -= p.blocks[0]; l = 1; }
+    if (l == 1 && bx >= p.blocks[1]) { bx -= p.blocks[1]; l = 2; }
+    const int Hl = l == 0 ? p.H[0] : l == 1 ? p.H[1] : p.H[2];
+    const int Wl = l == 0 ? p.W[0] : l == 1 ? p.W[1] : p.W[2];
+    const int Cl = l == 0 ? p.C[0] : l == 1 ? p.C[1] : p.C[2];
+    const int c_begin = blockIdx.y * kSampleCh;
+    if (c_begin >= Cl) return;                                   // block-uniform
+    const int HWl = Hl * Wl;
+    const int i = bx * 256 + threadIdx.x;
+    if (i >= HWl) return;
+    const int H0 = p.H[0], W0 = p.W[0];
+    const float* g0 = p.grid + (size_t)b * 2 * H0 * W0;
+    float g[2];
+    if (l == 0) {
+        g[0] = __ldg(g0 + i);
+        g[1] = __ldg(g0 + (size_t)H0 * W0 + i);
+    } else {
+        const int yo = i / Wl, xo = i - yo * Wl;
+        const int H1 = p.H[1], W1 = p.W[1];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float* plane = g0 + (size_t)c * H0 * W0;
+            if (l == 1) {
+                g[c] = halve_at(plane, H0, W0, H1, W1, yo, xo);
+            } else {
+                const HalvePos q = halve_pos(H1, W1, Hl, Wl, yo, xo);     // position in the level-1 grid, whose values are
+                const float v00 = halve_at(plane, H0, W0, H1, W1, q.y0, q.x0);             // halved from level 0 here
+                const float v01 = halve_at(plane, H0, W0, H1, W1, q.y0, q.x0 + q.xp);
+                const float v10 = halve_at(plane, H0, W0, H1, W1, q.y0 + q.yp, q.x0);
+                const float v11 = halve_at(plane, H0, W0, H1, W1, q.y0 + q.yp, q.x0 + q.xp);
+                g[c] = halve_mix(q, v00, v01, v10, v11);
+            }
+        }
+    }
+    const float* net = l == 0 ? p.net[0] : l == 1 ? p.net[1] : p.net[2];
+    float* out = l == 0 ? p.out[0] : l == 1 ? p.out[1] : p.out[2];
+    const float* img_b = net + (size_t)b * Cl * HWl;
+    float* out_b = out + (size_t)b * Cl * HWl;
+    if (Cl % kSampleCh == 0) sample_group<true>(img_b, g[0], g[1], out_b, Cl, Hl, Wl, HWl, i, c_begin);
+    else sample_group<false>(img_b, g[0], g[1], out_b, Cl, Hl, Wl, HWl, i, c_begin);
 }
 
 static size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
@@ -975,5 +1061,32 @@ extern "C" int tcs_grid_halve(const float* in, float* out, int B, int H, int W, 
     const long long total = (long long)B * 2 * Ho * Wo;
     grid_halve_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, H, W, Ho, Wo, total);
     TCS_CHECK_LAUNCH("tcs_grid_halve");
+    return 0;
+}
+
+extern "C" int tcs_warp_hidden_states(const float* net0, const float* net1, const float* net2, const float* grid,
+                                      float* out0, float* out1, float* out2, int B, int C0, int C1, int C2, int H, int W,
+                                      void* stream) {
+    using namespace tcs;
+    TCS_REQUIRE(net0 && net1 && net2 && grid && out0 && out1 && out2, TCS_E_BADARG, "tcs_warp_hidden_states: null pointer");
+    TCS_REQUIRE(B > 0 && B <= 65535 && C0 > 0 && C1 > 0 && C2 > 0, TCS_E_BADARG, "tcs_warp_hidden_states: bad sizes");
+    TCS_REQUIRE(H >= 4 && W >= 4, TCS_E_SHAPE, "tcs_warp_hidden_states: need H, W >= 4 (three levels, each halved)");
+    TCS_REQUIRE((long long)H * W < 0x7fffffffLL, TCS_E_SHAPE, "tcs_warp_hidden_states: image plane too large");
+    Hidden3Params p{};
+    p.net[0] = net0; p.net[1] = net1; p.net[2] = net2;
+    p.out[0] = out0; p.out[1] = out1; p.out[2] = out2;
+    p.grid = grid;
+    p.C[0] = C0; p.C[1] = C1; p.C[2] = C2;
+    p.H[0] = H; p.W[0] = W;
+    for (int l = 1; l < 3; ++l) { p.H[l] = p.H[l - 1] / 2; p.W[l] = p.W[l - 1] / 2; }     // F.interpolate(scale_factor=0.5): floor
+    int cmax = C0 > C1 ? C0 : C1;
+    if (C2 > cmax) cmax = C2;
+    const int groups = ceil_div(cmax, kSampleCh);
+    TCS_REQUIRE(groups <= 65535, TCS_E_SHAPE, "tcs_warp_hidden_states: C too large");
+    long long bx = 0;
+    for (int l = 0; l < 3; ++l) { p.blocks[l] = ceil_div(p.H[l] * p.W[l], 256); bx += p.blocks[l]; }
+    dim3 g((unsigned)bx, groups, B);
+    warp_hidden3_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    TCS_CHECK_LAUNCH("tcs_warp_hidden_states");
     return 0;
 }

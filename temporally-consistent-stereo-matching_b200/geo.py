@@ -206,7 +206,20 @@ def halve_grid(grid_xy):
 
 
 def warp_hidden_states(net_list, backward_grid):
-    """ref: tc_stereo.py:159-163.  Sample each hidden-state level with the (progressively halved) grid."""
+    """ref: tc_stereo.py:159-163.  Sample each hidden-state level with the (progressively halved) grid.  The model's
+    three-level case (each level half the previous one's size) is one launch; anything else chains the single ops."""
+    if len(net_list) == 3 and backward_grid.dim() == 4 and backward_grid.shape[1] == 2:
+        B, _, H, W = backward_grid.shape
+        dims = [(H, W), (H // 2, W // 2), (H // 2 // 2, W // 2 // 2)]
+        if H >= 4 and W >= 4 and all(n.dim() == 4 and n.shape[0] == B and tuple(n.shape[2:]) == d for n, d in zip(net_list, dims)):
+            nets = [_f32c("net_list[%d]" % i, n) for i, n in enumerate(net_list)]
+            grid = _f32c("backward_grid", backward_grid)
+            outs = [torch.empty_like(n) for n in nets]
+            with torch.cuda.device(grid.device):
+                _lib.call("tcs_warp_hidden_states", nets[0].data_ptr(), nets[1].data_ptr(), nets[2].data_ptr(), grid.data_ptr(),
+                          outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), B, nets[0].shape[1], nets[1].shape[1],
+                          nets[2].shape[1], H, W, _stream())
+            return outs
     out = []
     grid = backward_grid
     for i, net in enumerate(net_list):

@@ -124,7 +124,8 @@ def launches_per_frame(iters, first_frame, hidden_levels=3, mode="pyramid", num_
             n += 2                                                 # its prepasses
     else:
         # scatter: geometry, weights, splat, cost | lists: geometry, weights + count, row sums, offsets, fill, sort, cost
-        n += (7 if warp_lists else 4) + 1 + hidden_levels + (hidden_levels - 1)   # + grid; gathers; halves
+        # + grid; the hidden-state warp: one launch for the model's three levels, else gathers + halves
+        n += (7 if warp_lists else 4) + 1 + (1 if hidden_levels == 3 else hidden_levels + (hidden_levels - 1))
     return n + iters
 
 

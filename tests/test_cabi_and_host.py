@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libtcs_b200.so does not export %s" % n
     assert sorted(tcs_b200._lib.SIGNATURES) == names, "ctypes signatures and header disagree"
-    assert lib.tcs_abi_version() == tcs_b200._lib.ABI_VERSION == 5
+    assert lib.tcs_abi_version() == tcs_b200._lib.ABI_VERSION == 6
 
 
 def test_argument_errors_are_reported_without_a_gpu():
@@ -247,8 +247,9 @@ def test_bench_reference_arm_contract():
 
 def test_launch_count_model():
     from tcs_b200 import sequence
-    assert sequence.launches_per_frame(32, False) == 1 + 4 + 1 + 3 + 2 + 32   # fused build; geometry, weights, splat, finalize; grid; 3 gathers; 2 halvings; lookups
+    assert sequence.launches_per_frame(32, False) == 1 + 4 + 1 + 1 + 32   # fused build; geometry, weights, splat, finalize; grid; hidden-state warp; lookups
     assert sequence.launches_per_frame(32, True) == 1 + 1 + 32
     assert sequence.launches_per_frame(32, False, fused_build=False) == sequence.launches_per_frame(32, False) + 2
     # list formulation on a carried transposition: geometry, weights + count, row sums, offsets, fill, sort, cost
-    assert sequence.launches_per_frame(32, False, warp_lists=True) == 1 + 7 + 1 + 3 + 2 + 32
+    assert sequence.launches_per_frame(32, False, warp_lists=True) == 1 + 7 + 1 + 1 + 32
+    assert sequence.launches_per_frame(32, False, hidden_levels=2) == 1 + 4 + 1 + 2 + 1 + 32      # other depths chain gathers and halvings

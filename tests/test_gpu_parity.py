@@ -734,3 +734,23 @@ def test_relative_pose_matches_torch(tcs):
     assert one.shape == (4, 4) and torch.equal(one, got[0])
     with pytest.raises(ValueError):
         tcs.cal_relative_transformation(T1.cuda(), T2[:2].cuda())
+
+
+@pytest.mark.parametrize("B,H,W,Cs", [(2, 136, 240, (128, 128, 128)), (1, 15, 21, (8, 8, 8)), (1, 12, 16, (20, 7, 33)), (3, 5, 4, (16, 16, 16))])
+def test_hidden_state_warp_one_launch_is_bit_identical_to_the_chain(tcs, B, H, W, Cs):
+    """tcs_warp_hidden_states (tc_stereo.py:159-163 in one launch, grids halved on the fly) against the chain of
+    tcs_bilinear_sample / tcs_grid_halve calls it replaces: same operations in the same order, so every bit agrees -
+    odd sizes (floor halving), channel counts off the 16-channel groups, out-of-range and -1 grid entries."""
+    g = torch.Generator().manual_seed(H * W)
+    grid = torch.stack([torch.rand(B, H, W, generator=g) * (W + 6) - 3, torch.rand(B, H, W, generator=g) * (H + 6) - 3], 1)
+    grid.view(-1)[::13] = -1.0
+    nets = [torch.randn(B, c, H >> l, W >> l, generator=g).cuda() for l, c in enumerate(Cs)]
+    got = tcs.warp_hidden_states(nets, grid.cuda())
+    gg, want = grid.cuda(), []
+    for l, net in enumerate(nets):
+        want.append(tcs.sample_planar(net, gg))
+        if l < 2:
+            gg = tcs.halve_grid(gg)
+    for l in range(3):
+        assert got[l].shape == want[l].shape
+        assert torch.equal(got[l], want[l]), "level %d differs" % l
