@@ -40,10 +40,13 @@ RADIUS = 4
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
     ap.add_argument("--seqs-per-gpu", type=int, default=8)
+    ap.add_argument("--sequences", type=int, default=0,
+                    help="BASELINE config 4: this many sequences in TOTAL, sharded over the ranks with shard_sequences() (strong "
+                         "scaling; e.g. --sequences 64 --height 480 --width 640); 0 = --seqs-per-gpu on every rank (weak scaling)")
     ap.add_argument("--height", type=int, default=540)
     ap.add_argument("--width", type=int, default=960)
     ap.add_argument("--iters", type=int, default=32)
@@ -355,6 +358,10 @@ def run_b200(args):
     from tcs_b200 import sequence
 
     B, iters = args.seqs_per_gpu, args.iters
+    if args.sequences > 0:          # whole sequences per GPU: sequence s lives on rank s mod N
+        B = len(sequence.shard_sequences(args.sequences, world, rank))
+        if B == 0:
+            raise SystemExit("rank %d owns no sequence: --sequences must be >= the number of GPUs" % rank)
     H, W = feature_hw(args.height, args.width)
     fused_build = (args.mode == "pyramid" and args.precision != "fp32" and W <= 240 and W % 4 == 0
                    and os.environ.get("TCS_B200_FUSED_BUILD", "1") != "0")
@@ -446,7 +453,8 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms, phase_ms = tmax[0].item(), tmax[1:].tolist()
-    frames = world * B * K_steps
+    # frames of the whole job: every rank's sequences x steps, summed with the path's only collective (final metric reduce)
+    frames = int(round(sequence.reduce_metrics([float(B * K_steps)], device=device)[0]))
     value = frames / (total_ms * 1e-3)
     checksum = float(live[(K_steps - 1) % 2]["corr"].double().sum().item())
 
@@ -594,13 +602,14 @@ def run_b200(args):
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K_steps, "warmup": W_steps,
-            "ms_per_step": total_ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / K_steps, "higher_is_better": True, "scaling": "strong" if args.sequences > 0 else "weak", "vs_baseline": None,
             "dtype": {"fp16x3": "f16x3->f32", "bf16x3": "bf16x3->f32", "bf16": "bf16->f32", "fp16": "f16->f32", "fp32": "f32"}[args.precision],
             "data": "synthetic",
             "config": {"workload": workload_text(args, B),
                        "feature_hw": [H, W], "seqs_per_gpu": B, "precision": args.precision, "mode": args.mode,
                        "cuda_graphs": used_graphs, "fused_build": fused_build, "warp": ("scatter + warped-feature store (plain drop-in)" if args.want_fmap else "lists on carried transposition" if args.warp_carry else "scatter, cost only"), "l2": "inputs larger than L2 (%.0f MB of feature maps per step, 2 alternating slots)" % (2 * npix * C * 4 / 1e6),
-                       "parallelism": "sequences sharded per GPU, no data-path collective"},
+                       "total_sequences": args.sequences if args.sequences > 0 else world * B,
+                       "parallelism": "sequences sharded per GPU (sequence s -> rank s mod N), no data-path collective; one all_reduce of the frame count"},
             "e2e": e2e, "gpu_launches": K_steps * sequence.launches_per_frame(iters, False, mode=args.mode, fused_build=fused_build,
                                                                                     warp_lists=args.warp_carry and not args.want_fmap),
             "clocks": clocks, "roofline": roofline, "phases": phases_out, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "checksum": checksum,

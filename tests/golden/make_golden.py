@@ -53,8 +53,10 @@ def import_reference():
     return rcorr, rutils, rgeo
 
 
-def camera(B, H, W, rng, baseline=0.25):
-    """Feature-resolution pinhole camera + a small forward/yaw motion with per-sample jitter."""
+def camera(B, H, W, rng, baseline=0.25, tz=None):
+    """Feature-resolution pinhole camera + a small forward/yaw motion with per-sample jitter.  tz: a fixed translation
+    along the optical axis instead (metres): large positive values put near points behind the current camera (the
+    forward warp's invalid branch), negative ones put them behind the previous camera (get_backward_grid's -1 branch)."""
     K = np.zeros((B, 3, 3), np.float64)
     K[:, 0, 0] = K[:, 1, 1] = 0.5 * W
     K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = 0.5 * W - 0.5, 0.5 * H - 0.5, 1.0
@@ -63,7 +65,7 @@ def camera(B, H, W, rng, baseline=0.25):
     for b in range(B):
         yaw = np.deg2rad(0.6 + 0.3 * b)
         c, s = np.cos(yaw), np.sin(yaw)
-        cam2world = np.array([[c, 0, s, 0.02 * (b + 1)], [0, 1, 0, 0.01], [-s, 0, c, 0.12 + 0.05 * b], [0, 0, 0, 1.0]])
+        cam2world = np.array([[c, 0, s, 0.02 * (b + 1)], [0, 1, 0, 0.01], [-s, 0, c, (0.12 + 0.05 * b) if tz is None else tz], [0, 0, 0, 1.0]])
         T[b] = np.linalg.inv(cam2world)
     base = np.full((B, 1), baseline)
     f32 = lambda a: a.astype(np.float32)
@@ -100,10 +102,10 @@ def corr_case(rcorr, name, B, C, H, W, seed, correlated_shift):
     print(name, "mask density %.3f" % mask.mean().item(), {k: v.shape for k, v in out.items() if k.startswith("level")})
 
 
-def warp_case(rutils, rgeo, name, B, C, H, W, seed):
+def warp_case(rutils, rgeo, name, B, C, H, W, seed, tz=None):
     rng = np.random.default_rng(seed)
     g = torch.Generator().manual_seed(seed)
-    K, Kinv, T, Tinv, base = camera(B, H, W, rng)
+    K, Kinv, T, Tinv, base = camera(B, H, W, rng, tz=tz)
     disp = 0.5 + torch.rand(B, 1, H, W, generator=g) * (W / 4)
     disp.view(-1)[:: 37] = 0.0                        # exact zeros hit the clip(disp, 1e-3) branch
     fmap = torch.randn(B, C, H, W, generator=g)
@@ -112,6 +114,8 @@ def warp_case(rutils, rgeo, name, B, C, H, W, seed):
     wdisp, wfmap, wmask = rgeo.warp(disp, fmap, tT, tK, tKinv, tb)
     cost = torch.sum(F.normalize(cur_fmap, dim=1) * F.normalize(wfmap, dim=1), dim=1, keepdim=True) * wmask   # tc_stereo.py:139-140
     disp_init = (wdisp * wmask).clamp_min(0)
+    if tz is not None:   # the completed disparity is a network output, not the warped one: independent values reach z <= 0
+        disp_init = 0.5 + torch.rand(B, 1, H, W, generator=g) * (W / 4)
     grid = rgeo.get_backward_grid(disp_init, tTinv, tK, tKinv, tb)
     nets = [torch.tanh(torch.randn(B, 8, H >> i, W >> i, generator=g)) for i in range(3)]
     warped, gg, grids = [], grid, [grid]
@@ -166,6 +170,12 @@ def main():
         corr_case(rcorr, "corr_small", B=2, C=128, H=3, W=40, seed=1234, correlated_shift=5)
         corr_case(rcorr, "corr_oddwidth", B=1, C=128, H=2, W=78, seed=4321, correlated_shift=0)
         warp_case(rutils, rgeo, "warp_small", B=2, C=128, H=12, W=16, seed=1234)
+        # round 2: the branches the first set left vacuous: an odd width WITH a disparity signal (argmax mask
+        # density > 0, floor-pooled levels), near points behind the current camera (invalid sources in the forward warp) and
+        # behind the previous one (get_backward_grid's where(valid, uv, -1))
+        corr_case(rcorr, "corr_oddshift", B=1, C=128, H=3, W=77, seed=99, correlated_shift=4)
+        warp_case(rutils, rgeo, "warp_forward_jump", B=2, C=64, H=12, W=16, seed=77, tz=1.2)
+        warp_case(rutils, rgeo, "warp_backward_jump", B=2, C=64, H=12, W=16, seed=78, tz=-1.2)
 
 
 if __name__ == "__main__":

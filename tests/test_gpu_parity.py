@@ -64,7 +64,7 @@ def test_prepass_normalise(tcs):
     assert np.abs(split16 - host(n32)).max() <= 2.0 ** -20, "fp16 hi+lo"
 
 
-@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth"])
+@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth", "corr_oddshift"])
 @pytest.mark.parametrize("precision,rtol,atol", [("fp32", 1e-5, 1e-6), ("fp16x3", 1e-5, 1e-6), ("bf16x3", 1e-5, 8e-6),
                                                  ("bf16", 0.0, 2.0 ** -8), ("fp16", 0.0, 2.0 ** -10)])
 def test_build_golden(tcs, case, precision, rtol, atol):
@@ -74,7 +74,8 @@ def test_build_golden(tcs, case, precision, rtol, atol):
         assert_close(host(levels[l]), g["level%d" % l], rtol=rtol, atol=atol, what="%s %s level %d" % (case, precision, l))
 
 
-SHAPES = [(1, 136, 240), (2, 120, 160), (1, 96, 312), (1, 17, 100), (1, 3, 250)]
+SHAPES = [(1, 136, 240), (2, 120, 160), (1, 96, 312), (1, 17, 100), (1, 3, 250),
+          (1, 48, 480)]   # BASELINE config 5 rows (1088x1920 -> 272x480; two N tiles, four M tiles): the fp64 oracle takes ~10 s per 48 rows
 
 
 @pytest.mark.parametrize("B,H,W", SHAPES)
@@ -151,7 +152,7 @@ def test_build_two_n_tiles_and_m_tail(tcs):
 # (2) lookup, (3) alternate
 # ---------------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth"])
+@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth", "corr_oddshift"])
 def test_lookup_golden(tcs, case):
     g = load_golden(case)
     blk = tcs.CorrBlock1D.from_levels([cuda(g["level%d" % l]) for l in range(4)], radius=4)
@@ -160,7 +161,7 @@ def test_lookup_golden(tcs, case):
     assert_close(host(out), g["lookup"], what=case + " lookup vs reference")
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 136, 240), (3, 120, 160), (1, 96, 312), (1, 5, 67)])
+@pytest.mark.parametrize("B,H,W", [(1, 136, 240), (3, 120, 160), (1, 96, 312), (1, 5, 67), (1, 272, 480)])
 @pytest.mark.parametrize("radius", [4, 3])
 def test_lookup_full_size(tcs, B, H, W, radius):
     f1, f2 = make_fmaps(B, 128, H, W, 11 + W)
@@ -251,7 +252,7 @@ def test_lookup_coords_view_and_nan(tcs):
 # "next" row: lookup fused with BasicMotionEncoder.convc1 + relu
 # ---------------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth"])
+@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth", "corr_oddshift"])
 def test_lookup_encoded_golden(tcs, case):
     """Against the reference's own lookup output pushed through torch's conv2d + relu (what update.py:104 does)."""
     g = load_golden(case)
@@ -287,7 +288,7 @@ def test_lookup_encoded_full_size(tcs, B, H, W, cout, relu):
                  rtol=1e-4, atol=1e-5, what="fused vs lookup + torch conv2d on the GPU")
 
 
-@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth"])
+@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth", "corr_oddshift"])
 def test_alternate_golden(tcs, case):
     g = load_golden(case)
     blk = tcs.CorrBlock1D(cuda(g["fmap1"]), cuda(g["fmap2"]), mode="alternate")
@@ -371,7 +372,7 @@ def test_alternate_cuda_core_fallback_still_matches(tcs):
 # first frame: argmax_disp, cost volume
 # ---------------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth"])
+@pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth", "corr_oddshift"])
 def test_argmax_and_cost_volume_golden(tcs, case):
     g = load_golden(case)
     blk = tcs.CorrBlock1D.from_levels([cuda(g["level%d" % l]) for l in range(4)])
@@ -399,8 +400,12 @@ def test_argmax_full_size(tcs, B, H, W, shift):
 # (4) temporal step
 # ---------------------------------------------------------------------------------------------------------
 
-def test_warp_golden(tcs):
-    g = load_golden("warp_small")
+WARP_CASES = ["warp_small", "warp_forward_jump", "warp_backward_jump"]
+
+
+@pytest.mark.parametrize("case", WARP_CASES)
+def test_warp_golden(tcs, case):
+    g = load_golden(case)
     args = [cuda(g[k]) for k in ("disp", "fmap", "rel_T", "K", "K_inv", "baseline")]
     d, f, m, c = tcs.warp_with_cost(*args, cur_fmap=cuda(g["cur_fmap"]))
     assert_exact(host(m), g["warped_mask"], what="splat mask vs reference")
@@ -570,9 +575,11 @@ def test_warp_identity_pose_keeps_everything(tcs):
     assert_close(host(f), rf, rtol=1e-5, atol=2e-6, what="fmap")
 
 
-def test_backward_grid_and_hidden_states_golden(tcs):
-    g = load_golden("warp_small")
+@pytest.mark.parametrize("case", WARP_CASES)
+def test_backward_grid_and_hidden_states_golden(tcs, case):
+    g = load_golden(case)
     grid = tcs.get_backward_grid(cuda(g["disp_init"]), cuda(g["rel_T_inv"]), cuda(g["K"]), cuda(g["K_inv"]), cuda(g["baseline"]))
+    assert_exact(host(grid) == -1, g["backward_grid"] == -1, what="behind-the-camera entries vs reference")
     assert_close(host(grid), g["backward_grid"], rtol=1e-5, atol=1e-4, what="backward grid vs reference")
     assert_exact(host(grid), orc.backward_grid(g["disp_init"], g["rel_T_inv"], g["K"], g["K_inv"], g["baseline"]),
                  what="backward grid vs oracle (same arithmetic, bit for bit)")

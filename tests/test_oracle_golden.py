@@ -7,7 +7,8 @@ import pytest
 from conftest import assert_close, assert_exact, load_golden
 from oracle import tcs_oracle as orc
 
-CORR_CASES = ["corr_small", "corr_oddwidth"]
+CORR_CASES = ["corr_small", "corr_oddwidth", "corr_oddshift"]
+WARP_CASES = ["warp_small", "warp_forward_jump", "warp_backward_jump"]
 
 
 @pytest.mark.parametrize("case", CORR_CASES)
@@ -44,8 +45,9 @@ def test_argmax_and_cost_volume(case):
     assert_exact(main_cost, g["main_cost"], what=case + " main_cost")
 
 
-def test_warp_forward():
-    g = load_golden("warp_small")
+@pytest.mark.parametrize("case", WARP_CASES)
+def test_warp_forward(case):
+    g = load_golden(case)
     d, f, m = orc.warp(g["disp"], g["fmap"], g["rel_T"], g["K"], g["K_inv"], g["baseline"])
     assert_exact(m, g["warped_mask"], what="splat mask")
     assert_close(d, g["warped_disp"], rtol=1e-5, atol=1e-5, what="warped disparity")
@@ -54,9 +56,13 @@ def test_warp_forward():
     assert_close(cost, g["cost"], what="matching cost")
 
 
-def test_backward_grid_and_hidden_state_warp():
-    g = load_golden("warp_small")
+@pytest.mark.parametrize("case", WARP_CASES)
+def test_backward_grid_and_hidden_state_warp(case):
+    g = load_golden(case)
     grid = orc.backward_grid(g["disp_init"], g["rel_T_inv"], g["K"], g["K_inv"], g["baseline"])
+    assert_exact(grid == -1, g["backward_grid"] == -1, what="behind-the-camera entries (where(valid, uv, -1))")
+    if case == "warp_backward_jump":
+        assert 0.3 < (g["backward_grid"] == -1).mean() < 0.9          # the branch is not vacuous in this case
     assert_close(grid, g["backward_grid"], rtol=1e-5, atol=1e-4, what="backward grid")
     gg = g["grid0"]
     for i in range(3):
