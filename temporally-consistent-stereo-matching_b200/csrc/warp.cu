@@ -844,30 +844,16 @@ struct Hidden3Params {
     int blocks[3];       // pixel blocks of each level
 };
 
-__global__ void __launch_bounds__(256)
-warp_hidden3_kernel(const Hidden3Params p) {
-    const int b = blockIdx.z;
-    int bx = blockIdx.x, l = 0;
-    if (bx >= p.blocks[0]) { bx -= p.blocks[0]; l = 1; }
-    if (l == 1 && bx >= p.blocks[1]) { bx -= p.blocks[1]; l = 2; }
-    const int Hl = l == 0 ? p.H[0] : l == 1 ? p.H[1] : p.H[2];
-    const int Wl = l == 0 ? p.W[0] : l == 1 ? p.W[1] : p.W[2];
-    const int Cl = l == 0 ? p.C[0] : l == 1 ? p.C[1] : p.C[2];
-    const int c_begin = blockIdx.y * kSampleCh;
-    if (c_begin >= Cl) return;                                   // block-uniform
-    const int HWl = Hl * Wl;
-    const int i = bx * 256 + threadIdx.x;
-    if (i >= HWl) return;
-    const int H0 = p.H[0], W0 = p.W[0];
-    const float* g0 = p.grid + (size_t)b * 2 * H0 * W0;
+// The backward grid at level l for output pixel i: read (l = 0) or halved once / twice on the fly.  Not inlined: its
+// temporaries must not stretch the register allocation of the gather that follows (180 registers when inlined).
+__device__ __noinline__ float2 hidden3_grid(const float* __restrict__ g0, int l, int i, int H0, int W0, int H1, int W1, int Hl, int Wl) {
     float g[2];
     if (l == 0) {
         g[0] = __ldg(g0 + i);
         g[1] = __ldg(g0 + (size_t)H0 * W0 + i);
     } else {
         const int yo = i / Wl, xo = i - yo * Wl;
-        const int H1 = p.H[1], W1 = p.W[1];
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 2; ++c) {
             const float* plane = g0 + (size_t)c * H0 * W0;
             if (l == 1) {
@@ -882,12 +868,31 @@ warp_hidden3_kernel(const Hidden3Params p) {
             }
         }
     }
+    return make_float2(g[0], g[1]);
+}
+
+template <bool kFull>   // every level's channel count is a multiple of kSampleCh
+__global__ void __launch_bounds__(256)
+warp_hidden3_kernel(const Hidden3Params p) {
+    const int b = blockIdx.z;
+    int bx = blockIdx.x, l = 0;
+    if (bx >= p.blocks[0]) { bx -= p.blocks[0]; l = 1; }
+    if (l == 1 && bx >= p.blocks[1]) { bx -= p.blocks[1]; l = 2; }
+    const int Hl = l == 0 ? p.H[0] : l == 1 ? p.H[1] : p.H[2];
+    const int Wl = l == 0 ? p.W[0] : l == 1 ? p.W[1] : p.W[2];
+    const int Cl = l == 0 ? p.C[0] : l == 1 ? p.C[1] : p.C[2];
+    const int c_begin = blockIdx.y * kSampleCh;
+    if (c_begin >= Cl) return;                                   // block-uniform
+    const int HWl = Hl * Wl;
+    const int i = bx * 256 + threadIdx.x;
+    if (i >= HWl) return;
+    const float2 gxy = hidden3_grid(p.grid + (size_t)b * 2 * p.H[0] * p.W[0], l, i, p.H[0], p.W[0], p.H[1], p.W[1], Hl, Wl);
+    const float g[2] = {gxy.x, gxy.y};
     const float* net = l == 0 ? p.net[0] : l == 1 ? p.net[1] : p.net[2];
     float* out = l == 0 ? p.out[0] : l == 1 ? p.out[1] : p.out[2];
     const float* img_b = net + (size_t)b * Cl * HWl;
     float* out_b = out + (size_t)b * Cl * HWl;
-    if (Cl % kSampleCh == 0) sample_group<true>(img_b, g[0], g[1], out_b, Cl, Hl, Wl, HWl, i, c_begin);
-    else sample_group<false>(img_b, g[0], g[1], out_b, Cl, Hl, Wl, HWl, i, c_begin);
+    sample_group<kFull>(img_b, g[0], g[1], out_b, Cl, Hl, Wl, HWl, i, c_begin);
 }
 
 static size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
@@ -1086,7 +1091,10 @@ extern "C" int tcs_warp_hidden_states(const float* net0, const float* net1, cons
     long long bx = 0;
     for (int l = 0; l < 3; ++l) { p.blocks[l] = ceil_div(p.H[l] * p.W[l], 256); bx += p.blocks[l]; }
     dim3 g((unsigned)bx, groups, B);
-    warp_hidden3_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    if (C0 % kSampleCh == 0 && C1 % kSampleCh == 0 && C2 % kSampleCh == 0)
+        warp_hidden3_kernel<true><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    else
+        warp_hidden3_kernel<false><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     TCS_CHECK_LAUNCH("tcs_warp_hidden_states");
     return 0;
 }

@@ -4,9 +4,14 @@ Mirrors core/utils/geo_utils.py (warp :158-198, get_backward_grid :201-236, cal_
 :148-155) and core/utils/utils.py (bilinear_sampler :82-97) of the reference, plus the hidden-state warp
 loop of core/tc_stereo.py:159-163.  CUDA tensors only, inference only, no fallback.
 """
+import os
+
 import torch
 
 from . import _lib
+
+
+_HIDDEN_ONE_LAUNCH = os.environ.get("TCS_B200_HIDDEN_ONE_LAUNCH", "1") != "0"   # development aid: 0 chains the single ops
 
 
 def _stream():
@@ -208,7 +213,7 @@ def halve_grid(grid_xy):
 def warp_hidden_states(net_list, backward_grid):
     """ref: tc_stereo.py:159-163.  Sample each hidden-state level with the (progressively halved) grid.  The model's
     three-level case (each level half the previous one's size) is one launch; anything else chains the single ops."""
-    if len(net_list) == 3 and backward_grid.dim() == 4 and backward_grid.shape[1] == 2:
+    if len(net_list) == 3 and backward_grid.dim() == 4 and backward_grid.shape[1] == 2 and _HIDDEN_ONE_LAUNCH:
         B, _, H, W = backward_grid.shape
         dims = [(H, W), (H // 2, W // 2), (H // 2 // 2, W // 2 // 2)]
         if H >= 4 and W >= 4 and all(n.dim() == 4 and n.shape[0] == B and tuple(n.shape[2:]) == d for n, d in zip(net_list, dims)):

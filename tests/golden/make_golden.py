@@ -174,8 +174,8 @@ def main():
         # density > 0, floor-pooled levels), near points behind the current camera (invalid sources in the forward warp) and
         # behind the previous one (get_backward_grid's where(valid, uv, -1))
         corr_case(rcorr, "corr_oddshift", B=1, C=128, H=3, W=77, seed=99, correlated_shift=4)
-        warp_case(rutils, rgeo, "warp_forward_jump", B=2, C=64, H=12, W=16, seed=77, tz=1.2)
-        warp_case(rutils, rgeo, "warp_backward_jump", B=2, C=64, H=12, W=16, seed=78, tz=-1.2)
+        warp_case(rutils, rgeo, "warp_forward_jump", B=2, C=128, H=12, W=16, seed=77, tz=1.2)
+        warp_case(rutils, rgeo, "warp_backward_jump", B=2, C=128, H=12, W=16, seed=78, tz=-1.2)
 
 
 if __name__ == "__main__":
