@@ -726,7 +726,8 @@ backward_grid_kernel(const float* __restrict__ disp, const float* __restrict__ r
 constexpr int kSampleCh = 16;
 
 // One (output pixel, channel group) of the gather: img_b / out_b are the sample's [C,Hi,Wi] / [C,Ho*Wo] planes.
-template <bool kFull>   // kFull: C is a multiple of kSampleCh, no per-channel guards (keeps the loads batched)
+// kBatch: channels whose 4 corner loads are issued back to back before any is used.
+template <bool kFull, int kBatch = kSampleCh>   // kFull: C is a multiple of kSampleCh, no per-channel guards (keeps the loads batched)
 __device__ __forceinline__ void sample_group(const float* __restrict__ img_b, float gx, float gy, float* __restrict__ out_b,
                                              int C, int Hi, int Wi, int HWo, int i, int c_begin) {
     const float wm1 = (float)(Wi - 1), hm1 = (float)(Hi - 1);
@@ -751,26 +752,31 @@ __device__ __forceinline__ void sample_group(const float* __restrict__ img_b, fl
     const size_t plane_i = (size_t)Hi * Wi;
     const float* src = img_b + (size_t)c_begin * plane_i;
     float* dst = out_b + (size_t)c_begin * HWo + i;
-    float v[kSampleCh][4];
 #pragma unroll
-    for (int k = 0; k < kSampleCh; ++k) {
-        const bool live = kFull || (c_begin + k < C);
-        const float* s = src + (live ? (size_t)k * plane_i : 0);
-        v[k][0] = ldg_ordered_f1(s + o_nw);
-        v[k][1] = ldg_ordered_f1(s + o_ne);
-        v[k][2] = ldg_ordered_f1(s + o_sw);
-        v[k][3] = ldg_ordered_f1(s + o_se);
-    }
+    for (int k0 = 0; k0 < kSampleCh; k0 += kBatch) {
+        float v[kBatch][4];
 #pragma unroll
-    for (int k = 0; k < kSampleCh; ++k) {
-        if (!kFull && c_begin + k >= C) break;
-        // corners accumulate in the order nw, ne, sw, se; a corner outside the image contributes nothing
-        float r = 0.0f;
-        if (nw) r = __fmul_rn(v[k][0], w_nw);
-        if (ne) r = __fadd_rn(r, __fmul_rn(v[k][1], w_ne));
-        if (sw) r = __fadd_rn(r, __fmul_rn(v[k][2], w_sw));
-        if (se) r = __fadd_rn(r, __fmul_rn(v[k][3], w_se));
-        stg_stream_f1(dst + (size_t)k * HWo, r);
+        for (int j = 0; j < kBatch; ++j) {
+            const int k = k0 + j;
+            const bool live = kFull || (c_begin + k < C);
+            const float* s = src + (live ? (size_t)k * plane_i : 0);
+            v[j][0] = ldg_ordered_f1(s + o_nw);
+            v[j][1] = ldg_ordered_f1(s + o_ne);
+            v[j][2] = ldg_ordered_f1(s + o_sw);
+            v[j][3] = ldg_ordered_f1(s + o_se);
+        }
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const int k = k0 + j;
+            if (!kFull && c_begin + k >= C) break;
+            // corners accumulate in the order nw, ne, sw, se; a corner outside the image contributes nothing
+            float r = 0.0f;
+            if (nw) r = __fmul_rn(v[j][0], w_nw);
+            if (ne) r = __fadd_rn(r, __fmul_rn(v[j][1], w_ne));
+            if (sw) r = __fadd_rn(r, __fmul_rn(v[j][2], w_sw));
+            if (se) r = __fadd_rn(r, __fmul_rn(v[j][3], w_se));
+            stg_stream_f1(dst + (size_t)k * HWo, r);
+        }
     }
 }
 
@@ -892,7 +898,7 @@ warp_hidden3_kernel(const Hidden3Params p) {
     float* out = l == 0 ? p.out[0] : l == 1 ? p.out[1] : p.out[2];
     const float* img_b = net + (size_t)b * Cl * HWl;
     float* out_b = out + (size_t)b * Cl * HWl;
-    sample_group<kFull>(img_b, g[0], g[1], out_b, Cl, Hl, Wl, HWl, i, c_begin);
+    sample_group<kFull, kSampleCh / 2>(img_b, g[0], g[1], out_b, Cl, Hl, Wl, HWl, i, c_begin);   // 44 registers, 5 CTAs per SM
 }
 
 static size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }

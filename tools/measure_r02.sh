@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
     -c 900 --csv --log-file gpurun_out/r02_launches.csv $SMALL > gpurun_out/r02_ncu_launches.log 2>&1
 echo "launch list rc=$?"
 $SMALL > gpurun_out/r02_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:corr_lookup_r4x4o -s 300 -c 2 -o gpurun_out/r02_prof_lookup \
+ncu --set full --clock-control none --import-source on -k regex:corr_lookup_r4x4o -s 200 -c 2 -o gpurun_out/r02_prof_lookup \
     $SMALL > gpurun_out/r02_ncu_lookup.log 2>&1
 echo "lookup capture rc=$?"
 cat gpurun_out/r02_bench.json
