@@ -104,6 +104,53 @@ def _fused_warp(disp, fmap, relative_T, K, K_inv, baseline):
     return d, LazyWarpedFmap(cost, fmap.shape, rerun), m
 
 
+def strip_asserts(*modules):
+    """What `python -O` does, for the given (reference) modules only and at run time: every function and method defined
+    in them gets its code object re-compiled from the module's own source with the assert statements left out.
+
+    The reference guards its tensors with `assert not torch.isnan(x).any()` (geo_utils.py:14-15,26,52-53,211-235,
+    corr.py:77-78, tc_stereo.py:160, update.py:27-391: ten or more per GRU iteration); each one is a device -> host
+    synchronisation, which is what bounds the model's GPU time once the hot path is a handful of kernels (SURVEY.md
+    section 3.1).  Nothing else of the modules changes (same source, same line numbers, same globals).  Undone by
+    restore_asserts().  Returns the number of functions re-compiled."""
+    import inspect
+    import types
+
+    count = 0
+    for mod in modules:
+        src = inspect.getsource(mod)
+        top = compile(src, getattr(mod, "__file__", "<reference>"), "exec", optimize=1)
+        stripped = {}
+
+        def collect(code):
+            for c in code.co_consts:
+                if isinstance(c, types.CodeType):
+                    stripped[(c.co_name, c.co_firstlineno)] = c
+                    collect(c)
+        collect(top)
+
+        def functions(ns):
+            for v in list(vars(ns).values()):
+                f = v.__func__ if isinstance(v, (staticmethod, classmethod)) else v
+                if isinstance(f, types.FunctionType) and f.__module__ == mod.__name__:
+                    yield f
+                elif isinstance(v, type) and v.__module__ == mod.__name__ and ns is mod:
+                    yield from functions(v)
+        for f in functions(mod):
+            new = stripped.get((f.__code__.co_name, f.__code__.co_firstlineno))
+            if new is not None and new.co_freevars == f.__code__.co_freevars and new is not f.__code__:
+                _saved.setdefault(("code", id(f)), (f, f.__code__))
+                f.__code__ = new
+                count += 1
+    return count
+
+
+def restore_asserts():
+    for key in [k for k in _saved if k[0] == "code"]:
+        f, code = _saved.pop(key)
+        f.__code__ = code
+
+
 def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=None, stencils=None, fuse_cost=False):
     """tc_stereo_module: the imported `core.tc_stereo`.  Returns the dict of names that were replaced.
 

@@ -97,3 +97,28 @@ def test_kernels_refuse_tensors_that_require_grad():
     for check in (lambda: corr._check_fmap("fmap1", t), lambda: geo._f32c("disp", t)):
         with pytest.raises((RuntimeError, TypeError)):                  # TypeError: CPU tensor is refused first
             check()
+
+
+@needs_ref
+def test_strip_asserts_is_python_O_for_the_reference_modules_only():
+    """tcs_b200.strip_asserts re-compiles the reference's functions without their assert statements (each one a
+    device -> host sync on the GPU) and restore_asserts puts the original code objects back; results are unchanged."""
+    import dis
+    import tcs_b200
+    ref = ref_model.load()
+    ref_model.use_cpu_splat(ref)
+    has_assert = lambda f: any(i.opname == "LOAD_ASSERTION_ERROR" for i in dis.get_instructions(f))
+    targets = [ref.geo.get_backward_grid, ref.update.BasicMultiUpdateBlock.forward, ref.corr.CorrBlock1D.argmax_disp, ref.geo.disp2depth]
+    assert all(has_assert(f) for f in targets)
+    model = ref_model.make_model()
+    imgs, K, poses, base = ref_model.synthetic_sequence(2, 64, 96)
+    want = ref_model.run_sequence(model, imgs, K, poses, base, iters=2)
+    try:
+        n = tcs_b200.strip_asserts(ref.geo, ref.update, ref.corr, ref.tc_stereo)
+        assert n >= 40 and not any(has_assert(f) for f in targets)
+        assert has_assert(ref.softsplat.softsplat)                     # a module that was not named keeps its asserts
+        got = ref_model.run_sequence(model, imgs, K, poses, base, iters=2)
+    finally:
+        tcs_b200.restore_asserts()
+    assert all(has_assert(f) for f in targets)
+    assert all(torch.equal(a["flow"], b["flow"]) and torch.equal(a["flow_q"], b["flow_q"]) for a, b in zip(got, want))
