@@ -761,3 +761,36 @@ def test_hidden_state_warp_one_launch_is_bit_identical_to_the_chain(tcs, B, H, W
     for l in range(3):
         assert got[l].shape == want[l].shape
         assert torch.equal(got[l], want[l]), "level %d differs" % l
+
+
+def test_second_device_in_the_same_process(tcs):
+    """Kernel attributes (dynamic shared memory above 48 KB, carve-out hints) are per device: the build (fused and two-step),
+    the warp (both formulations), the lookups (pyramid, fused encode, tensor-core alternate) must work on cuda:1 after they ran
+    on cuda:0 in one process, and give the same bits there."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    g = torch.Generator().manual_seed(8)
+    f1 = torch.randn(1, 256, 6, 320, generator=g)
+    f2 = torch.randn(1, 256, 6, 320, generator=g)
+    s1 = torch.randn(1, 256, 6, 64, generator=g)
+    coords = make_coords(1, 6, 320, 5)
+    K, Kinv, T, _, base = camera(1, 6, 64, 2)
+    disp = 0.5 + torch.rand(1, 1, 6, 64, generator=g) * 4
+    w = torch.randn(64, 36, generator=g)
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        d = torch.device(dev)
+        blk = tcs.CorrBlock1D(f1.to(d), f2.to(d))                                   # two-step build (W2 > 240)
+        small = tcs.CorrBlock1D(f1[..., :240].contiguous().to(d), f2[..., :240].contiguous().to(d))   # fused build
+        alt = tcs.CorrBlock1D(f1.to(d), f2.to(d), mode="alternate")
+        res = [blk(coords.to(d)), small(coords[..., :240].contiguous().to(d)), alt(coords.to(d)), blk.lookup_encoded(coords.to(d), w.to(d))]
+        cam = [torch.from_numpy(x).to(d) for x in (T, K, Kinv, base)]
+        for det in (False, True):
+            res += [x for x in tcs.warp_with_cost(disp.to(d), s1.to(d), *cam, cur_fmap=s1.flip(3).contiguous().to(d), deterministic=det) if x is not None]
+        torch.cuda.synchronize(d)
+        outs.append([r.cpu() for r in res])
+    for i, (a, b, c) in enumerate(zip(*outs)):
+        if i in (6, 8):          # warped disparity / features of the atomic scatter: unordered adds
+            assert torch.allclose(a, b, rtol=1e-5, atol=2e-6) and torch.allclose(a, c, rtol=1e-5, atol=2e-6)
+        else:
+            assert torch.equal(a, b) and torch.equal(a, c), "output %d differs between devices" % i
