@@ -385,6 +385,41 @@ def test_real_model_single_pair_540x960(ref, tcs, model):
             assert rep[name][k] <= max(ABS_GATE_FIRST, 3 * floor[k]), "%s %s drift %.3g vs floor %.3g" % (name, k, rep[name][k], floor[k])
 
 
+def test_real_model_with_graphed_iteration_modules(ref, tcs, model):
+    """the four learned blocks of the GRU iteration (tc_stereo.py:175-200) replayed as CUDA graphs
+    (`tcs_b200.graph_modules`), TCStereo.forward itself unmodified.  A first frame and a temporal frame at 8 iterations, and a
+    second pass over both (replays of graphs captured in the first): bit-identical to the same drop-in run eagerly, i.e. the
+    capture changes launches, not arithmetic; and within the drift gate of the reference."""
+    imgs, K, poses, base = ref_model.synthetic_sequence(2, 480, 640, device="cuda")
+    want = ref_model.run_sequence(model, imgs, K, poses, base, 8)
+    _, floor = measure_floors(ref, lambda: ref_model.run_sequence(model, imgs, K, poses, base, 8), want)
+    kw = {"fuse_cost": True, "stencils": True}
+    with installed(tcs, ref, **kw):
+        eager = ref_model.run_sequence(model, imgs, K, poses, base, 8)
+        eager = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in o.items()} for o in eager]
+        handles = tcs.graph_modules(model)
+        try:
+            first = ref_model.run_sequence(model, imgs, K, poses, base, 8)
+            first = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in o.items()} for o in first]
+            again = ref_model.run_sequence(model, imgs, K, poses, base, 8)
+            assert all(h.replays >= 2 * 2 * 8 for h in handles.values()), {n: h.replays for n, h in handles.items()}
+            assert all(len(h.captured) <= 3 for h in handles.values()), {n: len(h.captured) for n, h in handles.items()}
+        finally:
+            tcs.ungraph_modules(model)
+    rep = {"floor": floor, "graphed": [drift(a, b) for a, b in zip(again, want)],
+           "graphed_vs_eager_max_abs_flow": [float((a["flow"] - b["flow"]).abs().max()) for a, b in zip(again, eager)]}
+    REPORT["graphed_modules_2x480x640_8iters"] = rep
+    print("\ngraphed iteration modules:", json.dumps(rep))
+    for t in range(2):
+        for a in (first, again):
+            assert torch.equal(a[t]["flow"], eager[t]["flow"]) and torch.equal(a[t]["flow_q"], eager[t]["flow_q"]), "frame %d: graphs changed the result" % t
+        for k in ("flow_q", "flow"):
+            fl = max(f[k] for f in floor[:t + 1])
+            assert rep["graphed"][t][k] <= max(ABS_GATE_FIRST if t == 0 else ABS_GATE_TEMPORAL, 3 * fl)
+    import dis
+    assert any(i.opname == "LOAD_ASSERTION_ERROR" for i in dis.get_instructions(ref.update.BasicMultiUpdateBlock.forward)), "asserts restored"
+
+
 def test_dropin_refuses_training(ref, tcs):
     """Gradients flow through corr / warp in the reference; the kernels have no backward, so the drop-in must refuse
     rather than silently cut them."""

@@ -9,6 +9,7 @@ BASELINE config 1 (single 540x960 pair padded to 544x960, batch 1, 32 GRU iterat
   dropin               tcs_b200.install(core.tc_stereo)
   dropin fused         + fuse_cost, fuse_motion_encoder, stencils
   dropin fused -O      + strip_asserts
+  ... + graphed iteration modules   + tcs_b200.graph_modules(model): the four learned blocks of the GRU iteration as CUDA graphs
 cuDNN in its default mode (TF32 allowed), as a user of the reference would run it.  Test infrastructure (imports oracle/).
 """
 import argparse
@@ -63,15 +64,20 @@ def main():
     out = {"config": {"height": args.height, "width": args.width, "iters": args.iters, "batch": 1, "reps": args.reps,
                       "gpu": torch.cuda.get_device_name(0)}}
     fused = dict(fuse_cost=True, fuse_motion_encoder=ref.update, stencils=ref.update)
-    for name, kw, strip in (("reference", None, False), ("reference -O", None, True), ("dropin", {}, False),
-                            ("dropin fused", fused, False), ("dropin fused -O", fused, True)):
+    for name, kw, strip, graphs in (("reference", None, False, False), ("reference -O", None, True, False), ("dropin", {}, False, False),
+                                    ("dropin fused", fused, False, False), ("dropin fused -O", fused, True, False),
+                                    ("dropin fused -O + graphed iteration modules", fused, True, True)):
         if strip:
             tcs_b200.strip_asserts(*mods)
         if kw is not None:
             tcs_b200.install(ref.tc_stereo, **kw)
+        if graphs:
+            tcs_b200.graph_modules(model, strip=False)
         try:
             out[name] = frames()
         finally:
+            if graphs:
+                tcs_b200.ungraph_modules(model, restore=False)
             if kw is not None:
                 tcs_b200.uninstall(ref.tc_stereo, ref.update)
             if strip:
