@@ -23,6 +23,7 @@ from .corr import LazyLookup
 
 GRAPHED = ("update_block", "disp_grad_refine", "disp_refine", "hiddenstate_update")
 _pool = None
+_static_outputs = set()      # id() of every graph's output tensors: a replay rewrites them WITHOUT touching their version counter
 
 
 def _flatten(obj, tensors):
@@ -91,6 +92,9 @@ class GraphedForward:
             raise RuntimeError("graph_modules: %s.forward cannot be captured (%s).  It must not synchronise or build tensors on the host: "
                                "install the drop-in with stencils=core.update and let graph_modules strip the asserts." % (self.name, e)) from e
         c.last = [None] * len(tensors)
+        keep = []
+        _flatten(c.outputs, keep)
+        _static_outputs.update(id(t) for t in keep)               # (the graph keeps them alive, so the ids stay theirs)
         return c
 
     def __call__(self, *args, **kwargs):
@@ -104,8 +108,9 @@ class GraphedForward:
             if src.data_ptr() == dst.data_ptr():
                 continue                                          # the caller handed the static buffer itself back
             seen = c.last[i]
-            if seen is not None and seen[0] is src and seen[1] == src._version:
-                continue                                          # same tensor object, unmodified since it was copied in
+            if seen is not None and seen[0] is src and seen[1] == src._version and id(src) not in _static_outputs:
+                continue                                          # same tensor object, unmodified since it was copied in (another
+                                                                  # graph's output is the same object every time but not the same data)
             dst.copy_(src)
             c.last[i] = (src, src._version)                       # keeps it alive: its storage cannot be recycled under the same identity
         c.graph.replay()
