@@ -22,7 +22,6 @@ import torch
 from .corr import LazyLookup
 
 GRAPHED = ("update_block", "disp_grad_refine", "disp_refine", "hiddenstate_update")
-_pool = None
 _static_outputs = set()      # id() of every graph's output tensors: a replay rewrites them WITHOUT touching their version counter
 
 
@@ -70,7 +69,6 @@ class GraphedForward:
         self.replays = 0
 
     def _capture(self, spec, tensors):
-        global _pool
         if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
             raise RuntimeError("graph_modules is inference only: call the model under torch.no_grad()")
         c = _Captured()
@@ -82,11 +80,12 @@ class GraphedForward:
             for _ in range(2):
                 self.forward(*_rebuild(spec, c.inputs)[0], **_rebuild(spec, c.inputs)[1])
         torch.cuda.current_stream().wait_stream(side)
-        if _pool is None:
-            _pool = torch.cuda.graph_pool_handle()
+        # One private memory pool PER GRAPH.  In a shared pool a later capture's OUTPUT may be given a block that an earlier
+        # capture used for an intermediate; the model replays the graphs in an order of its own (disp_refine's up_mask is read
+        # after hiddenstate_update ran again), so the earlier graph would overwrite it: measured, the mask came back as garbage.
         c.graph = torch.cuda.CUDAGraph()
         try:
-            with torch.cuda.graph(c.graph, pool=_pool):
+            with torch.cuda.graph(c.graph):
                 c.outputs = self.forward(*args, **kwargs)
         except RuntimeError as e:
             raise RuntimeError("graph_modules: %s.forward cannot be captured (%s).  It must not synchronise or build tensors on the host: "
