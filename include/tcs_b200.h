@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCS_ABI_VERSION 6
+#define TCS_ABI_VERSION 7
 
 /* argument errors (negative); CUDA launch errors are returned as positive cudaError_t values */
 #define TCS_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported combination */
@@ -237,6 +237,18 @@ int tcs_disp_propagate(const float* grad, const float* disp, float* prop, float*
  * the 3x3 zero-padded neighbours of (factor *) flow.  factor 2, 4 or 8; scale != 0 multiplies flow by factor. */
 int tcs_convex_upsample(const float* flow, const float* mask, float* out, int N, int D, int H, int W,
                         int factor, int scale, void* stream);
+
+/* ---- (6) "next" row: input stems of the disparity completion network ------------------ */
+
+/* ref: core/update.py:312-323,375-378 (DisparityCompletor: conv_disp_stem, conv_cost_stem, conv_mask_stem, the cat and
+ * conv_disp_fuse): a per-pixel 3 -> 64 perceptron, eight 1x1 convolutions in the reference, one kernel here.
+ *   disp, cost, mask [N,1,H,W] fp32 (the stems' inputs, i.e. disp/10 and mask-0.5 as update.py:373-374 prepares them);
+ *   weights: tcs_completor_stems_weight_floats() floats, 16-byte aligned, packed in this order, matrices TRANSPOSED to
+ *   [input][output]: w1d[64] b1d[64] W2d[64][64] b2d[64] | w1c[32] b1c[32] W2c[32][32] b2c[32] | w1m[32] b1m[32] W2m[32][32]
+ *   b2m[32] | W3[128][128] b3[128] | W4[128][64] b4[64];   out [N,64,H,W] fp32. */
+int tcs_completor_stems_weight_floats(void);
+int tcs_completor_stems(const float* disp, const float* cost, const float* mask, const float* weights, float* out,
+                        int N, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

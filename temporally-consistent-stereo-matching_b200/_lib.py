@@ -14,7 +14,7 @@ PREC_BF16, PREC_BF16X3, PREC_FP16, PREC_FP16X3 = 0, 1, 2, 3
 PRECISIONS = {"bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16, "fp16x3": PREC_FP16X3}
 MAX_LEVELS = 4
 MAX_RADIUS = 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -47,6 +47,8 @@ SIGNATURES = {
     "tcs_disp_gradient_xy": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "tcs_disp_grad_candidates": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tcs_disp_propagate": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "tcs_completor_stems_weight_floats": (_i, []),
+    "tcs_completor_stems": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "tcs_convex_upsample": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
 }
 

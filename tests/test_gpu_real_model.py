@@ -429,3 +429,33 @@ def test_dropin_refuses_training(ref, tcs):
         tcs.CorrBlock1D(f, f)
     with torch.no_grad():
         tcs.CorrBlock1D(f, f)
+
+
+def test_completor_stems_one_kernel(ref, tcs, model):
+    """SURVEY.md section 8f rank 3's other half: the four input stems of DisparityCompletor (update.py:312-323,375-378; eight 1x1
+    convolutions, four ReLUs and a cat) as one kernel, under the completor's own unmodified forward.  Against the
+    reference's layers in true fp32 (this module's fixture switches TF32 off): 1e-5 rel + 2e-6 abs; the completor's outputs
+    with the stems fused: the same gate on disp_init (x10 values), and the patch must come off cleanly."""
+    comp = model.disp_completor
+    g = torch.Generator().manual_seed(3)
+    N, H, W = 2, 120, 160
+    disp = (torch.rand(N, 1, H, W, generator=g) * 3).cuda()
+    cost = (torch.rand(N, 1, H, W, generator=g) * 2 - 1).cuda()
+    mask = ((torch.rand(N, 1, H, W, generator=g) > 0.3).float() - 0.5).cuda()
+    with torch.no_grad():
+        want = comp.conv_disp_fuse(torch.cat((comp.conv_disp_stem(disp), comp.conv_cost_stem(cost), comp.conv_mask_stem(mask)), dim=1))
+        got = tcs.completor_stems(disp, cost, mask, tcs.pack_stem_weights(comp))
+        assert_close(host(got), host(want), rtol=1e-5, atol=2e-6, what="fused completor stems vs the reference's eight convolutions")
+        ctx = [torch.randn(N, 128, H >> l, W >> l, generator=g).cuda() for l in range(3)]
+        ref_out = comp(disp * 10, cost, mask + 0.5, ctx)
+        h = tcs.fuse_completor_stems(comp)
+        try:
+            fused_out = comp(disp * 10, cost, mask + 0.5, ctx)
+            assert h.fused_calls == 1
+            # a marker used any other way turns into the tensor the original layers give
+            assert torch.equal(comp.conv_disp_stem(disp) + 0, h.original["conv_disp_stem"](disp))
+        finally:
+            tcs.unfuse_completor_stems(comp)
+        assert "forward" not in comp.conv_disp_fuse.__dict__
+        for a, b, name in zip(fused_out[:3], ref_out[:3], ("disp_completed", "disp_mono", "w")):
+            assert_close(host(a), host(b), rtol=1e-4, atol=1e-4, what="completor output %s with fused stems" % name)

@@ -66,16 +66,21 @@ def main():
     fused = dict(fuse_cost=True, fuse_motion_encoder=ref.update, stencils=ref.update)
     for name, kw, strip, graphs in (("reference", None, False, False), ("reference -O", None, True, False), ("dropin", {}, False, False),
                                     ("dropin fused", fused, False, False), ("dropin fused -O", fused, True, False),
-                                    ("dropin fused -O + graphed iteration modules", fused, True, True)):
+                                    ("dropin fused -O + graphed iteration modules", fused, True, True),
+                                    ("dropin fused -O + graphed iteration modules + fused completor stems", fused, True, "stems")):
         if strip:
             tcs_b200.strip_asserts(*mods)
         if kw is not None:
             tcs_b200.install(ref.tc_stereo, **kw)
         if graphs:
             tcs_b200.graph_modules(model, strip=False)
+        if graphs == "stems":
+            tcs_b200.fuse_completor_stems(model.disp_completor)
         try:
             out[name] = frames()
         finally:
+            if graphs == "stems":
+                tcs_b200.unfuse_completor_stems(model.disp_completor)
             if graphs:
                 tcs_b200.ungraph_modules(model, restore=False)
             if kw is not None:
