@@ -56,6 +56,13 @@ for key in ("sequence_3x480x640_8iters", "sequence_3x480x640_32iters"):
     for c in CFG:
         out.append("| `%s` | " % c + " | ".join("%s / %s" % (f(t["flow_q"]), f(t["flow"])) for t in v[c]) + " |")
     out.append("")
+if "graphed_modules_2x480x640_8iters" in d:
+    v = d["graphed_modules_2x480x640_8iters"]
+    out += ["## `graph_modules`: the GRU iteration's learned blocks replayed as CUDA graphs (2 frames of 480x640, 8 iterations, second pass = replays only)", "",
+            "| | frame 0 | frame 1 |", "|---|---|---|",
+            "| floor (largest of 4 noise samples) | " + " | ".join("%s / %s" % (f(t["flow_q"]), f(t["flow"])) for t in v["floor"]) + " |",
+            "| graphed drop-in vs the reference | " + " | ".join("%s / %s" % (f(t["flow_q"]), f(t["flow"])) for t in v["graphed"]) + " |",
+            "| graphed vs the same drop-in run eagerly, max abs d flow | " + " | ".join(f(x) for x in v["graphed_vs_eager_max_abs_flow"]) + " |", ""]
 w = {k: v for k, v in d.items() if k.startswith("warp_vs_reference_kernel")}
 if w:
     out += ["## Row a8: `tcs_warp_forward` against the reference's own splat kernel (full size, C = 256)", "",
