@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCS_ABI_VERSION 7
+#define TCS_ABI_VERSION 8
 
 /* argument errors (negative); CUDA launch errors are returned as positive cudaError_t values */
 #define TCS_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported combination */
@@ -74,10 +74,13 @@ int tcs_corr_prepass_kblocked(const float* fmap, void* hi, void* lo,
  *   a_hi,a_lo  [B,H,W1,C] operands of the left image  (lo nullable unless prec is *X3)
  *   b_hi,b_lo  [B,H,W2,C] operands of the right image
  *   lvl[l]     [B,H,W1,W2>>l] fp32 (out), l < num_levels <= 4; every level pointer 16-byte aligned
+ *   W2_pitch   0 (dense rows) or the row pitch of level 0 in floats (level l: W2_pitch >> l), a multiple of 16 above W2
+ *              with W2 % 8 == 0: the columns past W2 of every level are written as exact zeros, which puts widths like the
+ *              KITTI shape's 312 on tcs_corr_lookup's predicate-free path (rows that start on 16-byte boundaries)
  * Requires C % 64 == 0, W1 >= 1, W2 >= 8. */
 int tcs_corr_build(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                    float* lvl0, float* lvl1, float* lvl2, float* lvl3,
-                   int B, int H, int W1, int W2, int C, int num_levels, int prec, void* stream);
+                   int B, int H, int W1, int W2, int C, int num_levels, int prec, int W2_pitch, void* stream);
 
 /* The same result in ONE kernel straight from the fp32 NCHW feature maps: normalisation, the 16-bit hi/lo
  * split and the K-major operand layout happen on chip, so the operands never make a round trip through HBM
@@ -105,10 +108,12 @@ int tcs_corr_build_fp32(const float* a_n32, const float* b_n32,
  *           boundary past its end (the Python wrapper pads)
  *   coords  fp32, x coordinate of pixel (b,h,w1) at  coords[b*coords_bstride + h*W1 + w1]
  *           (coords_bstride lets the caller pass channel 0 of a [B,2,H,W1] tensor)
- *   out     [B, num_levels*(2r+1), H, W1] fp32 */
+ *   out     [B, num_levels*(2r+1), H, W1] fp32
+ *   W2_pitch  0, or the row pitch the levels were built with (see tcs_corr_build; 4 levels and radius 4 only).  The
+ *           sampling arithmetic (normalisation by W2 - 1, zero padding from W2 on) always uses W2. */
 int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                     const float* coords, long long coords_bstride, float* out,
-                    int B, int H, int W1, int W2, int num_levels, int radius, void* stream);
+                    int B, int H, int W1, int W2, int num_levels, int radius, int W2_pitch, void* stream);
 
 /* Lookup fused with the motion encoder's first layer: out = [relu](W . taps + bias), the 36 taps never leave
  * the registers.  ref: core/update.py:97,104 (BasicMotionEncoder.convc1, a 1x1 Conv2d(36, 64), then F.relu)
@@ -118,7 +123,7 @@ int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float* lvl2, con
 int tcs_corr_lookup_encode(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                            const float* coords, long long coords_bstride, const float* weight, const float* bias,
                            float* out, int B, int H, int W1, int W2, int num_levels, int radius, int Cout, int relu,
-                           void* stream);
+                           int W2_pitch, void* stream);
 
 /* ---- (3) alternate (on-the-fly) lookup ---------------------------------------------------------- */
 

@@ -70,16 +70,28 @@ def normalized_operands(fmap, precision="bf16x3", want_hi=True, want_lo=None, wa
     return hi, lo, n32
 
 
-def alloc_pyramid(B, H, W1, W2, num_levels, device):
+def level_pitch(W2, num_levels=4, radius=4):
+    """Row pitch (floats) of level 0 for a W2-wide volume: W2 itself, or the next multiple of 16 when that puts the rows of
+    levels 0 and 2 on 16-byte boundaries (the lookup's predicate-free kernels; KITTI's 312 -> 320).  Needs W2 % 8 == 0 (no
+    pooled entry then mixes real and padding columns) and the standard 4 levels / radius 4."""
+    if W2 % 16 != 0 and W2 % 8 == 0 and num_levels == 4 and radius == 4 and os.environ.get("TCS_B200_LEVEL_PITCH", "1") != "0":
+        return (W2 + 15) & ~15
+    return W2
+
+
+def alloc_pyramid(B, H, W1, W2, num_levels, device, pitch=None, zero=False):
     """One flat fp32 buffer holding every level [B,H,W1,W2>>l], each 128-byte aligned (the lookup's 32-byte
-    loads need 32) and padded so the lookup may read up to the next 16-byte boundary past a level's end."""
-    sizes = [B * H * W1 * (W2 >> l) for l in range(num_levels)]
+    loads need 32) and padded so the lookup may read up to the next 16-byte boundary past a level's end.
+    pitch: row pitch of level 0 (level l: pitch >> l); the returned levels are then views of the first W2>>l columns of each
+    row, and whoever fills them must leave zeros in the rest (tcs_corr_build does; zero=True for copies)."""
+    P = pitch or W2
+    sizes = [B * H * W1 * (P >> l) for l in range(num_levels)]
     offs, total = [], 0
     for s in sizes:
         offs.append(total)
         total += (_pad16(s) + 4 + 31) & ~31
-    flat = torch.empty(total, dtype=torch.float32, device=device)
-    levels = [flat[o:o + s].view(B, H, W1, W2 >> l) for l, (o, s) in enumerate(zip(offs, sizes))]
+    flat = (torch.zeros if (zero and P != W2) else torch.empty)(total, dtype=torch.float32, device=device)
+    levels = [flat[o:o + s].view(B, H, W1, P >> l)[..., :W2 >> l] for l, (o, s) in enumerate(zip(offs, sizes))]
     return flat, levels
 
 
@@ -87,7 +99,7 @@ FUSED_MAX_W2 = 240
 FUSED_MAX_W1 = 256
 
 
-def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3", fused=None):
+def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3", fused=None, pitch=None):
     """All pyramid levels of the 1-D all-pairs cosine correlation (ref: corr.py:54-62 + :15-23).
 
     precision: 'bf16' | 'bf16x3' | 'fp16' | 'fp16x3' (tcgen05 tensor cores) or 'fp32' (CUDA cores).
@@ -102,7 +114,14 @@ def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3", fused=None):
         raise ValueError("fmap1 %s and fmap2 %s disagree on B, C or H" % (tuple(fmap1.shape), tuple(fmap2.shape)))
     if not 1 <= num_levels <= _lib.MAX_LEVELS:
         raise ValueError("num_levels must be in [1, %d]" % _lib.MAX_LEVELS)
-    flat, levels = alloc_pyramid(B, H, W1, W2, num_levels, fmap1.device)
+    if precision != "fp32" and precision not in _lib.PRECISIONS:
+        raise ValueError("unknown precision %r" % (precision,))
+    fits = 8 <= W2 <= FUSED_MAX_W2 and W1 <= FUSED_MAX_W1 and W1 % 4 == 0 and W2 % 4 == 0 and C % 32 == 0
+    if fused is None:
+        fused = fits and precision != "fp32" and os.environ.get("TCS_B200_FUSED_BUILD", "1") != "0"
+    if fused or precision == "fp32":
+        pitch = None                                # only the pre-pass + tcgen05 build writes pitched rows
+    flat, levels = alloc_pyramid(B, H, W1, W2, num_levels, fmap1.device, pitch=pitch)
     ptrs = [levels[l].data_ptr() if l < num_levels else None for l in range(4)]
     with torch.cuda.device(fmap1.device):
         if precision == "fp32":
@@ -110,11 +129,6 @@ def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3", fused=None):
             _, _, b32 = normalized_operands(fmap2, want_hi=False, want_n32=True)
             _lib.call("tcs_corr_build_fp32", a32.data_ptr(), b32.data_ptr(), *ptrs, B, H, W1, W2, C, num_levels, _stream())
         else:
-            if precision not in _lib.PRECISIONS:
-                raise ValueError("unknown precision %r" % (precision,))
-            fits = 8 <= W2 <= FUSED_MAX_W2 and W1 <= FUSED_MAX_W1 and W1 % 4 == 0 and W2 % 4 == 0 and C % 32 == 0
-            if fused is None:
-                fused = fits and os.environ.get("TCS_B200_FUSED_BUILD", "1") != "0"
             if fused:
                 _lib.call("tcs_corr_build_fused", fmap1.data_ptr(), fmap2.data_ptr(), *ptrs, B, H, W1, W2, C, num_levels,
                           _lib.PRECISIONS[precision], _stream())
@@ -123,7 +137,7 @@ def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3", fused=None):
             b_hi, b_lo, _ = normalized_operands(fmap2, precision)
             _lib.call("tcs_corr_build", a_hi.data_ptr(), a_lo.data_ptr() if a_lo is not None else None,
                       b_hi.data_ptr(), b_lo.data_ptr() if b_lo is not None else None, *ptrs,
-                      B, H, W1, W2, C, num_levels, _lib.PRECISIONS[precision], _stream())
+                      B, H, W1, W2, C, num_levels, _lib.PRECISIONS[precision], pitch or 0, _stream())
     return flat, levels
 
 
@@ -196,8 +210,11 @@ class CorrBlock1D:
         self.device = fmap1.device
         self.fmap1 = fmap1          # what the build read (the model's fmap1 itself when it is fp32 and contiguous)
         self._cost_volume = None
+        self.W2p = self.W2
         if self.mode == "pyramid":
-            self._flat, self._levels = build_pyramid(fmap1, fmap2, num_levels, self.precision)
+            self._flat, self._levels = build_pyramid(fmap1, fmap2, num_levels, self.precision,
+                                                     pitch=level_pitch(self.W2, num_levels, radius))
+            self.W2p = self._levels[0].stride(2)            # the row pitch the build really used (== W2 when dense)
             self._fmaps = None
         else:
             self._flat, self._levels = None, None
@@ -230,7 +247,8 @@ class CorrBlock1D:
         self.C, self.fmap1 = None, None
         self.num_levels, self.radius, self.thres = len(levels), radius, 0.2
         self.precision, self.mode, self.device = "external", "pyramid", lv0.device
-        self._flat, self._levels = alloc_pyramid(self.B, self.H, self.W1, self.W2, self.num_levels, self.device)
+        self.W2p = level_pitch(self.W2, self.num_levels, radius)
+        self._flat, self._levels = alloc_pyramid(self.B, self.H, self.W1, self.W2, self.num_levels, self.device, pitch=self.W2p, zero=True)
         for dst, src in zip(self._levels, levels):
             if tuple(dst.shape) != tuple(src.shape):
                 raise ValueError("level shape %s, expected %s" % (tuple(src.shape), tuple(dst.shape)))
@@ -251,10 +269,19 @@ class CorrBlock1D:
         return self.get_cost_volume()
 
     def _level0(self):
+        """Level 0 for argmax_disp / get_cost_volume, which may treat a pitched level as a dense volume `pitch` wide: its
+        zero columns past W2 are masked like every other w2 > w1 — as long as no w1 reaches them (W1 <= W2, the model's
+        case); otherwise a dense copy."""
         if self._levels is not None:
-            return self._levels[0]
+            lv = self._levels[0]
+            return lv.contiguous() if (lv.stride(2) != self.W2 and self.W1 > self.W2) else lv
         _, levels = build_pyramid(self._fmaps[0], self._fmaps[1], 1, self.precision)
         return levels[0]
+
+    def _pitch_arg(self):
+        """The row pitch for the C-ABI (0 = dense), read off the level-0 view so that a replaced level is seen."""
+        p = self._levels[0].stride(2)
+        return 0 if p == self.W2 else p
 
     # -- reference methods ----------------------------------------------------------------------------
     def __call__(self, coords):
@@ -266,7 +293,7 @@ class CorrBlock1D:
             if self.mode == "pyramid":
                 ptrs = [self._levels[l].data_ptr() if l < self.num_levels else None for l in range(4)]
                 _lib.call("tcs_corr_lookup", *ptrs, cptr, cstride, out.data_ptr(),
-                          self.B, self.H, self.W1, self.W2, self.num_levels, self.radius, _stream())
+                          self.B, self.H, self.W1, self.W2, self.num_levels, self.radius, self._pitch_arg(), _stream())
             elif self._alt_tc:
                 _lib.call("tcs_corr_lookup_alt_tc", self._a_hi.data_ptr(), self._a_lo.data_ptr() if self._a_lo is not None else None,
                           self._b_hi.data_ptr(), self._b_lo.data_ptr() if self._b_lo is not None else None, cptr, cstride,
@@ -296,7 +323,7 @@ class CorrBlock1D:
         ptrs = [self._levels[l].data_ptr() for l in range(4)]
         with torch.cuda.device(self.device):
             _lib.call("tcs_corr_lookup_encode", *ptrs, cptr, cstride, w.data_ptr(), bb.data_ptr() if bb is not None else None,
-                      out.data_ptr(), self.B, self.H, self.W1, self.W2, 4, 4, cout, 1 if relu else 0, _stream())
+                      out.data_ptr(), self.B, self.H, self.W1, self.W2, 4, 4, cout, 1 if relu else 0, self._pitch_arg(), _stream())
         return out
 
     def lazy(self, coords):
@@ -308,10 +335,11 @@ class CorrBlock1D:
         """ref: corr.py:25-31,64-65.  [B, W2, H, W1], zero where w2 > w1.  Built on first use."""
         if self._cost_volume is None:
             lvl0 = self._level0()
-            out = torch.empty((self.B, self.W2, self.H, self.W1), dtype=torch.float32, device=self.device)
+            P = lvl0.stride(2)                      # a pitched level 0 is a dense volume P wide whose columns past W2 are zero
+            out = torch.empty((self.B, P, self.H, self.W1), dtype=torch.float32, device=self.device)
             with torch.cuda.device(self.device):
-                _lib.call("tcs_corr_cost_volume", lvl0.data_ptr(), out.data_ptr(), self.B, self.H, self.W1, self.W2, _stream())
-            self._cost_volume = out
+                _lib.call("tcs_corr_cost_volume", lvl0.data_ptr(), out.data_ptr(), self.B, self.H, self.W1, P, _stream())
+            self._cost_volume = out if P == self.W2 else out[:, :self.W2].contiguous()
         return self._cost_volume
 
     def argmax_disp(self, thres=0.3):
@@ -319,8 +347,9 @@ class CorrBlock1D:
         lvl0 = self._level0()
         outs = [torch.empty((self.B, 1, self.H, self.W1), dtype=torch.float32, device=self.device) for _ in range(3)]
         with torch.cuda.device(self.device):
+            # (a pitched level 0: its zero columns past W2 are all masked, w2 >= W2 > w1, like every other w2 > w1)
             _lib.call("tcs_corr_argmax", lvl0.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
-                      self.B, self.H, self.W1, self.W2, float(thres), _stream())
+                      self.B, self.H, self.W1, lvl0.stride(2), float(thres), _stream())
         return tuple(outs)
 
     @staticmethod

@@ -205,9 +205,17 @@ static int make_operand_map(CUtensorMap* tm, const void* base, int BH, int W, in
 
 extern "C" int tcs_corr_build(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                               float* lvl0, float* lvl1, float* lvl2, float* lvl3,
-                              int B, int H, int W1, int W2, int C, int num_levels, int prec, void* stream) {
+                              int B, int H, int W1, int W2, int C, int num_levels, int prec, int W2_pitch, void* stream) {
     using namespace tcs;
     TCS_REQUIRE(a_hi != nullptr && b_hi != nullptr && lvl0 != nullptr, TCS_E_BADARG, "tcs_corr_build: null operand / level 0");
+    // Row pitch of level 0 (level l: pitch >> l).  With a pitch beyond W2 the right operand's rows past W2 are TMA zero fill, so
+    // the extra columns of every level come out as exact zeros (W2 % 8 == 0: no pooled entry mixes real and padding columns).
+    const int W2_valid = W2;
+    if (W2_pitch > 0 && W2_pitch != W2) {
+        TCS_REQUIRE(W2_pitch > W2 && W2_pitch % 16 == 0 && W2 % 8 == 0, TCS_E_SHAPE,
+                    "tcs_corr_build: a row pitch (%d) other than W2 (%d) needs W2 %% 8 == 0 and a pitch that is a multiple of 16", W2_pitch, W2);
+        W2 = W2_pitch;
+    }
     TCS_REQUIRE(prec >= TCS_PREC_BF16 && prec <= TCS_PREC_FP16X3, TCS_E_BADARG, "tcs_corr_build: bad prec %d", prec);
     const bool x3 = (prec == TCS_PREC_BF16X3 || prec == TCS_PREC_FP16X3);
     const bool fp16 = (prec == TCS_PREC_FP16 || prec == TCS_PREC_FP16X3);
@@ -242,10 +250,10 @@ extern "C" int tcs_corr_build(const void* a_hi, const void* a_lo, const void* b_
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     int rc;
     if ((rc = make_operand_map(&ta_hi, a_hi, B * H, W1, C, kBlockM, fp16)) != 0) return rc;
-    if ((rc = make_operand_map(&tb_hi, b_hi, B * H, W2, C, p.block_n, fp16)) != 0) return rc;
+    if ((rc = make_operand_map(&tb_hi, b_hi, B * H, W2_valid, C, p.block_n, fp16)) != 0) return rc;
     if (x3) {
         if ((rc = make_operand_map(&ta_lo, a_lo, B * H, W1, C, kBlockM, fp16)) != 0) return rc;
-        if ((rc = make_operand_map(&tb_lo, b_lo, B * H, W2, C, p.block_n, fp16)) != 0) return rc;
+        if ((rc = make_operand_map(&tb_lo, b_lo, B * H, W2_valid, C, p.block_n, fp16)) != 0) return rc;
     } else {
         ta_lo = ta_hi;
         tb_lo = tb_hi;

@@ -347,7 +347,7 @@ __device__ __forceinline__ void span_taps_oct(const SpanOct& sp, float* __restri
 // Block size 64 / 96 / 128 are equivalent, 256 is 3 % slower.
 __global__ void __launch_bounds__(kLookThreads)
 corr_lookup_r4x4o_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
-                         float* __restrict__ out, int HW, int W2) {
+                         float* __restrict__ out, int HW, int W2, int W2p) {   // W2p: row pitch of level 0 (>= W2, zeros beyond W2)
     const int b = blockIdx.z;
     const int hw = blockIdx.x * kLookThreads + threadIdx.x;
     if (hw >= HW) return;
@@ -356,11 +356,11 @@ corr_lookup_r4x4o_kernel(const LevelPtrs lv, const float* __restrict__ coords, l
     const float c0 = sane_coord(__ldg(coords + b * coords_bstride + hw));
     if (blockIdx.y == 0) {
         SpanOct s0;
-        span_load_oct(s0, lv.p[0], p, c0, 0, W2);
+        span_load_oct(s0, lv.p[0], p, c0, 0, W2p);                      // addressing: the pitch; sampling arithmetic: the width
         span_taps_oct<false>(s0, out, hw, HW, b, 0, W2, nullptr);
     } else {
         Span s1;
-        span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
+        span_load(s1, lv.p[2], p, npix, c0, 2, W2p >> 2, true);
         span_taps_reg<false, true>(s1, out, hw, HW, 4, b, 2, W2 >> 2, nullptr);
     }
 }
@@ -370,7 +370,7 @@ corr_lookup_r4x4o_kernel(const LevelPtrs lv, const float* __restrict__ coords, l
 template <bool kPadded>
 __global__ void __launch_bounds__(kLookThreads)
 corr_lookup_r4x4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
-                        float* __restrict__ out, int HW, int W2) {
+                        float* __restrict__ out, int HW, int W2, int W2p) {
     const int b = blockIdx.z;
     const int hw = blockIdx.x * kLookThreads + threadIdx.x;
     if (hw >= HW) return;
@@ -380,10 +380,10 @@ corr_lookup_r4x4_kernel(const LevelPtrs lv, const float* __restrict__ coords, lo
     if (kPadded) c0 = sane_coord(c0);
     Span sp;                                   // blockIdx.y = level pair (see corr_lookup_r4x4o_kernel)
     if (blockIdx.y == 0) {
-        span_load(sp, lv.p[0], p, npix, c0, 0, W2, true);
+        span_load(sp, lv.p[0], p, npix, c0, 0, W2p, true);
         span_taps_reg<false, kPadded>(sp, out, hw, HW, 4, b, 0, W2, nullptr);
     } else {
-        span_load(sp, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
+        span_load(sp, lv.p[2], p, npix, c0, 2, W2p >> 2, true);
         span_taps_reg<false, kPadded>(sp, out, hw, HW, 4, b, 2, W2 >> 2, nullptr);
     }
 }
@@ -421,7 +421,7 @@ template <int kMode>   // 0: any width; 1: W2 % 16 == 0 (no bounds predicates); 
 __global__ void __launch_bounds__(kLookThreads)
 corr_lookup_encode_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
                           const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ out,
-                          int HW, int W2, int Cout, int relu) {
+                          int HW, int W2, int W2p, int Cout, int relu) {
     __shared__ __align__(16) float s_w[kEncMaxOut * kEncTaps];
     __shared__ float s_b[kEncMaxOut];
     const int tid = threadIdx.x;
@@ -440,13 +440,13 @@ corr_lookup_encode_kernel(const LevelPtrs lv, const float* __restrict__ coords, 
     Span s1;
     if (kMode == 2) {
         SpanOct s0;
-        span_load_oct(s0, lv.p[0], p, c0, 0, W2);
-        span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
+        span_load_oct(s0, lv.p[0], p, c0, 0, W2p);
+        span_load(s1, lv.p[2], p, npix, c0, 2, W2p >> 2, true);
         span_taps_oct<true>(s0, nullptr, 0, HW, b, 0, W2, tp);
     } else {
         Span s0;
-        span_load(s0, lv.p[0], p, npix, c0, 0, W2, true);
-        span_load(s1, lv.p[2], p, npix, c0, 2, W2 >> 2, true);
+        span_load(s0, lv.p[0], p, npix, c0, 0, W2p, true);
+        span_load(s1, lv.p[2], p, npix, c0, 2, W2p >> 2, true);
         span_taps_reg<true, kPadded>(s0, nullptr, 0, HW, 4, b, 0, W2, tp);
     }
     span_taps_reg<true, kPadded>(s1, nullptr, 0, HW, 4, b, 2, W2 >> 2, tp + 18);
@@ -720,11 +720,14 @@ static int check_lookup_args(const char* fn, const float* const* lv, const float
 
 extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                const float* coords, long long coords_bstride, float* out,
-                               int B, int H, int W1, int W2, int num_levels, int radius, void* stream) {
+                               int B, int H, int W1, int W2, int num_levels, int radius, int W2_pitch, void* stream) {
     using namespace tcs;
     const float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
     int rc = check_lookup_args("tcs_corr_lookup", lv, coords, out, B, H, W1, W2, num_levels, radius);
     if (rc != 0) return rc;
+    const int W2p = W2_pitch > 0 ? W2_pitch : W2;
+    TCS_REQUIRE(W2p == W2 || (num_levels == 4 && radius == 4 && W2p > W2 && W2p % 16 == 0 && W2 % 8 == 0), TCS_E_SHAPE,
+                "tcs_corr_lookup: a row pitch (%d) other than W2 (%d) needs 4 levels, radius 4, W2 %% 8 == 0 and a pitch that is a multiple of 16", W2p, W2);
     LevelPtrs lp;
     for (int l = 0; l < 4; ++l) lp.p[l] = lv[l];
     const long long npix = (long long)B * H * W1;
@@ -739,12 +742,12 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
         // W2 % 16 == 0: the rows of levels 0 and 2 start on 16-byte boundaries (no bounds predicates); with a 32-byte
         // aligned level 0 its span comes as 32-byte loads
         const dim3 grid2(grid.x, 2, B);            // 4 levels: one thread per (pixel, level pair)
-        if (num_levels == 4 && W2 % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
-            corr_lookup_r4x4o_kernel<<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
-        else if (num_levels == 4 && W2 % 16 == 0)
-            corr_lookup_r4x4_kernel<true><<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
+        if (num_levels == 4 && W2p % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
+            corr_lookup_r4x4o_kernel<<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, W2p);
+        else if (num_levels == 4 && W2p % 16 == 0)
+            corr_lookup_r4x4_kernel<true><<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, W2p);
         else if (num_levels == 4)     // any width: span in registers, no shared memory (+2 % in the step)
-            corr_lookup_r4x4_kernel<false><<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2);
+            corr_lookup_r4x4_kernel<false><<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, W2p);
         else
             corr_lookup_r4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels);
     } else {
@@ -758,11 +761,14 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
 extern "C" int tcs_corr_lookup_encode(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                       const float* coords, long long coords_bstride, const float* weight,
                                       const float* bias, float* out, int B, int H, int W1, int W2, int num_levels,
-                                      int radius, int Cout, int relu, void* stream) {
+                                      int radius, int Cout, int relu, int W2_pitch, void* stream) {
     using namespace tcs;
     const float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
     int rc = check_lookup_args("tcs_corr_lookup_encode", lv, coords, out, B, H, W1, W2, num_levels, radius);
     if (rc != 0) return rc;
+    const int W2p = W2_pitch > 0 ? W2_pitch : W2;
+    TCS_REQUIRE(W2p == W2 || (W2p > W2 && W2p % 16 == 0 && W2 % 8 == 0), TCS_E_SHAPE,
+                "tcs_corr_lookup_encode: a row pitch (%d) other than W2 (%d) needs W2 %% 8 == 0 and a pitch that is a multiple of 16", W2p, W2);
     TCS_REQUIRE(num_levels == 4 && radius == 4, TCS_E_SHAPE, "tcs_corr_lookup_encode: implemented for num_levels=4, radius=4 (36 taps)");
     TCS_REQUIRE(weight != nullptr, TCS_E_BADARG, "tcs_corr_lookup_encode: null weight");
     TCS_REQUIRE(Cout > 0 && Cout <= kEncMaxOut && Cout % 4 == 0, TCS_E_SHAPE, "tcs_corr_lookup_encode: Cout=%d must be a multiple of 4, <= %d", Cout, kEncMaxOut);
@@ -779,12 +785,12 @@ extern "C" int tcs_corr_lookup_encode(const float* lvl0, const float* lvl1, cons
         }
     );
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (W2 % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
-        corr_lookup_encode_kernel<2><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, weight, bias, out, H * W1, W2, Cout, relu);
-    else if (W2 % 16 == 0)
-        corr_lookup_encode_kernel<1><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, weight, bias, out, H * W1, W2, Cout, relu);
+    if (W2p % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
+        corr_lookup_encode_kernel<2><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, weight, bias, out, H * W1, W2, W2p, Cout, relu);
+    else if (W2p % 16 == 0)
+        corr_lookup_encode_kernel<1><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, weight, bias, out, H * W1, W2, W2p, Cout, relu);
     else
-        corr_lookup_encode_kernel<0><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, weight, bias, out, H * W1, W2, Cout, relu);
+        corr_lookup_encode_kernel<0><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, weight, bias, out, H * W1, W2, W2p, Cout, relu);
     TCS_CHECK_LAUNCH("tcs_corr_lookup_encode");
     return 0;
 }

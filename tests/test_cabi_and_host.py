@@ -28,14 +28,14 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libtcs_b200.so does not export %s" % n
     assert sorted(tcs_b200._lib.SIGNATURES) == names, "ctypes signatures and header disagree"
-    assert lib.tcs_abi_version() == tcs_b200._lib.ABI_VERSION == 7
+    assert lib.tcs_abi_version() == tcs_b200._lib.ABI_VERSION == 8
 
 
 def test_argument_errors_are_reported_without_a_gpu():
     """Validation happens before any CUDA call, so the status codes can be checked on a CPU-only host."""
     import tcs_b200
     lib = tcs_b200._lib.load()
-    assert lib.tcs_corr_lookup(None, None, None, None, None, 0, None, 1, 1, 1, 16, 4, 4, None) == -1
+    assert lib.tcs_corr_lookup(None, None, None, None, None, 0, None, 1, 1, 1, 16, 4, 4, 0, None) == -1
     assert b"null" in lib.tcs_last_error()
     assert lib.tcs_corr_prepass(ctypes.c_void_p(256), ctypes.c_void_p(256), None, None, 1, 100, 1, 1, 0, None) == -2
     assert lib.tcs_warp_scratch_bytes(0, 256, 4, 4) == 0

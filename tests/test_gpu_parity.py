@@ -763,6 +763,37 @@ def test_hidden_state_warp_one_launch_is_bit_identical_to_the_chain(tcs, B, H, W
         assert torch.equal(got[l], want[l]), "level %d differs" % l
 
 
+@pytest.mark.parametrize("B,H,W1,W2", [(1, 20, 312, 312), (2, 5, 312, 312), (1, 6, 400, 312), (1, 4, 104, 104 + 8 * 25)])
+def test_pitched_levels_give_the_same_bits_as_dense_ones(tcs, monkeypatch, B, H, W1, W2):
+    """Widths with W2 % 16 == 8 (the KITTI shape's 312) are built with a row pitch of the next multiple of 16, zeros in
+    the padding, which puts them on the lookup's predicate-free kernels.  Everything that reads the levels must give the
+    bits it gives on dense rows: the levels themselves, the lookup (out-of-range, integer and non-finite coordinates
+    included), the fused lookup + 1x1, argmax_disp and the cost volume (also when W1 > W2, where w1 reaches past W2)."""
+    g = torch.Generator().manual_seed(W1 + W2)
+    f1 = torch.randn(B, 256, H, W1, generator=g).cuda()
+    f2 = (torch.roll(f1[..., :W2], -3, dims=3) + 0.3 * torch.randn(B, 256, H, W2, generator=g).cuda()) if W1 >= W2 else torch.randn(B, 256, H, W2, generator=g).cuda()
+    coords = make_coords(B, H, W1, 3)
+    coords.view(-1)[2] = float("nan")
+    coords = coords.cuda()
+    w = torch.randn(64, 36, generator=g).cuda() * 0.2
+    pitched = tcs.CorrBlock1D(f1, f2)
+    assert pitched.W2p == (W2 + 15) // 16 * 16 and pitched.W2p != W2 and pitched._levels[0].shape[-1] == W2
+    monkeypatch.setenv("TCS_B200_LEVEL_PITCH", "0")
+    dense = tcs.CorrBlock1D(f1, f2)
+    assert dense.W2p == W2
+    for l in range(4):
+        assert torch.equal(pitched._levels[l], dense._levels[l]), "level %d" % l
+        assert float(pitched._flat.abs().max()) <= 1.0 + 1e-5            # and nothing but zeros / cosines anywhere in the buffer
+    assert torch.equal(pitched(coords), dense(coords))
+    assert torch.equal(pitched.lookup_encoded(coords, w), dense.lookup_encoded(coords, w))
+    for a, b in zip(pitched.argmax_disp(), dense.argmax_disp()):
+        assert torch.equal(a, b)
+    assert torch.equal(pitched.get_cost_volume(), dense.get_cost_volume())
+    monkeypatch.delenv("TCS_B200_LEVEL_PITCH")
+    again = tcs.CorrBlock1D.from_levels([lv.contiguous() for lv in dense._levels])     # copies into pitched, zero-padded rows
+    assert again.W2p == pitched.W2p and torch.equal(again(coords), dense(coords))
+
+
 def test_second_device_in_the_same_process(tcs):
     """Kernel attributes (dynamic shared memory above 48 KB, carve-out hints) are per device: the build (fused and two-step),
     the warp (both formulations), the lookups (pyramid, fused encode, tensor-core alternate) must work on cuda:1 after they ran
