@@ -783,7 +783,9 @@ def test_pitched_levels_give_the_same_bits_as_dense_ones(tcs, monkeypatch, B, H,
     assert dense.W2p == W2
     for l in range(4):
         assert torch.equal(pitched._levels[l], dense._levels[l]), "level %d" % l
-        assert float(pitched._flat.abs().max()) <= 1.0 + 1e-5            # and nothing but zeros / cosines anywhere in the buffer
+        lv = pitched._levels[l]
+        phys = torch.as_strided(lv, (B, H, W1, pitched.W2p >> l), lv.stride(), lv.storage_offset())
+        assert float(phys[..., W2 >> l:].abs().max()) == 0.0, "level %d: the padding columns must be exact zeros" % l
     assert torch.equal(pitched(coords), dense(coords))
     assert torch.equal(pitched.lookup_encoded(coords, w), dense.lookup_encoded(coords, w))
     for a, b in zip(pitched.argmax_disp(), dense.argmax_disp()):
