@@ -763,7 +763,7 @@ def test_hidden_state_warp_one_launch_is_bit_identical_to_the_chain(tcs, B, H, W
         assert torch.equal(got[l], want[l]), "level %d differs" % l
 
 
-@pytest.mark.parametrize("B,H,W1,W2", [(1, 20, 312, 312), (2, 5, 312, 312), (1, 6, 400, 312), (1, 4, 104, 104 + 8 * 25)])
+@pytest.mark.parametrize("B,H,W1,W2", [(1, 20, 312, 312), (2, 5, 312, 312), (1, 6, 400, 312), (1, 4, 104, 296)])
 def test_pitched_levels_give_the_same_bits_as_dense_ones(tcs, monkeypatch, B, H, W1, W2):
     """Widths with W2 % 16 == 8 (the KITTI shape's 312) are built with a row pitch of the next multiple of 16, zeros in
     the padding, which puts them on the lookup's predicate-free kernels.  Everything that reads the levels must give the
