@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kLookThreads)
 corr_lookup_r4x4o_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
                          float* __restrict__ out, int HW, int W2, int W2p) {   // W2p: row pitch of level 0 (>= W2, zeros beyond W2)
     const int b = blockIdx.z;
-    const int hw = blockIdx.x * kLookThreads + threadIdx.x;
+    const int hw = blockIdx.x * blockDim.x + threadIdx.x;           // launched with kLookThreads, or 32 for a small frame
     if (hw >= HW) return;
     const long long npix = (long long)gridDim.z * HW;
     const long long p = (long long)b * HW + hw;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kLookThreads)
 corr_lookup_r4x4_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
                         float* __restrict__ out, int HW, int W2, int W2p) {
     const int b = blockIdx.z;
-    const int hw = blockIdx.x * kLookThreads + threadIdx.x;
+    const int hw = blockIdx.x * blockDim.x + threadIdx.x;
     if (hw >= HW) return;
     const long long npix = (long long)gridDim.z * HW;
     const long long p = (long long)b * HW + hw;
@@ -741,13 +741,19 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
         );
         // W2 % 16 == 0: the rows of levels 0 and 2 start on 16-byte boundaries (no bounds predicates); with a 32-byte
         // aligned level 0 its span comes as 32-byte loads
-        const dim3 grid2(grid.x, 2, B);            // 4 levels: one thread per (pixel, level pair)
+        // 4 levels: one thread per (pixel, level pair).  A single frame (batch 1: 2 x 255 CTAs of 128 threads at 540p) leaves
+        // most of the 148 SMs' warp slots empty and the call is one latency chain long; 32-thread CTAs spread the same threads
+        // over four times as many CTAs (TCS_LOOKUP_SMALL_CTA=0 keeps 128).
+        static const int small_cta = carveout_percent("TCS_LOOKUP_SMALL_CTA", 1);
+        const long long ctas128 = (long long)grid.x * 2 * B;
+        const int threads = (small_cta > 0 && ctas128 < 8LL * num_sms()) ? 32 : kLookThreads;
+        const dim3 grid2((unsigned)ceil_div(H * W1, threads), 2, B);
         if (num_levels == 4 && W2p % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
-            corr_lookup_r4x4o_kernel<<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, W2p);
+            corr_lookup_r4x4o_kernel<<<grid2, threads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, W2p);
         else if (num_levels == 4 && W2p % 16 == 0)
-            corr_lookup_r4x4_kernel<true><<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, W2p);
+            corr_lookup_r4x4_kernel<true><<<grid2, threads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, W2p);
         else if (num_levels == 4)     // any width: span in registers, no shared memory (+2 % in the step)
-            corr_lookup_r4x4_kernel<false><<<grid2, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, W2p);
+            corr_lookup_r4x4_kernel<false><<<grid2, threads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, W2p);
         else
             corr_lookup_r4_kernel<<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, num_levels);
     } else {
