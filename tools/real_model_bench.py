@@ -31,10 +31,11 @@ def main():
     ap.add_argument("--width", type=int, default=960)
     ap.add_argument("--iters", type=int, default=32)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--mixed-precision", action="store_true", help="the shipped scripts' --mixed_precision: learned blocks under fp16 autocast")
     args = ap.parse_args()
     import tcs_b200
     ref = ref_model.load()
-    model = ref_model.make_model("cuda")
+    model = ref_model.make_model("cuda", mixed_precision=args.mixed_precision)
     imgs, K, poses, base = ref_model.synthetic_sequence(2, args.height, args.width, device="cuda")
     mods = (ref.geo, ref.update, ref.corr, ref.tc_stereo, ref.utils)
 
@@ -61,7 +62,7 @@ def main():
                 res[name] = statistics.median(ts)
             return res
 
-    out = {"config": {"height": args.height, "width": args.width, "iters": args.iters, "batch": 1, "reps": args.reps,
+    out = {"config": {"height": args.height, "width": args.width, "iters": args.iters, "batch": 1, "reps": args.reps, "mixed_precision": args.mixed_precision,
                       "gpu": torch.cuda.get_device_name(0)}}
     fused = dict(fuse_cost=True, fuse_motion_encoder=ref.update, stencils=ref.update)
     for name, kw, strip, graphs in (("reference", None, False, False), ("reference -O", None, True, False), ("dropin", {}, False, False),
@@ -89,7 +90,7 @@ def main():
                 tcs_b200.restore_asserts()
         print(name, out[name], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "real_model_timing.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "real_model_timing%s.json" % ("_amp" if args.mixed_precision else "")), "w"), indent=1)
 
 
 if __name__ == "__main__":
