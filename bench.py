@@ -6,13 +6,15 @@
     python [-O] bench.py --impl reference-gpu ...             (the reference's own PyTorch code for the path on the B200)
 
 A step = the hot path's share of ONE temporal frame for every sequence this GPU owns (B sequences batched
-along the batch axis): 2 normalise pre-passes + tcgen05 correlation build of all 4 levels, forward warp of the
-previous disparity/features + matching cost, backward grid + 3-level hidden-state gather, and 32 pyramid
-lookups.  Inputs (feature maps, per-iteration coordinates, hidden states, poses) are synthetic and already
+along the batch axis): the fused tcgen05 correlation build of all 4 levels (normalisation and hi/lo split on chip), forward
+warp of the previous disparity/features + matching cost, backward grid + the 3-level hidden-state warp, and 32 pyramid
+lookups (--mode alternate: 32 tensor-core on-the-fly lookups, no pyramid).  Inputs (feature maps, per-iteration coordinates, hidden states, poses) are synthetic and already
 resident in HBM for `value`; `e2e` feeds the same step from pinned HOST buffers through the public Python API
 (H2D of the feature maps and D2H of the results inside the timed region).  Sequences are independent, so
-N GPUs run N*B sequences with no data-path collective (weak scaling); NCCL is used for the barrier and the
-max-over-ranks of the timings.  One JSON line is printed by rank 0.
+N GPUs run N*B sequences with no data-path collective (weak scaling; --sequences S shards S sequences in total: strong
+scaling, BASELINE config 4); NCCL is used for the barrier, the max-over-ranks of the timings and the final all_reduce of the
+frame count.  One JSON line is printed by rank 0.  The reference arms (--impl reference: the reference's own code on the host
+cores; --impl reference-gpu: the same code on the B200) never load libtcs_b200.so.
 """
 import argparse
 import json
