@@ -323,7 +323,7 @@ def test_real_model_sequence_drift(ref, tcs, model, iters):
         for t in range(3):
             for k in ("flow_q", "flow"):
                 fl = max(f[k] for f in floor[:t + 1])
-                factor = 3 if (iters <= 8 or t == 0) else 10
+                factor = 3 if t == 0 else 10        # temporal frames: the response is bimodal (see FLOOR_SAMPLES), four samples can all land low
                 gate = ABS_GATE_FIRST if t == 0 else ABS_GATE_TEMPORAL
                 assert rep[name][t][k] <= max(gate, factor * fl), "%s frame %d %s drift %.3g vs floor %.3g" % (name, t, k, rep[name][t][k], fl)
 
