@@ -10,8 +10,12 @@
 
 namespace tcs {
 
-constexpr int kPreTileW = 32;
+#ifndef TCS_PRE_TILE_W
+#define TCS_PRE_TILE_W 32
+#endif
+constexpr int kPreTileW = TCS_PRE_TILE_W;          // pixels per CTA: 32 (128-byte channel rows) or 64 (256-byte rows)
 constexpr int kPreThreads = 256;
+constexpr int kPreLoadLanes = kPreTileW / 4;        // threads that cover one channel row with 16-byte loads
 constexpr float kFp16OperandScale = 256.0f;  // unit-vector entries x 2^8 keep fp16 away from subnormals
 
 template <bool kFp16>
@@ -47,12 +51,12 @@ corr_prepass_kernel(const float* __restrict__ fmap, uint32_t* __restrict__ hi, u
 
     // ---- load [C][32] (w fastest in global) -> tile[w][c]
     {
-        const int w4 = (tid & 7) * 4;
-        const int c_off = tid >> 3;  // 0..31
+        const int w4 = (tid % kPreLoadLanes) * 4;
+        const int c_off = tid / kPreLoadLanes;
         const bool vec_ok = ((W & 3) == 0) && (w0 + w4 + 3 < W);
         const size_t plane = (size_t)H * W;
         const float* src = fmap + ((size_t)b * C * H + h) * W + w0 + w4;
-        for (int c = c_off; c < C; c += kPreThreads / 8) {
+        for (int c = c_off; c < C; c += kPreThreads / kPreLoadLanes) {
             const float* p = src + (size_t)c * plane;
             float v[4];
             if (vec_ok) {
@@ -148,13 +152,13 @@ static int launch_prepass(const float* fmap, void* hi, void* lo, float* n32, int
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (fp16) {
         TCS_ONCE_PER_DEVICE(
-            TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 513 * 4));
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreTileW * 513 * 4));
             { const int cv = carveout_percent("TCS_CARVE_PREPASS", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); }
         );
         corr_prepass_kernel<true><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W, kblocked);
     } else {
         TCS_ONCE_PER_DEVICE(
-            TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 513 * 4));
+            TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreTileW * 513 * 4));
             { const int cv = carveout_percent("TCS_CARVE_PREPASS", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); }
         );
         corr_prepass_kernel<false><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W, kblocked);
