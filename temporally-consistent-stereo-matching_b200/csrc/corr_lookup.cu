@@ -345,7 +345,10 @@ __device__ __forceinline__ void span_taps_oct(const SpanOct& sp, float* __restri
 // One thread per (pixel, level pair), blockIdx.y = pair: 50 registers instead of 80, so 40 warps per SM hide the
 // latency of the scattered loads instead of 24 (20.4 -> 19.5 us; the coordinate is simply read twice).
 // Block size 64 / 96 / 128 are equivalent, 256 is 3 % slower.
-__global__ void __launch_bounds__(kLookThreads)
+#ifndef TCS_LOOKUP_MINBLOCKS
+#define TCS_LOOKUP_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(kLookThreads, TCS_LOOKUP_MINBLOCKS)
 corr_lookup_r4x4o_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
                          float* __restrict__ out, int HW, int W2, int W2p) {   // W2p: row pitch of level 0 (>= W2, zeros beyond W2)
     const int b = blockIdx.z;
