@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCS_ABI_VERSION 8
+#define TCS_ABI_VERSION 9
 
 /* argument errors (negative); CUDA launch errors are returned as positive cudaError_t values */
 #define TCS_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported combination */
@@ -242,6 +242,14 @@ int tcs_disp_propagate(const float* grad, const float* disp, float* prop, float*
  * the 3x3 zero-padded neighbours of (factor *) flow.  factor 2, 4 or 8; scale != 0 multiplies flow by factor. */
 int tcs_convex_upsample(const float* flow, const float* mask, float* out, int N, int D, int H, int W,
                         int factor, int scale, void* stream);
+
+/* ---- (7) "next" row: backward of the lookup, for training ------------------------------------ */
+
+/* ref: the autograd of core/corr.py:33-52 (grid_sample's gradient w.r.t. its input; coords are detached, tc_stereo.py:176)
+ * folded through core/corr.py:21-23 (avg_pool2d's gradient): d(lookup output) -> d(volume), every element written once.
+ *   grad_out [B, num_levels*(2r+1), H, W1] fp32, coords as for tcs_corr_lookup, grad_volume [B,H,W1,W2] fp32 (out, dense). */
+int tcs_corr_lookup_backward(const float* grad_out, const float* coords, long long coords_bstride, float* grad_volume,
+                             int B, int H, int W1, int W2, int num_levels, int radius, void* stream);
 
 /* ---- (6) "next" row: input stems of the disparity completion network ------------------ */
 

@@ -300,9 +300,31 @@ __device__ __forceinline__ void span_taps_R(const float* R, int span_first, floa
 // is the number of load requests the SM keeps in flight, not their bytes (23.0 -> 20.4 us).  Needs W2 % 8 == 0 and a
 // 32-byte aligned base: rows then start on 32-byte boundaries and an oct is entirely inside or outside its row.
 // (The same for level 2, whose 240-byte rows would need half-oct fix-ups, is no faster than quads: 23.1 us.)
+// TCS_LOOKUP_L2HINT (experiment): 1 = the window loads carry an L2 evict_last policy and the tap
+// stores an evict_first one (successive GRU iterations read nearly the same windows: ~76 MB of granules, which would fit L2
+// if the 36 MB of output planes per call did not push them out); 2 = only the loads are hinted.
+#ifndef TCS_LOOKUP_L2HINT
+#define TCS_LOOKUP_L2HINT 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void ldg_oct(float* r, const float* p) {
+#if TCS_LOOKUP_L2HINT
+    const uint64_t pol = l2_policy_evict_last();
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p), "l"(pol));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+#endif
 }
 
 struct SpanOct {
@@ -500,6 +522,58 @@ corr_lookup_generic_kernel(const LevelPtrs lv, const float* __restrict__ coords,
             r = fmaf(v1, w_hi, __fmul_rn(v0, w_lo));
         }
         o[(long long)t * HW] = r;
+    }
+}
+
+// ---- backward of the lookup w.r.t. the volume (training) ---------------------------------
+// ref: autograd of core/corr.py:33-52 (grid_sample's gradient w.r.t. its INPUT: every output tap sends g * weight to its
+// two in-range neighbours; coords are detached, tc_stereo.py:176) folded through core/corr.py:21-23 (avg_pool2d's
+// gradient: a level-l entry hands 2^-l of its gradient to each of its 2^l level-0 columns).  Output: d(volume)
+// [B,H,W1,W2], dense, written exactly once per element (no atomics, deterministic: torch's own grid_sampler backward
+// scatters with atomicAdd).  One warp per pixel: lane l < num_levels gathers its level's taps into that level's window
+// gradient (shared memory, private to the lane), then all lanes write the pixel's row of d(volume), coalesced.
+constexpr int kBwdWin = 2 * TCS_MAX_RADIUS + 4;     // window entries per level: 2r + 1 taps, their right neighbours, +-1 of round trip
+
+__global__ void __launch_bounds__(256)
+corr_lookup_backward_kernel(const float* __restrict__ gout, const float* __restrict__ coords, long long coords_bstride,
+                            float* __restrict__ dvol, int HW, int W2, int num_levels, int radius, long long npix) {
+    __shared__ float s_g[8][TCS_MAX_LEVELS][kBwdWin];
+    __shared__ int s_first[8][TCS_MAX_LEVELS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long p = (long long)blockIdx.x * 8 + warp;
+    if (p >= npix) return;                                              // warp-uniform
+    const long long b = p / HW, hw = p - b * HW;
+    const float c0 = sane_coord(__ldg(coords + b * coords_bstride + hw));
+    const int taps = 2 * radius + 1;
+    if (lane < num_levels) {
+        const int l = lane, Wl = W2 >> l;
+        const float wm1 = (float)(Wl - 1), rc = __frcp_rn(wm1), hwm1 = __fmul_rn(0.5f, wm1);
+        const float cl = c0 * (1.0f / (float)(1 << l));
+        const int first = (int)fminf(fmaxf(floorf(cl), -64.0f), (float)(Wl + 64)) - radius - 1;
+        float* g = s_g[warp][l];
+        for (int k = 0; k < kBwdWin; ++k) g[k] = 0.0f;
+        const float* go = gout + ((b * num_levels + l) * taps) * (long long)HW + hw;
+        for (int t = 0; t < taps; ++t) {
+            const TapPos tp = tap_position(__fadd_rn((float)(t - radius), cl), wm1, rc, hwm1, Wl);
+            const float gv = __ldg(go + (long long)t * HW);
+            const int k = tp.x0 - first;
+            if (tp.w_lo != 0.0f && k >= 0 && k < kBwdWin) g[k] = fmaf(gv, tp.w_lo, g[k]);
+            if (tp.w_hi != 0.0f && k + 1 >= 0 && k + 1 < kBwdWin) g[k + 1] = fmaf(gv, tp.w_hi, g[k + 1]);
+        }
+        s_first[warp][l] = first;
+    }
+    __syncwarp();
+    float* row = dvol + p * W2;
+    for (int j = lane; j < W2; j += 32) {
+        float v = 0.0f;
+        float scale = 1.0f;
+        for (int l = 0; l < num_levels; ++l) {
+            const int e = j >> l;                                       // the level-l entry this column was pooled into
+            const int k = e - s_first[warp][l];
+            if (e < (W2 >> l) && k >= 0 && k < kBwdWin) v = fmaf(s_g[warp][l][k], scale, v);
+            scale *= 0.5f;
+        }
+        row[j] = v;
     }
 }
 
@@ -851,5 +925,19 @@ extern "C" int tcs_corr_cost_volume(const float* lvl0, float* out, int B, int H,
     dim3 grid(ceil_div(W2, 32), ceil_div(W1, 32), B * H);
     corr_cost_volume_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(lvl0, out, H, W1, W2);
     TCS_CHECK_LAUNCH("tcs_corr_cost_volume");
+    return 0;
+}
+
+extern "C" int tcs_corr_lookup_backward(const float* grad_out, const float* coords, long long coords_bstride, float* grad_volume,
+                                        int B, int H, int W1, int W2, int num_levels, int radius, void* stream) {
+    using namespace tcs;
+    TCS_REQUIRE(grad_out && coords && grad_volume, TCS_E_BADARG, "tcs_corr_lookup_backward: null pointer");
+    TCS_REQUIRE(num_levels >= 1 && num_levels <= TCS_MAX_LEVELS && radius >= 0 && radius <= TCS_MAX_RADIUS, TCS_E_SHAPE,
+                "tcs_corr_lookup_backward: num_levels in [1,%d], radius in [0,%d]", TCS_MAX_LEVELS, TCS_MAX_RADIUS);
+    TCS_REQUIRE(B > 0 && H > 0 && W1 > 0 && (W2 >> (num_levels - 1)) >= 2, TCS_E_SHAPE, "tcs_corr_lookup_backward: bad sizes");
+    const long long npix = (long long)B * H * W1;
+    corr_lookup_backward_kernel<<<(unsigned)ceil_div_ll(npix, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        grad_out, coords, coords_bstride, grad_volume, H * W1, W2, num_levels, radius, npix);
+    TCS_CHECK_LAUNCH("tcs_corr_lookup_backward");
     return 0;
 }

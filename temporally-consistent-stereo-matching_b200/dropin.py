@@ -151,7 +151,7 @@ def restore_asserts():
         f.__code__ = code
 
 
-def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=None, stencils=None, fuse_cost=False):
+def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=None, stencils=None, fuse_cost=False, training=False):
     """tc_stereo_module: the imported `core.tc_stereo`.  Returns the dict of names that were replaced.
 
     fuse_cost: `warp` also evaluates the matching cost of tc_stereo.py:139-140 in its normalise kernel (against the
@@ -168,6 +168,26 @@ def install(tc_stereo_module, precision=None, mode=None, fuse_motion_encoder=Non
     BasicMotionEncoder.forward (update.py:103-112) evaluates `relu(convc1(corr))` with the fused lookup + 1x1
     kernel; fp32 only — under autocast the reference's conv runs in fp16."""
     from . import corr, geo
+
+    if training:
+        # gradients flow through the correlation block only (train.py); nothing that would cut one may be installed
+        if fuse_motion_encoder is not None or stencils is not None or fuse_cost or mode not in (None, "pyramid"):
+            raise ValueError("training=True installs the differentiable correlation block only: no fuse_motion_encoder, stencils, "
+                             "fuse_cost or mode='alternate' (their kernels have no backward)")
+        from .train import DifferentiableCorrBlock1D
+
+        class _Trainable(DifferentiableCorrBlock1D):
+            def __init__(self, fmap1, fmap2, num_levels=4, radius=4, thres=0.2):
+                super().__init__(fmap1, fmap2, num_levels, radius, thres, precision=precision)
+        _Trainable.__name__ = "CorrBlock1D"
+        new = {"CorrBlock1D": _Trainable, "warp": geo.warp, "get_backward_grid": geo.get_backward_grid,
+               "bilinear_sampler": geo.bilinear_sampler, "cal_relative_transformation": geo.cal_relative_transformation}
+        for name in _NAMES:
+            if not hasattr(tc_stereo_module, name):
+                raise AttributeError("%s has no attribute %r; is it the reference's core.tc_stereo?" % (tc_stereo_module, name))
+            _saved.setdefault((id(tc_stereo_module), name), getattr(tc_stereo_module, name))
+            setattr(tc_stereo_module, name, new[name])
+        return new
 
     block = corr.CorrBlock1D
     if precision is not None or mode is not None or fuse_motion_encoder is not None or fuse_cost:

@@ -490,3 +490,68 @@ def test_real_model_mixed_precision_with_everything_on(ref, tcs):
             # fp16 activations: the reference's own floor is ~1e-2 px here; the fused lookup + 1x1 keeps fp32 where the
             # reference's convc1 rounds to fp16, so the drop-in is allowed the same order of magnitude
             assert rep["everything_on"][t][k] <= max(5e-2, 3 * max(f[k] for f in floor[:t + 1])), (t, k, rep["everything_on"][t][k])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_training_gradients_of_the_correlation_block_match_the_reference(ref, tcs, precision):
+    """gradients w.r.t. fmap1 / fmap2 through two lookups and the cost volume, against the
+    reference's autograd (grid_sample, avg_pool2d, einsum, F.normalize backward) on the same GPU.  1e-4 rel (torch's
+    grid_sampler backward scatters with atomics; the kernel's is a gather)."""
+    g = torch.Generator().manual_seed(12)
+    B, C, H, W = 2, 128, 6, 88
+    base1 = torch.randn(B, C, H, W, generator=g).cuda()
+    base2 = (torch.roll(base1.cpu(), -3, dims=3) + 0.3 * torch.randn(B, C, H, W, generator=g)).cuda()
+    xs = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+    coords = [(xs - torch.rand(B, 1, H, W, generator=g) * 20).cuda() for _ in range(2)]
+    coords[1].view(-1)[::17] = -30.0                                   # taps that leave the image: no gradient
+    cot = [torch.randn(B, 36, H, W, generator=g).cuda() for _ in range(2)]
+    cot_cv = torch.randn(B, W, H, W, generator=g).cuda()
+
+    def run(make_block):
+        f1 = base1.clone().requires_grad_(True)
+        f2 = base2.clone().requires_grad_(True)
+        blk = make_block(f1, f2)
+        loss = sum((blk(c) * k).sum() for c, k in zip(coords, cot)) + (blk.get_cost_volume() * cot_cv).sum()
+        loss.backward()
+        return f1.grad, f2.grad, loss.detach()
+
+    r1, r2, rl = run(lambda a, b: ref.corr.CorrBlock1D(a, b, num_levels=4, radius=4))
+    t1, t2, tl = run(lambda a, b: tcs.DifferentiableCorrBlock1D(a, b, num_levels=4, radius=4, precision=precision))
+    scale = float(r1.abs().max())
+    assert_close(host(t1), host(r1), rtol=1e-4, atol=1e-5 * scale, what="d loss / d fmap1 (%s)" % precision)
+    assert_close(host(t2), host(r2), rtol=1e-4, atol=1e-5 * scale, what="d loss / d fmap2 (%s)" % precision)
+    assert abs(float(tl - rl)) <= 1e-4 * abs(float(rl)) + 1e-3
+    # and without grad it is the plain block
+    with torch.no_grad():
+        blk = tcs.DifferentiableCorrBlock1D(base1, base2)
+        assert torch.equal(blk(coords[0]), tcs.CorrBlock1D(base1, base2)(coords[0]))
+
+
+def test_training_step_through_the_real_model(ref, tcs):
+    """install(training=True): TCStereo.forward in training mode (test_mode=False) with the differentiable correlation block;
+    the gradients that reach the feature head (conv2) and the context encoder agree with the reference's."""
+    model = ref_model.make_model("cuda")
+    for p in model.parameters():
+        p.requires_grad_(True)
+    model.train()
+    imgs, K, poses, base = ref_model.synthetic_sequence(1, 128, 192, device="cuda")
+
+    def grads():
+        model.zero_grad(set_to_none=True)
+        out = model(imgs[0][0], imgs[0][1], iters=2, test_mode=False)
+        loss = sum(f[1].abs().mean() for f in out["flow_predictions"]) + 1e-3 * out["cost_volume"].abs().mean()
+        loss.backward()
+        return {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None and (n.startswith("conv2") or n.startswith("cnet.layer1"))}
+
+    want = grads()
+    tcs.install(ref.tc_stereo, training=True, precision="fp32")
+    try:
+        got = grads()
+    finally:
+        tcs.uninstall(ref.tc_stereo)
+    assert want and set(want) == set(got)
+    for n in want:
+        denom = float(want[n].abs().max()) + 1e-12
+        assert float((got[n] - want[n]).abs().max()) / denom <= 5e-3, "gradient of %s differs by %.2e of its scale" % (n, float((got[n] - want[n]).abs().max()) / denom)
+    with pytest.raises(ValueError):
+        tcs.install(ref.tc_stereo, training=True, stencils=ref.update)
