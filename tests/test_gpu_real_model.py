@@ -550,8 +550,11 @@ def test_training_step_through_the_real_model(ref, tcs):
     finally:
         tcs.uninstall(ref.tc_stereo)
     assert want and set(want) == set(got)
+    top = max(float(v.abs().max()) for v in want.values())
+    assert top > 0
     for n in want:
-        denom = float(want[n].abs().max()) + 1e-12
+        # (a bias in front of an instance norm has a mathematically zero gradient: 1e-12 of rounding noise on both sides)
+        denom = max(float(want[n].abs().max()), 1e-4 * top)
         assert float((got[n] - want[n]).abs().max()) / denom <= 5e-3, "gradient of %s differs by %.2e of its scale" % (n, float((got[n] - want[n]).abs().max()) / denom)
     with pytest.raises(ValueError):
         tcs.install(ref.tc_stereo, training=True, stencils=ref.update)
