@@ -122,3 +122,66 @@ def test_strip_asserts_is_python_O_for_the_reference_modules_only():
         tcs_b200.restore_asserts()
     assert all(has_assert(f) for f in targets)
     assert all(torch.equal(a["flow"], b["flow"]) and torch.equal(a["flow_q"], b["flow_q"]) for a, b in zip(got, want))
+
+
+def test_graph_argument_flattening_round_trips():
+    from tcs_b200 import graphed
+    a, b, c = torch.zeros(2), torch.ones(3), torch.full((1,), 2.0)
+    args = ([a, b], [[c, None], [a]], None, True, 3, "x")
+    tensors = []
+    spec = graphed._flatten((args, {"flag": False, "t": b}), tensors)
+    assert [t is u for t, u in zip(tensors, (a, b, c, a, b))] == [True] * 5
+    hash(spec)                                                           # the spec is a dict key
+    (ra, rk) = graphed._rebuild(spec, tensors)
+    assert ra[0][0] is a and ra[1][0][1] is None and ra[3] is True and ra[4] == 3 and rk["t"] is b and rk["flag"] is False
+    assert isinstance(ra[0], list) and isinstance(ra, tuple)
+    spec2 = graphed._flatten((([a, b], [[c, None], [a]], None, False, 3, "x"), {"flag": False, "t": b}), [])
+    assert spec2 != spec                                                 # a flag is part of the signature
+    out = graphed._fresh_containers([a, (b, [c])])
+    assert out[0] is a and out[1][1][0] is c and out is not None
+
+
+def test_level_pitch_and_pitched_allocation():
+    from tcs_b200 import corr
+    assert corr.level_pitch(312) == 320 and corr.level_pitch(240) == 240 and corr.level_pitch(480) == 480
+    assert corr.level_pitch(78) == 78                                   # W2 % 8 != 0: a pooled entry would mix real and padding columns
+    assert corr.level_pitch(312, num_levels=3) == 312 and corr.level_pitch(312, radius=3) == 312
+    flat, levels = corr.alloc_pyramid(2, 3, 312, 312, 4, "cpu", pitch=320, zero=True)
+    assert [tuple(l.shape) for l in levels] == [(2, 3, 312, 312 >> i) for i in range(4)]
+    assert [l.stride(2) for l in levels] == [320 >> i for i in range(4)]
+    assert all(l.data_ptr() % 128 == flat.data_ptr() % 128 for l in levels) and float(flat.abs().sum()) == 0.0
+    lv = levels[1]
+    assert lv.view(2 * 3 * 312, 1, 1, 156).shape == (1872, 1, 1, 156)   # the reference's corr_pyramid view still works on pitched rows
+
+
+@needs_ref
+def test_completor_stem_weights_are_packed_in_the_kernels_layout():
+    """pack_stem_weights against the reference's own DisparityCompletor layers on the CPU: a numpy perceptron over the packed
+    buffer (matrices [input][output]) must reproduce update.py:375-378."""
+    import numpy as np
+    from tcs_b200 import completor as cm
+    ref = ref_model.load()
+    torch.manual_seed(5)
+    comp = ref.update.DisparityCompletor()
+    for p in comp.parameters():
+        torch.nn.init.normal_(p, std=0.3)
+    pk = cm.pack_stem_weights(comp).numpy()
+    assert pk.size == 31296
+    d, c, m = 0.7, -0.2, 0.5
+    x = torch.tensor
+    with torch.no_grad():
+        one = lambda v: x([[[[v]]]], dtype=torch.float32)
+        want = comp.conv_disp_fuse(torch.cat((comp.conv_disp_stem(one(d)), comp.conv_cost_stem(one(c)), comp.conv_mask_stem(one(m))), dim=1)).reshape(-1).numpy()
+    o = 0
+    feats = []
+    for n, v in ((64, d), (32, c), (32, m)):
+        w1, b1 = pk[o:o + n], pk[o + n:o + 2 * n]
+        W2 = pk[o + 2 * n:o + 2 * n + n * n].reshape(n, n)
+        b2 = pk[o + 2 * n + n * n:o + 3 * n + n * n]
+        feats.append(np.maximum(w1 * v + b1, 0) @ W2 + b2)
+        o += 3 * n + n * n
+    cat = np.concatenate(feats)
+    W3 = pk[o:o + 128 * 128].reshape(128, 128); b3 = pk[o + 128 * 128:o + 128 * 128 + 128]; o += 128 * 128 + 128
+    W4 = pk[o:o + 128 * 64].reshape(128, 64); b4 = pk[o + 128 * 64:o + 128 * 64 + 64]
+    got = np.maximum(cat @ W3 + b3, 0) @ W4 + b4
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
