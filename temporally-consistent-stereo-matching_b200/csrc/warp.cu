@@ -898,7 +898,10 @@ warp_hidden3_kernel(const Hidden3Params p) {
     float* out = l == 0 ? p.out[0] : l == 1 ? p.out[1] : p.out[2];
     const float* img_b = net + (size_t)b * Cl * HWl;
     float* out_b = out + (size_t)b * Cl * HWl;
-    sample_group<kFull, kSampleCh / 2>(img_b, g[0], g[1], out_b, Cl, Hl, Wl, HWl, i, c_begin);   // 44 registers, 5 CTAs per SM
+#ifndef TCS_HIDDEN_BATCH
+#define TCS_HIDDEN_BATCH 8
+#endif
+    sample_group<kFull, TCS_HIDDEN_BATCH>(img_b, g[0], g[1], out_b, Cl, Hl, Wl, HWl, i, c_begin);   // 8: 44 registers, 5 CTAs per SM
 }
 
 static size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
