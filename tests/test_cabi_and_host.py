@@ -253,3 +253,15 @@ def test_launch_count_model():
     # list formulation on a carried transposition: geometry, weights + count, row sums, offsets, fill, sort, cost
     assert sequence.launches_per_frame(32, False, warp_lists=True) == 1 + 7 + 1 + 1 + 32
     assert sequence.launches_per_frame(32, False, hidden_levels=2) == 1 + 4 + 1 + 2 + 1 + 32      # other depths chain gathers and halvings
+
+
+def test_bench_reference_gpu_arm_degrades_without_a_gpu():
+    """`bench.py --impl reference-gpu` needs a CUDA device; without one it says so in one JSON line and exits 0."""
+    import json
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only container")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference-gpu", "--steps", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["impl"] == "reference-gpu" and "unavailable" in d
