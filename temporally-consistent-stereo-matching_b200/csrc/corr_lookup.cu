@@ -205,6 +205,49 @@ __device__ __forceinline__ void span_taps_reg(const Span& sp, float* __restrict_
     span_taps_R<kKeep, kPadded>(R, sp.span_first, sp.cb, out, out_px, HW, num_levels, b, lb, Wb, keep);
 }
 
+// The nine taps of a REGULAR pixel (see span_taps_R): tap t interpolates V[t] and V[t + 1] at sample_pos_fast(t - 4 + c).  Taps
+// are processed two at a time with packed fp32 (TCS_LOOKUP_X2, default on): the same round-to-nearest operations in the same
+// order per lane, so the result is bit-identical to the scalar form; what changes is the issue-slot count (this kernel is
+// co-limited by instruction issue and load latency: 49 % issue-active at 36 % occupancy, profiles/r02_kernel_lookup.md).
+#ifndef TCS_LOOKUP_X2
+#define TCS_LOOKUP_X2 1
+#endif
+template <bool kKeep>
+__device__ __forceinline__ void regular_taps(const float* V, float c, float wm1, float rc, float hwm1, float* __restrict__ o, int HW,
+                                             float* keep) {
+#if TCS_LOOKUP_X2
+    const f32x2 c2 = pk2(c), rc2 = pk2(rc), nw2 = pk2(-wm1), two2 = pk2(2.0f), m1 = pk2(-1.0f), one2 = pk2(1.0f), h2 = pk2(hwm1);
+#pragma unroll
+    for (int t = 0; t < 8; t += 2) {
+        const f32x2 xk = add2(pk2((float)(t - 4), (float)(t - 3)), c2);
+        const f32x2 q0 = mul2(xk, rc2);                                   // div_by_const(), lane-wise
+        const f32x2 q = fma2(fma2(q0, nw2, xk), rc2, q0);
+        const f32x2 ix = mul2(add2(fma2(two2, q, m1), one2), h2);         // sample_pos_fast()
+        const f32x2 x0 = pk2(floorf(lo2(ix)), floorf(hi2(ix)));
+        const f32x2 w_hi = sub2(ix, x0), w_lo = sub2(add2(x0, one2), ix);
+        const f32x2 r = fma2(pk2(V[t + 1], V[t + 2]), w_hi, mul2(pk2(V[t], V[t + 1]), w_lo));
+        if (kKeep) { keep[t] = lo2(r); keep[t + 1] = hi2(r); }
+        else { stg_stream_f1(o, lo2(r)); stg_stream_f1(o + HW, hi2(r)); }
+        o += 2 * (long long)HW;
+    }
+    {
+        const float ix = sample_pos_fast(__fadd_rn(4.0f, c), wm1, rc, hwm1);
+        const float x0f = floorf(ix);
+        const float r = fmaf(V[9], __fsub_rn(ix, x0f), __fmul_rn(V[8], __fsub_rn(__fadd_rn(x0f, 1.0f), ix)));
+        if (kKeep) keep[8] = r; else stg_stream_f1(o, r);
+    }
+#else
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const float ix = sample_pos_fast(__fadd_rn((float)(t - 4), c), wm1, rc, hwm1);
+        const float x0f = floorf(ix);
+        const float r = fmaf(V[t + 1], __fsub_rn(ix, x0f), __fmul_rn(V[t], __fsub_rn(__fadd_rn(x0f, 1.0f), ix)));
+        if (kKeep) keep[t] = r; else stg_stream_f1(o, r);
+        o += HW;
+    }
+#endif
+}
+
 // R[0..23]: the span itself (entry j = in-row index span_first + j of level lb, zero outside the row when kPadded).
 template <bool kKeep, bool kPadded>
 __device__ __forceinline__ void span_taps_R(const float* R, int span_first, float cb_, float* __restrict__ out, long long out_px,
@@ -228,14 +271,7 @@ __device__ __forceinline__ void span_taps_R(const float* R, int span_first, floa
             float Q[10];
 #pragma unroll
             for (int i = 0; i < 10; ++i) Q[i] = (cs == 2) ? R[i + 7] : R[i + 6];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float ix = sample_pos_fast(__fadd_rn((float)(t - 4), cb), wm1, rc, hwm1);
-                const float x0f = floorf(ix);
-                const float r = fmaf(Q[t + 1], __fsub_rn(ix, x0f), __fmul_rn(Q[t], __fsub_rn(__fadd_rn(x0f, 1.0f), ix)));
-                if (kKeep) keep[t] = r; else stg_stream_f1(o, r);
-                o += HW;
-            }
+            regular_taps<kKeep>(Q, cb, wm1, rc, hwm1, o, HW, keep);
         } else {
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
@@ -266,14 +302,7 @@ __device__ __forceinline__ void span_taps_R(const float* R, int span_first, floa
         const float fuf = floorf(cu), frac = cu - fuf;
         const bool regular = kPadded && Wu <= 1024 && frac >= kRegLo && frac <= kRegHi && (int)fuf == fu;   // fu unclamped
         if (kPadded && __all_sync(active, regular)) {
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {                        // the select index is 1 for every tap
-                const float ix = sample_pos_fast(__fadd_rn((float)(t - 4), cu), wm1, rc, hwm1);
-                const float x0f = floorf(ix);
-                const float r = fmaf(P[t + 2], __fsub_rn(ix, x0f), __fmul_rn(P[t + 1], __fsub_rn(__fadd_rn(x0f, 1.0f), ix)));
-                if (kKeep) keep[9 + t] = r; else stg_stream_f1(o, r);
-                o += HW;
-            }
+            regular_taps<kKeep>(P + 1, cu, wm1, rc, hwm1, o, HW, kKeep ? keep + 9 : keep);   // the select index is 1 for every tap
         } else {
 #pragma unroll
         for (int t = 0; t < 9; ++t) {

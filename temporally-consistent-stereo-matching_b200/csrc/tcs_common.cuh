@@ -87,6 +87,18 @@ __device__ __forceinline__ float div_by_const(float x, float c, float rc) {
     return __fmaf_rn(r, rc, q0);
 }
 
+// Packed pairs of fp32 (sm_100: FADD2 / FMUL2 / FFMA2 — one issue slot for two independent lanes).  Round-to-nearest, nothing
+// contracted: each lane's result is bit-identical to the scalar __fadd_rn / __fmul_rn / __fmaf_rn.
+struct f32x2 { uint64_t v; };
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f32x2 pk2(float a) { return pk2(a, a); }
+__device__ __forceinline__ float lo2(f32x2 x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); return a; }
+__device__ __forceinline__ float hi2(f32x2 x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); return b; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+
 // Explicit shared-space accesses by 32-bit shared address.  Pointers into dynamically carved shared memory
 // lose their address space in the compiler's eyes and turn into generic LD/ST (slower, and tracked on the
 // long scoreboard); these keep them LDS/STS.  volatile: they stay ordered with the mbarrier waits around them.
