@@ -2,20 +2,28 @@
 // as 16-bit tensor-core operands (hi [+ lo residual]) and/or as fp32 (alternate-path operand).
 // ref: core/corr.py:58-59 (F.normalize(fmap, dim=1): x / max(||x||_2, 1e-12)).
 //
-// HBM-bound transpose.  One CTA = one (b, h) row x 32 consecutive w.  The [C x 32] fp32 tile is read
-// once with 16-byte loads (128 B per channel row), transposed through shared memory (pitch C+1 words:
-// conflict-free both ways), reduced per pixel with warp shuffles and written as 512 B (16-bit) /
-// 1 KB (fp32) contiguous pixels.  Algorithmic bytes per pixel: 4C in + 2C (hi) [+ 2C lo] [+ 4C n32].
+// HBM-bound transpose.  One CTA = one (b, h) row x 32 consecutive w; thread = (pixel, group of 16 channels): lanes are
+// consecutive pixels, so every channel is one coalesced 128-byte warp load, and the thread's 16 channels leave as whole
+// 32-byte sectors (2 x 16-byte stores per 16-bit tensor) of the channels-last row.  The values stay in registers between the
+// norm and the emit; the only shared memory is the [groups][32] table of partial sums of squares, added in group order by
+// every thread of the pixel (deterministic).  The first version staged the tile transposed in shared memory and spent 37
+// instructions per element (53 % issue-active at 42 % DRAM, profiles/r02_prepass.md); this one spends about 10.
+// Algorithmic bytes per pixel: 4C in + 2C (hi) [+ 2C lo] [+ 4C n32].
 #include "tcs_common.cuh"
 
 namespace tcs {
 
-#ifndef TCS_PRE_TILE_W
-#define TCS_PRE_TILE_W 32
+constexpr int kPreTileW = 32;                // pixels per CTA = lanes
+#ifndef TCS_PRE_THREADS
+#define TCS_PRE_THREADS 256
 #endif
-constexpr int kPreTileW = TCS_PRE_TILE_W;          // pixels per CTA: 32 (128-byte channel rows) or 64 (256-byte rows)
-constexpr int kPreThreads = 256;
-constexpr int kPreLoadLanes = kPreTileW / 4;        // threads that cover one channel row with 16-byte loads
+#ifndef TCS_PRE_GROUP
+#define TCS_PRE_GROUP 16
+#endif
+constexpr int kPreThreads = TCS_PRE_THREADS;
+constexpr int kPreWarps = kPreThreads / 32;
+constexpr int kPreGroup = TCS_PRE_GROUP;     // channels per thread item (16, 32 or 64: whole sectors of the 16-bit rows)
+constexpr int kPreMaxGroups = 512 / kPreGroup;
 constexpr float kFp16OperandScale = 256.0f;  // unit-vector entries x 2^8 keep fp16 away from subnormals
 
 template <bool kFp16>
@@ -36,83 +44,72 @@ __device__ __forceinline__ uint32_t pack_hi_lo(float a, float b, uint32_t& lo_pa
     }
 }
 
-template <bool kFp16>
+// kItems: channel groups per thread (groups g = warp + kPreWarps * i): ceil(C / kPreGroup / kPreWarps) rounded up to 1, 2 or 4.
+template <bool kFp16, int kItems>
 __global__ void __launch_bounds__(kPreThreads)
 corr_prepass_kernel(const float* __restrict__ fmap, uint32_t* __restrict__ hi, uint32_t* __restrict__ lo,
                     float* __restrict__ n32, int C, int H, int W, int kblocked) {
-    extern __shared__ float tile[];  // [32][C + 1]
-    const int pitch = C + 1;
-    const int w0 = blockIdx.x * kPreTileW;
-    const int h = blockIdx.y;
-    const int b = blockIdx.z;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
+    __shared__ float part[kPreMaxGroups][kPreTileW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * kPreTileW + lane;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const bool live = w < W;
+    const int groups = C / kPreGroup;
+    const size_t plane = (size_t)H * W;
+    const float* src = fmap + ((size_t)b * C * H + h) * W + (live ? w : 0);
 
-    // ---- load [C][32] (w fastest in global) -> tile[w][c]
-    {
-        const int w4 = (tid % kPreLoadLanes) * 4;
-        const int c_off = tid / kPreLoadLanes;
-        const bool vec_ok = ((W & 3) == 0) && (w0 + w4 + 3 < W);
-        const size_t plane = (size_t)H * W;
-        const float* src = fmap + ((size_t)b * C * H + h) * W + w0 + w4;
-        for (int c = c_off; c < C; c += kPreThreads / kPreLoadLanes) {
-            const float* p = src + (size_t)c * plane;
-            float v[4];
-            if (vec_ok) {
-                float4 t = ldg_stream_f4(reinterpret_cast<const float4*>(p));
-                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-            } else {
+    // ---- every load of the thread first (kItems x 16 independent 4-byte loads, each a full line per warp)
+    float x[kItems][kPreGroup];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = (w0 + w4 + i < W) ? __ldg(p + i) : 0.0f;
-            }
+    for (int i = 0; i < kItems; ++i) {
+        const int g = warp + kPreWarps * i;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) tile[(w4 + i) * pitch + c] = v[i];
-        }
+        for (int k = 0; k < kPreGroup; ++k)
+            x[i][k] = (live && g < groups) ? ldg_stream_f1(src + (size_t)(g * kPreGroup + k) * plane) : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const int g = warp + kPreWarps * i;
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kPreGroup; ++k) acc = fmaf(x[i][k], x[i][k], acc);
+        if (g < groups) part[g][lane] = acc;
     }
     __syncthreads();
+    if (!live) return;
+    float ss = 0.0f;
+    for (int g = 0; g < groups; ++g) ss += part[g][lane];          // the same order in every thread of the pixel
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    const float rden = __frcp_rn(denom);
+    const size_t pix = ((size_t)b * H + h) * W + w;
 
-    // ---- per pixel: norm over channels, normalise, emit.  Each warp owns 4 pixels; their reductions are
-    // interleaved (independent shuffle chains) and x / denom uses the exact 3-instruction division by a
-    // loop-invariant denominator.
-    constexpr int kPix = kPreTileW / (kPreThreads / 32);   // 4
-    const int pairs = C >> 6;  // channel pairs per lane: channels 2*lane + 64*k, +1
-    float ss[kPix];
+    // ---- x / denom (the exact 3-instruction division by a loop-invariant denominator), split, emit
 #pragma unroll
-    for (int i = 0; i < kPix; ++i) {
-        const float* row = tile + (warp * kPix + i) * pitch;
-        float acc = 0.0f;
-        for (int c = lane; c < C; c += 32) {
-            const float v = row[c];
-            acc = fmaf(v, v, acc);
+    for (int i = 0; i < kItems; ++i) {
+        const int g = warp + kPreWarps * i;
+        if (g >= groups) break;                                     // warp-uniform
+        const int c = g * kPreGroup;
+        float v[kPreGroup];
+#pragma unroll
+        for (int k = 0; k < kPreGroup; ++k) v[k] = div_by_const(x[i][k], denom, rden);
+        if (n32 != nullptr) {
+            float4* o = reinterpret_cast<float4*>(n32 + pix * C + c);
+#pragma unroll
+            for (int k = 0; k < kPreGroup; k += 4) o[k >> 2] = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
         }
-        ss[i] = acc;
-    }
+        if (hi != nullptr) {
+            uint32_t ph[kPreGroup / 2], pl[kPreGroup / 2];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+            for (int k = 0; k < kPreGroup; k += 2) ph[k >> 1] = pack_hi_lo<kFp16>(v[k], v[k + 1], pl[k >> 1]);
+            // pixel-major [B,H,W,C] or K-block-major [B,H,C/64,W,64]: either way 16 channels are one aligned 32-byte sector
+            const size_t e = kblocked ? ((((size_t)b * H + h) * (C >> 6) + (c >> 6)) * W + w) * 64 + (c & 63) : pix * C + c;
+            uint4* oh = reinterpret_cast<uint4*>(hi + (e >> 1));
 #pragma unroll
-        for (int i = 0; i < kPix; ++i) ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], o);
+            for (int q = 0; q < kPreGroup / 8; ++q) oh[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+            if (lo != nullptr) {
+                uint4* ol = reinterpret_cast<uint4*>(lo + (e >> 1));
 #pragma unroll
-    for (int i = 0; i < kPix; ++i) {
-        const int wl = warp * kPix + i;
-        const int w = w0 + wl;
-        if (w >= W) break;  // warp-uniform
-        const float* row = tile + wl * pitch;
-        const float denom = fmaxf(sqrtf(ss[i]), 1e-12f);
-        const float rden = __frcp_rn(denom);
-        const size_t pix = ((size_t)b * H + h) * W + w;
-        for (int k = 0; k < pairs; ++k) {
-            const int c = 2 * lane + 64 * k;
-            const float a = div_by_const(row[c], denom, rden);
-            const float d = div_by_const(row[c + 1], denom, rden);
-            if (n32 != nullptr) *reinterpret_cast<float2*>(n32 + pix * C + c) = make_float2(a, d);
-            if (hi != nullptr) {
-                uint32_t lo_pack;
-                const uint32_t hi_pack = pack_hi_lo<kFp16>(a, d, lo_pack);
-                // pixel-major [B,H,W,C] or K-block-major [B,H,C/64,W,64]: either way this warp store is one 128-byte line
-                const size_t e = kblocked ? ((((size_t)b * H + h) * pairs + k) * W + w) * 64 + 2 * lane : pix * C + c;
-                hi[e >> 1] = hi_pack;
-                if (lo != nullptr) lo[e >> 1] = lo_pack;
+                for (int q = 0; q < kPreGroup / 8; ++q) ol[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
             }
         }
     }
@@ -147,22 +144,17 @@ static int launch_prepass(const float* fmap, void* hi, void* lo, float* n32, int
     TCS_REQUIRE(aligned16(fmap) && aligned16(hi) && aligned16(lo) && aligned16(n32), TCS_E_ALIGN,
                 "tcs_corr_prepass: pointers must be 16-byte aligned");
     const bool fp16 = (prec == TCS_PREC_FP16 || prec == TCS_PREC_FP16X3);
-    const size_t smem = (size_t)kPreTileW * (C + 1) * sizeof(float);
     dim3 grid(ceil_div(W, kPreTileW), H, B);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (fp16) {
-        TCS_ONCE_PER_DEVICE(
-            TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreTileW * 513 * 4));
-            { const int cv = carveout_percent("TCS_CARVE_PREPASS", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); }
-        );
-        corr_prepass_kernel<true><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W, kblocked);
-    } else {
-        TCS_ONCE_PER_DEVICE(
-            TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreTileW * 513 * 4));
-            { const int cv = carveout_percent("TCS_CARVE_PREPASS", -1); if (cv >= 0) TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_prepass_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cv)); }
-        );
-        corr_prepass_kernel<false><<<grid, kPreThreads, smem, s>>>(fmap, (uint32_t*)hi, (uint32_t*)lo, n32, C, H, W, kblocked);
-    }
+    uint32_t* h32 = static_cast<uint32_t*>(hi);
+    uint32_t* l32 = static_cast<uint32_t*>(lo);
+#define TCS_PREPASS_LAUNCH(F16, ITEMS) corr_prepass_kernel<F16, ITEMS><<<grid, kPreThreads, 0, s>>>(fmap, h32, l32, n32, C, H, W, kblocked)
+    const int per_thread = ceil_div(C / kPreGroup, kPreWarps);
+    static_assert(512 / kPreGroup <= 4 * kPreWarps, "prepass: at most 4 channel groups per thread");
+    if (per_thread <= 1) { if (fp16) TCS_PREPASS_LAUNCH(true, 1); else TCS_PREPASS_LAUNCH(false, 1); }
+    else if (per_thread <= 2) { if (fp16) TCS_PREPASS_LAUNCH(true, 2); else TCS_PREPASS_LAUNCH(false, 2); }
+    else { if (fp16) TCS_PREPASS_LAUNCH(true, 4); else TCS_PREPASS_LAUNCH(false, 4); }
+#undef TCS_PREPASS_LAUNCH
     TCS_CHECK_LAUNCH("tcs_corr_prepass");
     return 0;
 }
