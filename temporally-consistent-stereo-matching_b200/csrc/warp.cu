@@ -727,7 +727,10 @@ constexpr int kSampleCh = 16;
 
 // One (output pixel, channel group) of the gather: img_b / out_b are the sample's [C,Hi,Wi] / [C,Ho*Wo] planes.
 // kBatch: channels whose 4 corner loads are issued back to back before any is used.
-template <bool kFull, int kBatch = kSampleCh>   // kFull: C is a multiple of kSampleCh, no per-channel guards (keeps the loads batched)
+// Addresses: ONE 64-bit base per tensor and 32-bit element offsets (the hosts require C * H * W < 2^31), so that a load costs
+// a 32-bit add and one widening multiply-add instead of five 64-bit instructions: the kernel is bound by instruction issue
+// (67 % issue-active at 37 % DRAM with 57 instructions per output element before, profiles/r02_warp_kernels.md).
+template <bool kFull, int kBatch = kSampleCh, int kCh = kSampleCh>   // kFull: C is a multiple of kCh, no per-channel guards (keeps the loads batched)
 __device__ __forceinline__ void sample_group(const float* __restrict__ img_b, float gx, float gy, float* __restrict__ out_b,
                                              int C, int Hi, int Wi, int HWo, int i, int c_begin) {
     const float wm1 = (float)(Wi - 1), hm1 = (float)(Hi - 1);
@@ -748,22 +751,27 @@ __device__ __forceinline__ void sample_group(const float* __restrict__ img_b, fl
     const float w_ne = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(y1f, iy));
     const float w_sw = __fmul_rn(__fsub_rn(x1f, ix), __fsub_rn(iy, y0f));
     const float w_se = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(iy, y0f));
-    const int o_nw = y0 * Wi + x0, o_ne = y0 * Wi + x1, o_sw = y1 * Wi + x0, o_se = y1 * Wi + x1;
-    const size_t plane_i = (size_t)Hi * Wi;
-    const float* src = img_b + (size_t)c_begin * plane_i;
-    float* dst = out_b + (size_t)c_begin * HWo + i;
+    // Four corner addresses and the output address walk the channel planes as plain 64-bit BYTE addresses (one add-with-carry
+    // pair each per channel).  Written as pointers or as base[index] the compiler keeps element indices and rebuilds every
+    // address with a 64-bit add and a 64-bit shift-add: 31 integer instructions per channel against 11 of useful work.
+    const uint64_t plane_b = (uint64_t)Hi * Wi * 4u, out_b_step = (uint64_t)HWo * 4u;
+    const uint64_t src = reinterpret_cast<uint64_t>(img_b) + (uint64_t)c_begin * plane_b;
+    uint64_t a_nw = src + 4u * (uint64_t)(unsigned)(y0 * Wi + x0), a_ne = src + 4u * (uint64_t)(unsigned)(y0 * Wi + x1);
+    uint64_t a_sw = src + 4u * (uint64_t)(unsigned)(y1 * Wi + x0), a_se = src + 4u * (uint64_t)(unsigned)(y1 * Wi + x1);
+    uint64_t a_dst = reinterpret_cast<uint64_t>(out_b) + ((uint64_t)c_begin * HWo + i) * 4u;
 #pragma unroll
-    for (int k0 = 0; k0 < kSampleCh; k0 += kBatch) {
+    for (int k0 = 0; k0 < kCh; k0 += kBatch) {
         float v[kBatch][4];
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
             const int k = k0 + j;
-            const bool live = kFull || (c_begin + k < C);
-            const float* s = src + (live ? (size_t)k * plane_i : 0);
-            v[j][0] = ldg_ordered_f1(s + o_nw);
-            v[j][1] = ldg_ordered_f1(s + o_ne);
-            v[j][2] = ldg_ordered_f1(s + o_sw);
-            v[j][3] = ldg_ordered_f1(s + o_se);
+            v[j][0] = ldg_ordered_f1(reinterpret_cast<const float*>(a_nw));
+            v[j][1] = ldg_ordered_f1(reinterpret_cast<const float*>(a_ne));
+            v[j][2] = ldg_ordered_f1(reinterpret_cast<const float*>(a_sw));
+            v[j][3] = ldg_ordered_f1(reinterpret_cast<const float*>(a_se));
+            if (kFull || c_begin + k + 1 < C) {                     // a dead channel re-reads the last live one
+                a_nw += plane_b; a_ne += plane_b; a_sw += plane_b; a_se += plane_b;
+            }
         }
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
@@ -775,7 +783,8 @@ __device__ __forceinline__ void sample_group(const float* __restrict__ img_b, fl
             if (ne) r = __fadd_rn(r, __fmul_rn(v[j][1], w_ne));
             if (sw) r = __fadd_rn(r, __fmul_rn(v[j][2], w_sw));
             if (se) r = __fadd_rn(r, __fmul_rn(v[j][3], w_se));
-            stg_stream_f1(dst + (size_t)k * HWo, r);
+            stg_stream_f1(reinterpret_cast<float*>(a_dst), r);
+            a_dst += out_b_step;
         }
     }
 }
@@ -877,7 +886,12 @@ __device__ __noinline__ float2 hidden3_grid(const float* __restrict__ g0, int l,
     return make_float2(g[0], g[1]);
 }
 
-template <bool kFull>   // every level's channel count is a multiple of kSampleCh
+#ifndef TCS_HIDDEN_CH
+#define TCS_HIDDEN_CH 32
+#endif
+constexpr int kHiddenCh = TCS_HIDDEN_CH;   // channels per thread: the per-pixel set-up (grid halving, two exact divisions) is paid once per group
+
+template <bool kFull>   // every level's channel count is a multiple of kHiddenCh
 __global__ void __launch_bounds__(256)
 warp_hidden3_kernel(const Hidden3Params p) {
     const int b = blockIdx.z;
@@ -887,7 +901,7 @@ warp_hidden3_kernel(const Hidden3Params p) {
     const int Hl = l == 0 ? p.H[0] : l == 1 ? p.H[1] : p.H[2];
     const int Wl = l == 0 ? p.W[0] : l == 1 ? p.W[1] : p.W[2];
     const int Cl = l == 0 ? p.C[0] : l == 1 ? p.C[1] : p.C[2];
-    const int c_begin = blockIdx.y * kSampleCh;
+    const int c_begin = blockIdx.y * kHiddenCh;
     if (c_begin >= Cl) return;                                   // block-uniform
     const int HWl = Hl * Wl;
     const int i = bx * 256 + threadIdx.x;
@@ -901,7 +915,7 @@ warp_hidden3_kernel(const Hidden3Params p) {
 #ifndef TCS_HIDDEN_BATCH
 #define TCS_HIDDEN_BATCH 8
 #endif
-    sample_group<kFull, TCS_HIDDEN_BATCH>(img_b, g[0], g[1], out_b, Cl, Hl, Wl, HWl, i, c_begin);   // 8: 44 registers, 5 CTAs per SM
+    sample_group<kFull, TCS_HIDDEN_BATCH, kHiddenCh>(img_b, g[0], g[1], out_b, Cl, Hl, Wl, HWl, i, c_begin);   // 8: 44 registers, 5 CTAs per SM
 }
 
 static size_t align256(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
@@ -1057,7 +1071,8 @@ extern "C" int tcs_bilinear_sample(const float* img, const float* grid_xy, float
     TCS_REQUIRE(B > 0 && B <= 65535 && C > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, TCS_E_BADARG, "tcs_bilinear_sample: bad sizes");
     const int groups = ceil_div(C, kSampleCh);
     TCS_REQUIRE(groups <= 65535, TCS_E_SHAPE, "tcs_bilinear_sample: C too large");
-    TCS_REQUIRE((long long)Hi * Wi < 0x7fffffffLL, TCS_E_SHAPE, "tcs_bilinear_sample: image plane too large");
+    TCS_REQUIRE((long long)groups * kSampleCh * Hi * Wi < 0x7fffffffLL && (long long)groups * kSampleCh * Ho * Wo < 0x7fffffffLL, TCS_E_SHAPE,
+                "tcs_bilinear_sample: C * H * W must stay below 2^31 (32-bit element offsets per sample)");
     dim3 g(ceil_div(Ho * Wo, 256), groups, B);
     if (C % kSampleCh == 0)
         bilinear_sample_kernel<true><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(img, grid_xy, out, C, Hi, Wi, Ho, Wo);
@@ -1095,12 +1110,13 @@ extern "C" int tcs_warp_hidden_states(const float* net0, const float* net1, cons
     for (int l = 1; l < 3; ++l) { p.H[l] = p.H[l - 1] / 2; p.W[l] = p.W[l - 1] / 2; }     // F.interpolate(scale_factor=0.5): floor
     int cmax = C0 > C1 ? C0 : C1;
     if (C2 > cmax) cmax = C2;
-    const int groups = ceil_div(cmax, kSampleCh);
+    const int groups = ceil_div(cmax, kHiddenCh);
     TCS_REQUIRE(groups <= 65535, TCS_E_SHAPE, "tcs_warp_hidden_states: C too large");
+    TCS_REQUIRE((long long)groups * kHiddenCh * H * W < 0x7fffffffLL, TCS_E_SHAPE, "tcs_warp_hidden_states: C * H * W must stay below 2^31");
     long long bx = 0;
     for (int l = 0; l < 3; ++l) { p.blocks[l] = ceil_div(p.H[l] * p.W[l], 256); bx += p.blocks[l]; }
     dim3 g((unsigned)bx, groups, B);
-    if (C0 % kSampleCh == 0 && C1 % kSampleCh == 0 && C2 % kSampleCh == 0)
+    if (C0 % kHiddenCh == 0 && C1 % kHiddenCh == 0 && C2 % kHiddenCh == 0)
         warp_hidden3_kernel<true><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     else
         warp_hidden3_kernel<false><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
