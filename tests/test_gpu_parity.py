@@ -64,6 +64,27 @@ def test_prepass_normalise(tcs):
     assert np.abs(split16 - host(n32)).max() <= 2.0 ** -20, "fp16 hi+lo"
 
 
+@pytest.mark.parametrize("C", [64, 128, 192, 256, 320, 512])
+@pytest.mark.parametrize("W", [1, 31, 33, 100])
+def test_prepass_channel_counts_and_ragged_widths(tcs, C, W):
+    """Every channel-group split of the pre-pass (1, 2 or 4 groups per thread, idle warps at C = 64) and widths that leave
+    partial 32-pixel tiles; the K-block-major operands are the pixel-major ones re-laid out, bit for bit."""
+    f1, _ = make_fmaps(2, C, 3, W, 100 + C + W)
+    f1[0, :, 1, 0] = 0.0                                           # an all-zero pixel: x / max(0, 1e-12) = 0 (corr.py:58)
+    hi, lo, n32 = tcs.normalized_operands(f1.cuda(), "fp16x3", want_n32=True)
+    ref = orc.normalize_features(f1.numpy()).transpose(0, 2, 3, 1)
+    assert_close(host(n32), ref, rtol=1e-6, atol=1e-7, what="n32 C=%d W=%d" % (C, W))
+    assert np.all(host(n32)[0, 1, 0] == 0.0)
+    split = (host(hi.float()) + host(lo.float())) / 256.0
+    assert np.abs(split - host(n32)).max() <= 2.0 ** -20
+    hk, lk, _ = tcs.normalized_operands(f1.cuda(), "fp16x3", kblocked=True)
+    for a, k in ((hi, hk), (lo, lk)):
+        relaid = a.view(2, 3, W, C // 64, 64).permute(0, 1, 3, 2, 4).contiguous()
+        assert torch.equal(relaid, k), "K-block-major operands differ from the pixel-major ones"
+    hb, lb, _ = tcs.normalized_operands(f1.cuda(), "bf16x3")
+    assert np.abs(host(hb.float()) + host(lb.float()) - host(n32)).max() <= 2.0 ** -16
+
+
 @pytest.mark.parametrize("case", ["corr_small", "corr_oddwidth", "corr_oddshift"])
 @pytest.mark.parametrize("precision,rtol,atol", [("fp32", 1e-5, 1e-6), ("fp16x3", 1e-5, 1e-6), ("bf16x3", 1e-5, 8e-6),
                                                  ("bf16", 0.0, 2.0 ** -8), ("fp16", 0.0, 2.0 ** -10)])
