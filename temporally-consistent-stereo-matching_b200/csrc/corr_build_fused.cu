@@ -35,10 +35,14 @@ constexpr int kBlockK = 32;                         // channels per pipeline sta
 constexpr int kUmmaK = 16;
 constexpr int kMaxN = 240;                          // one N tile
 constexpr int kMaxW1 = 256;
-constexpr int kStages = 2;                          // operand tile stages
+#ifndef TCS_FUSED_CTAS
+#define TCS_FUSED_CTAS 1                            // CTAs per SM: 2 = half-size CTAs whose norm and convert passes interleave on the SM
+#endif
+constexpr int kCtasPerSm = TCS_FUSED_CTAS;
+constexpr int kStages = kCtasPerSm == 2 ? 1 : 2;    // operand tile stages
 constexpr int kSlotK = 16;                          // channels per staging slot (two slots feed one operand stage)
 #ifndef TCS_FUSED_SLOTS
-#define TCS_FUSED_SLOTS 5
+#define TCS_FUSED_SLOTS (TCS_FUSED_CTAS == 2 ? 2 : 5)
 #endif
 constexpr int kSlots = TCS_FUSED_SLOTS;             // fp32 staging slots: three in flight while one is converted
 constexpr int kATile = kBlockM * kBlockK * 2;       // 8 KB
@@ -47,11 +51,14 @@ constexpr int kStageBytes = 2 * kATile + 2 * kBTile;    // A_hi, A_lo, B_hi, B_l
 constexpr int kABox = kSlotK * kBlockM * 4;         // 8 KB of fp32
 constexpr int kBBox = kSlotK * kMaxN * 4;           // 15 KB of fp32 (box width = block_n <= 240)
 constexpr int kSlotBytes = kABox + kBBox;           // 23 KB
-constexpr int kXSlots = 4;                          // norm pass only: the (then idle) operand stages serve as extra staging slots
-constexpr int kAccStages = 2;
+constexpr int kXSlots = kCtasPerSm == 2 ? 2 : 4;    // norm pass only: the (then idle) operand stages serve as extra staging slots
+constexpr int kAccStages = kCtasPerSm == 2 ? 1 : 2;
 constexpr int kAccCols = 256;
 constexpr int kTmemCols = kAccStages * kAccCols;
-constexpr int kConvWarps = 10;
+#ifndef TCS_FUSED_CONV_WARPS
+#define TCS_FUSED_CONV_WARPS (TCS_FUSED_CTAS == 2 ? 6 : 10)
+#endif
+constexpr int kConvWarps = TCS_FUSED_CONV_WARPS;
 constexpr int kConvThreads = kConvWarps * 32;       // 320
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 32 * (2 + kConvWarps + kEpiWarps);   // 512
@@ -59,7 +66,7 @@ constexpr int kEpiStageBytes = 4096;                // per epilogue warp: [32][3
 constexpr int kInvBytes = (kMaxW1 + 256) * 4;       // 1/norm of the A pixels, then of the B pixels
 constexpr int kBarrierBytes = 256;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kSlots * kSlotBytes + kEpiWarps * kEpiStageBytes + kInvBytes + kBarrierBytes;
-static_assert(kSmemBytes <= 232448, "fused build: shared memory budget exceeded");
+static_assert(kSmemBytes <= 232448 / kCtasPerSm - (kCtasPerSm - 1) * 1024, "fused build: shared memory budget exceeded");
 static_assert(kXSlots * kSlotBytes <= kStages * kStageBytes, "extra norm-pass slots live inside the operand stages");
 constexpr int kRing1 = kSlots + kXSlots;            // staging ring of the norm pass
 static_assert(8 * (2 * kRing1 + 2 * kStages + 2 * kAccStages + 1) + 4 <= kBarrierBytes, "barrier area");
@@ -78,6 +85,8 @@ struct Params {
     float out_scale;   // undoes the operand scaling in the epilogue
     float in_scale;    // 2^8 for fp16 operands (keeps unit-vector entries away from subnormals), 1 for bf16
     int tma_store;     // levels 0 and 1 leave through TMA (needs W2 % 8 == 0)
+    int tile_mode;     // work items are single M tiles (unit u = k * grid + cta), not whole rows
+    int stagger_ns;    // two CTAs per SM: the second half of the grid starts this much later, so that the pair's passes interleave
 };
 
 template <bool kFp16>
@@ -97,6 +106,11 @@ __device__ __forceinline__ void split16(float a, float b, uint32_t& hi, uint32_t
     }
 }
 
+__device__ __forceinline__ unsigned long long ptx_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void conv_barrier() {   // converters only (named barrier 1)
     asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");
 }
@@ -223,6 +237,13 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpilogueArgs& p, const C
 // the tail costs one tile rather than one row.
 __device__ __forceinline__ bool work_item(const Params& p, int k, int& row, int& m_lo, int& m_hi) {
     const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
+    if (p.tile_mode) {
+        const int u = k * grid + cta;
+        if (u >= p.num_rows * p.num_m) return false;
+        row = u / p.num_m;
+        m_lo = u - row * p.num_m; m_hi = m_lo + 1;
+        return true;
+    }
     const int waves = p.num_rows / grid;
     m_lo = 0; m_hi = p.num_m;
     if (k < waves) { row = k * grid + cta; return true; }
@@ -239,7 +260,7 @@ __device__ __forceinline__ bool work_item(const Params& p, int k, int& row, int&
 }
 
 template <bool kFp16>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                         const __grid_constant__ CUtensorMap tm_l0, const __grid_constant__ CUtensorMap tm_l1, const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -305,8 +326,8 @@ corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
             int row, m_lo, m_hi;
             for (int k = 0; work_item(p, k, row, m_lo, m_hi); ++k) {
                 for (int m_t = m_lo; m_t < m_hi; ++m_t, ++iter) {
-                    const uint32_t acc = iter & 1;
-                    const uint32_t acc_phase = (iter >> 1) & 1;
+                    const uint32_t acc = iter % kAccStages;
+                    const uint32_t acc_phase = (iter / kAccStages) & 1;
                     ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                     ptx::tc_fence_after_sync();
                     const uint32_t tmem_d = tmem_base + acc * kAccCols;
@@ -339,6 +360,10 @@ corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
         // Per row: pass 1 (A tile of every M tile, B only with the first), then pass 2 (A tile + B for every M tile).
         if (lane == 0) {
             uint32_t bits = 0;                         // per-slot phase parity (the two passes use rings of different length)
+            if (p.stagger_ns > 0 && (int)blockIdx.x >= ((int)gridDim.x + 1) / 2) {
+                const unsigned long long t0 = ptx_globaltimer();
+                while (ptx_globaltimer() - t0 < (unsigned long long)p.stagger_ns) __nanosleep(200);
+            }
             int rows_done = 0;
             int row, m_lo, m_hi;
             for (; work_item(p, rows_done, row, m_lo, m_hi); ++rows_done) {
@@ -459,8 +484,8 @@ corr_build_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
         int row, m_lo, m_hi;
         for (int k = 0; work_item(p, k, row, m_lo, m_hi); ++k) {
             for (int m_t = m_lo; m_t < m_hi; ++m_t, ++iter) {
-                const uint32_t acc = iter & 1;
-                const uint32_t acc_phase = (iter >> 1) & 1;
+                const uint32_t acc = iter % kAccStages;
+                const uint32_t acc_phase = (iter / kAccStages) & 1;
                 ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 ptx::tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols;
@@ -568,7 +593,12 @@ extern "C" int tcs_corr_build_fused(const float* fmap1, const float* fmap2,
         TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_build_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     );
     const int units = p.num_rows * p.num_m;
-    const int grid = units < num_sms() ? units : num_sms();
+    const int ctas = kCtasPerSm * num_sms();
+    const int grid = units < ctas ? units : ctas;
+    p.tile_mode = kCtasPerSm == 2 ? 1 : 0;
+    { const char* e = getenv("TCS_FUSED_TILE_MODE"); if (e != nullptr) p.tile_mode = atoi(e) != 0; }
+    p.stagger_ns = 0;
+    if (kCtasPerSm == 2 && grid > num_sms()) { const char* e = getenv("TCS_FUSED_STAGGER_NS"); p.stagger_ns = e != nullptr ? atoi(e) : 10000; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (fp16) corr_build_fused_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(tma, tmb, tml0, tml1, p);
     else corr_build_fused_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(tma, tmb, tml0, tml1, p);
