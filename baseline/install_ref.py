@@ -6,8 +6,8 @@ baseline/_ref/ is git-ignored (nothing of the reference enters this repository's
 gpurun-ignored, so it travels to the GPU box, where /root/reference does not exist.  The reference has no
 setup.py / pyproject, so `pip install --target baseline/_ref /root/reference` has nothing
 to build; this script is the install: a byte-for-byte copy of the eleven Python files that TCStereo.forward
-imports (core/tc_stereo.py:1-8 and their own imports), checked by size.  The drivers (evaluate_stereo.py,
-train_stereo.py) hard-require wandb / skimage / pykitti and are not copied.
+imports (core/tc_stereo.py:1-8 and their own imports) plus train_stereo.py for its init_loss().  The drivers (evaluate_stereo.py,
+train_stereo.py) hard-require wandb / skimage / pykitti and are never imported.
 
 Used by: oracle/ref_model.py (tests, bench.py --impl reference-gpu, the cpu arm).  Never by the product path.
 """
@@ -30,6 +30,7 @@ FILES = [
     "core/utils/basic_layers.py",
     "core/utils/splatting/__init__.py",
     "core/utils/splatting/softsplat.py",
+    "train_stereo.py",          # never imported (it needs wandb): oracle/ref_model.load_init_loss() extracts init_loss() from its source
 ]
 
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCS_ABI_VERSION 9
+#define TCS_ABI_VERSION 10
 
 /* argument errors (negative); CUDA launch errors are returned as positive cudaError_t values */
 #define TCS_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported combination */
@@ -250,6 +250,22 @@ int tcs_convex_upsample(const float* flow, const float* mask, float* out, int N,
  *   grad_out [B, num_levels*(2r+1), H, W1] fp32, coords as for tcs_corr_lookup, grad_volume [B,H,W1,W2] fp32 (out, dense). */
 int tcs_corr_lookup_backward(const float* grad_out, const float* coords, long long coords_bstride, float* grad_volume,
                              int B, int H, int W1, int W2, int num_levels, int radius, void* stream);
+
+/* ref: train_stereo.py:150-172 (init_loss: the per-pixel terms of the cost-volume initialisation loss), on level 0 of the pyramid
+ * instead of the masked transposed cost volume of core/corr.py:25-31 (cv[b,w2,h,w1] = level0[b,h,w1,w2] * [w2 <= w1]):
+ *   phi[b,h,w1]       = frac * rho(df + 1) + (1 - frac) * rho(df), df = floor(index_gt), rho(i) = cv[clip(i, 0, W2-1)]   (:151-158)
+ *   cost_nm[b,j,h,w1] = j-th largest entry along w2 of cv with [index_gt - 1.5, index_gt + 1.5) and every column of a pixel
+ *                       whose mask is 0 filled with 0 (:166-171), j < k <= 8
+ *   idx_nm[b,j,h,w1]  = its w2, or -1 when it is a filled / masked zero (no gradient reaches the volume through it)
+ * level0 [B,H,W1,W2_pitch] fp32 (W2_pitch 0 = dense), index_gt [B,H,W1] fp32 already clipped to [0, W2-1] (:164), mask [B,H,W1]
+ * bytes (:162-163).  W2 <= 512.  Ties go to the lowest w2. */
+int tcs_init_loss_forward(const float* level0, int W2_pitch, const float* index_gt, const unsigned char* mask,
+                          float* phi, float* cost_nm, int* idx_nm, int B, int H, int W1, int W2, int k, void* stream);
+
+/* The autograd of the above (torch.gather / masked_fill / topk backward in the reference): grad_level0 [B,H,W1,W2] fp32, dense,
+ * zero-filled here, then (1 - frac) g_phi and frac g_phi at the two gathered entries and grad_cost_nm at idx_nm >= 0. */
+int tcs_init_loss_backward(const float* grad_phi, const float* grad_cost_nm, const float* index_gt, const int* idx_nm,
+                           float* grad_level0, int B, int H, int W1, int W2, int k, void* stream);
 
 /* ---- (6) "next" row: input stems of the disparity completion network ------------------ */
 

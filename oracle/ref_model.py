@@ -52,6 +52,27 @@ def load():
     return _loaded
 
 
+def load_init_loss(root=None):
+    """The reference's own init_loss (train_stereo.py:138-182) as a function.  train_stereo.py cannot be imported (wandb,
+    skimage, pykitti are absent), so the function definition is cut out of its source with `ast` and compiled on its own; it
+    needs only torch and torch.nn.functional."""
+    import ast
+    import torch
+    import torch.nn.functional as F
+    root = root or reference_root()
+    path = os.path.join(root, "train_stereo.py") if root else None
+    if not path or not os.path.exists(path):
+        raise ImportError("train_stereo.py of the reference is not installed (python baseline/install_ref.py)")
+    src = open(path).read()
+    tree = ast.parse(src)
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "init_loss"]
+    if len(fn) != 1:
+        raise ImportError("init_loss not found in %s" % path)
+    ns = {"torch": torch, "F": F}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)
+    return ns["init_loss"]
+
+
 def use_cpu_splat(ref, threaded=False):
     """CPU runs: replace the cupy kernel launch by a restatement of softsplat.py:284-335 — the numpy oracle's
     (sequential, the parity checker) or, threaded=True, torch_port.splat (index_add_ on all host threads: the CPU

@@ -421,3 +421,83 @@ def convex_upsample(flow, mask, factor=4, scale=True):
     for k in range(9):
         out = (out + w[:, :, k] * up[:, :, k][:, :, None, None]).astype(F32)
     return out.transpose(0, 1, 4, 2, 5, 3).reshape(N, D, factor * H, factor * W)     # permute(0,1,4,2,5,3)
+
+
+# ------------------------------------------------------------------------------------------------------
+# (7) training: the cost-volume initialisation loss
+# ------------------------------------------------------------------------------------------------------
+
+def _interp_nearest_down(x, scale):
+    """F.interpolate(x, scale_factor=scale, mode='nearest') for 1/scale an integer: output (i, j) takes input
+    (floor(i / scale), floor(j / scale)); output size floor(in * scale)."""
+    step = int(round(1.0 / scale))
+    Ho, Wo = int(np.floor(x.shape[-2] * scale)), int(np.floor(x.shape[-1] * scale))
+    return x[..., :Ho * step:step, :Wo * step:step]
+
+
+def _interp_bilinear_ac(x, scale):
+    """F.interpolate(x, scale_factor=scale, mode='bilinear', align_corners=True): source = dst * (in - 1) / (out - 1)."""
+    B, C, H, W = x.shape
+    Ho, Wo = int(np.floor(H * scale)), int(np.floor(W * scale))
+    ys = np.arange(Ho, dtype=F32) * (F32(H - 1) / F32(max(Ho - 1, 1)))
+    xs = np.arange(Wo, dtype=F32) * (F32(W - 1) / F32(max(Wo - 1, 1)))
+    y0 = np.minimum(np.floor(ys).astype(np.int64), H - 1)
+    x0 = np.minimum(np.floor(xs).astype(np.int64), W - 1)
+    y1, x1 = np.minimum(y0 + 1, H - 1), np.minimum(x0 + 1, W - 1)
+    wy, wx = (ys - y0.astype(F32)).reshape(1, 1, Ho, 1), (xs - x0.astype(F32)).reshape(1, 1, 1, Wo)
+    top = x[:, :, y0][:, :, :, x0] * (F32(1) - wx) + x[:, :, y0][:, :, :, x1] * wx
+    bot = x[:, :, y1][:, :, :, x0] * (F32(1) - wx) + x[:, :, y1][:, :, :, x1] * wx
+    return _f(top * (F32(1) - wy) + bot * wy)
+
+
+def init_loss(cost_volume, flow_gt, valid, max_flow=700, k=1, scale=0.25, threshold=0.1, valid_interp=None):
+    """ref: train_stereo.py:138-182.  cost_volume [B,D,H,W] (corr.py:25-31), flow_gt [B,1,Hf,Wf], valid [B,1,Hf,Wf].
+    Returns a dict: the loss and its terms, the per-pixel phi_gt / cost_nm / mask, and d loss / d cost_volume (the gradient
+    torch.gather, masked_fill and topk pass back; ties in topk: lowest index).
+    valid_interp: torch's own result of line 143 (the bilinear interpolation of `valid`).  The reference then tests it with
+    `== 1`, so the LAST BIT of a float interpolation of ones decides whether a pixel counts, and that bit differs between this
+    restatement, torch's CPU kernel and torch's CUDA kernel (0.99999994 vs 1.0 at 2 of 480 pixels of the golden case); the pin
+    against the reference's output therefore takes torch's interpolation as given."""
+    cv = _f(cost_volume)
+    B, D, H, W = cv.shape
+    flow = _f(F32(scale) * _interp_nearest_down(_f(flow_gt), scale))                                   # :141
+    val = _f(valid_interp) if valid_interp is not None else _interp_bilinear_ac(_f(valid), scale)      # :143
+    mag = np.sqrt(np.sum(flow * flow, axis=1, keepdims=True))                                          # :145
+    val = (val == 1) & (mag < F32(max_flow * scale))                                                   # :148
+    index_gt = _f(np.arange(W, dtype=F32).reshape(1, 1, 1, W) - (-flow))                               # :160-161
+    mask = (index_gt >= 0) & (index_gt <= D - 1) & val                                                 # :162-163
+    index_gt = np.clip(index_gt, 0, D - 1).astype(F32)                                                 # :164
+    bb, hh, ww = np.meshgrid(np.arange(B), np.arange(H), np.arange(W), indexing="ij")
+
+    def rho(d):                                                                                        # :150-152
+        d = np.clip(d, 0, D - 1)
+        return cv[bb, d[:, 0], hh, ww][:, None]
+
+    df = np.floor(index_gt).astype(np.int64)                                                           # :155
+    frac = _f(index_gt - df.astype(F32))
+    phi = _f(_f(frac * rho(df + 1)) + _f(_f(F32(1) - frac) * rho(df)))                                 # :158
+    n_mask = int(mask.sum())
+    gt_loss = F32(1) - F32(phi[mask].astype(np.float64).mean()) if n_mask else F32(np.nan)             # :166
+    rng = np.arange(D, dtype=F32).reshape(1, D, 1, 1)
+    low, high = _f(index_gt - F32(1.5)), _f(index_gt + F32(1.5))                                       # :169-170
+    filled = ((rng >= low) & (rng < high)) | ~mask                                                     # :171
+    cv_nm = np.where(filled, F32(0), cv)
+    order = np.argsort(-cv_nm, axis=1, kind="stable")[:, :k]                                           # :173 topk, descending
+    cost_nm = np.take_along_axis(cv_nm, order, axis=1)
+    hinge = _f(cost_nm + F32(threshold) - phi)                                                         # :174
+    active = (hinge > 0) & np.repeat(mask, k, axis=1)
+    nm_loss = F32(np.clip(hinge, 0, None)[np.repeat(mask, k, axis=1)].astype(np.float64).mean()) if n_mask else F32(np.nan)
+    # ---- gradient w.r.t. cost_volume
+    g = np.zeros_like(cv)
+    if n_mask:
+        gphi = np.where(mask, F32(-1.0 / n_mask), F32(0))                                              # d gt_loss / d phi (phi is detached in nm_loss)
+        i0, i1 = np.clip(df, 0, D - 1), np.clip(df + 1, 0, D - 1)
+        np.add.at(g, (bb, i0[:, 0], hh, ww), (_f(F32(1) - frac) * gphi)[:, 0])
+        np.add.at(g, (bb, i1[:, 0], hh, ww), (frac * gphi)[:, 0])
+        gnm = np.where(active, F32(1.0 / (n_mask * k)), F32(0))
+        for j in range(k):
+            through = ~np.take_along_axis(filled, order[:, j:j + 1], axis=1)                           # masked_fill passes no gradient
+            np.add.at(g, (bb, order[:, j], hh, ww), (gnm[:, j:j + 1] * through)[:, 0])
+    return {"loss": F32(gt_loss + nm_loss), "gt_loss": gt_loss, "nm_loss": nm_loss,
+            "forward_mask_rate": F32(((cost_nm[:, :1] + F32(0.3) - phi) > 0).astype(F32).mean()),       # :180
+            "phi": phi, "cost_nm": cost_nm, "mask": mask, "index_gt": index_gt, "grad_cost_volume": g}

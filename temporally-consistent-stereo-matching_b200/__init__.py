@@ -19,10 +19,10 @@ from .geo import (bilinear_sampler, cal_relative_transformation, get_backward_gr
 from .dropin import install, uninstall, strip_asserts, restore_asserts  # noqa: E402
 from .graphed import graph_modules, ungraph_modules  # noqa: E402
 from .completor import completor_stems, fuse_completor_stems, unfuse_completor_stems, pack_stem_weights  # noqa: E402
-from .train import DifferentiableCorrBlock1D  # noqa: E402
+from .train import DifferentiableCorrBlock1D, LazyCostVolume, init_loss  # noqa: E402
 from .sequence import HotPathRunner, hot_path_frame, shard_sequences  # noqa: E402
 
-__all__ = ["CorrBlock1D", "DifferentiableCorrBlock1D", "build_pyramid", "normalized_operands", "warp", "warp_with_cost", "WarpCarry", "get_backward_grid",
+__all__ = ["CorrBlock1D", "DifferentiableCorrBlock1D", "LazyCostVolume", "init_loss", "build_pyramid", "normalized_operands", "warp", "warp_with_cost", "WarpCarry", "get_backward_grid",
            "disp2disp_gradient_xy", "disp2disp_grad_candidates", "propagate_disparity", "convex_upsample",
            "bilinear_sampler", "sample_planar", "halve_grid", "warp_hidden_states", "cal_relative_transformation",
            "install", "uninstall", "strip_asserts", "restore_asserts", "graph_modules", "ungraph_modules", "completor_stems", "fuse_completor_stems", "unfuse_completor_stems", "pack_stem_weights", "HotPathRunner", "hot_path_frame", "shard_sequences"]

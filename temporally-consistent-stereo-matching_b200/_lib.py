@@ -14,7 +14,7 @@ PREC_BF16, PREC_BF16X3, PREC_FP16, PREC_FP16X3 = 0, 1, 2, 3
 PRECISIONS = {"bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16, "fp16x3": PREC_FP16X3}
 MAX_LEVELS = 4
 MAX_RADIUS = 8
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -33,6 +33,8 @@ SIGNATURES = {
     "tcs_corr_lookup": (_i, [_p, _p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_lookup_encode": (_i, [_p, _p, _p, _p, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_lookup_backward": (_i, [_p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "tcs_init_loss_forward": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "tcs_init_loss_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "tcs_fmap_pool_w": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "tcs_corr_lookup_alt": (_i, [_p, _p, _p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_lookup_alt_tc": (_i, [_p, _p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p]),

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libtcs_b200.so")
 
-SOURCES = ["runtime.cu", "corr_prepass.cu", "corr_build.cu", "corr_build_fused.cu", "corr_build_fp32.cu", "corr_lookup.cu", "corr_lookup_alt_tc.cu", "warp.cu", "stencils.cu", "pose.cu", "completor.cu"]
+SOURCES = ["runtime.cu", "corr_prepass.cu", "corr_build.cu", "corr_build_fused.cu", "corr_build_fp32.cu", "corr_lookup.cu", "corr_lookup_alt_tc.cu", "warp.cu", "stencils.cu", "pose.cu", "completor.cu", "init_loss.cu"]
 HEADERS = ["tcs_common.cuh", "sm100_ptx.cuh", "corr_epilogue.cuh", "tma_host.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"] + os.environ.get("TCS_B200_NVCC_EXTRA", "").split()     # e.g. -DTCS_PRE_TILE_W=64 (experiments)

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libtcs_b200.so does not export %s" % n
     assert sorted(tcs_b200._lib.SIGNATURES) == names, "ctypes signatures and header disagree"
-    assert lib.tcs_abi_version() == tcs_b200._lib.ABI_VERSION == 9
+    assert lib.tcs_abi_version() == tcs_b200._lib.ABI_VERSION == 10
 
 
 def test_argument_errors_are_reported_without_a_gpu():

@@ -848,3 +848,42 @@ def test_second_device_in_the_same_process(tcs):
             assert torch.allclose(a, b, rtol=1e-5, atol=2e-6) and torch.allclose(a, c, rtol=1e-5, atol=2e-6)
         else:
             assert torch.equal(a, b) and torch.equal(a, c), "output %d differs between devices" % i
+
+
+# ---------------------------------------------------------------------------------------------------------
+# training: the cost-volume initialisation loss on level 0
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_init_loss_kernel_matches_the_oracle_on_the_golden_case(tcs, precision):
+    """tcs_b200.init_loss (one kernel each way on the pyramid's level 0) against the oracle on the case whose loss the reference's
+    own init_loss produced; the interpolation of `valid` is torch's on this device (see the oracle's docstring)."""
+    import torch.nn.functional as F
+    g = load_golden("init_loss_small")
+    k, thr = int(g["k"]), float(g["threshold"])
+    f1, f2 = cuda(g["fmap1"]).requires_grad_(True), cuda(g["fmap2"]).requires_grad_(True)
+    flow, valid = cuda(g["flow_gt"]), cuda(g["valid"])
+    blk = tcs.DifferentiableCorrBlock1D(f1, f2, precision=precision)
+    cv = blk.get_cost_volume()
+    assert isinstance(cv, tcs.LazyCostVolume) and cv.size(1) == g["cost_volume"].shape[1]
+    loss, metrics = tcs.init_loss(cv, flow, valid, k=k, scale=0.25, threshold=thr)
+    vi = F.interpolate(valid, scale_factor=0.25, mode="bilinear", align_corners=True)
+    o = orc.init_loss(host(cv.materialize()), g["flow_gt"], g["valid"], k=k, scale=0.25, threshold=thr, valid_interp=host(vi))
+    assert abs(metrics["init_gt_loss"] - float(o["gt_loss"])) <= 2e-6
+    assert abs(metrics["init_nm_loss"] - float(o["nm_loss"])) <= 2e-6
+    assert abs(metrics["init_loss"] - float(o["loss"])) <= 2e-6
+    assert abs(metrics["forward_mask_rate"] - float(o["forward_mask_rate"])) <= 1e-6
+    assert abs(metrics["init_loss"] - float(g["loss"])) <= 1e-3, "far from the reference's own value"
+    # the gradient that reaches the volume: d loss / d level 0 against the oracle's d loss / d cost_volume (transposed, w2 <= w1)
+    (dvol,) = torch.autograd.grad(loss, blk._vol, retain_graph=True)
+    B, D, H, W = g["cost_volume"].shape
+    tri = np.arange(D).reshape(1, D, 1, 1) <= np.arange(W).reshape(1, 1, 1, W)
+    assert_close(host(dvol).transpose(0, 3, 1, 2) * tri, o["grad_cost_volume"] * tri, rtol=1e-5, atol=1e-9, what="d loss / d volume")
+    assert np.all((host(dvol).transpose(0, 3, 1, 2) * ~tri) == 0), "a gradient outside w2 <= w1"
+    loss.backward()
+    assert torch.isfinite(f1.grad).all() and float(f1.grad.abs().max()) > 0 and float(f2.grad.abs().max()) > 0
+
+
+def test_init_loss_refuses_a_plain_tensor(tcs):
+    with pytest.raises(TypeError):
+        tcs.init_loss(torch.zeros(1, 8, 2, 8, device="cuda"), torch.zeros(1, 1, 8, 32, device="cuda"), torch.ones(1, 1, 8, 32, device="cuda"))

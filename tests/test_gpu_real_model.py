@@ -532,6 +532,49 @@ def test_training_gradients_of_the_correlation_block_match_the_reference(ref, tc
         assert torch.equal(blk(coords[0]), tcs.CorrBlock1D(base1, base2)(coords[0]))
 
 
+@pytest.mark.parametrize("W,k", [(64, 3), (72, 1), (100, 5)])
+def test_init_loss_against_the_reference_function(ref, tcs, W, k):
+    """train_stereo.py:138-182 itself (cut out of the reference's source, run on this GPU on the materialised cost volume of the
+    SAME block) against tcs_b200.init_loss on level 0: the loss terms and the gradients that reach fmap1 / fmap2.  W = 72 has
+    pitched rows (72 -> 80), W = 100 a ragged last lane group."""
+    ref_init_loss = ref_model.load_init_loss()
+    g = torch.Generator().manual_seed(40 + W)
+    B, C, H = 2, 128, 24
+    disp = torch.rand(B, 1, H, W, generator=g) * (W / 5.0)
+    b2 = torch.randn(B, C, H, W, generator=g)
+    xs = (torch.arange(W).view(1, 1, 1, W) - disp.round().long()).clamp(0, W - 1)
+    b1 = torch.gather(b2, 3, xs.expand(B, C, H, W)) + 0.4 * torch.randn(B, C, H, W, generator=g)
+    flow = (-4.0 * disp.repeat_interleave(4, 2).repeat_interleave(4, 3) + 0.9 * torch.rand(B, 1, 4 * H, 4 * W, generator=g)).cuda()
+    flow[0, 0, :8, :16] = -4.0 * (W + 3.0)
+    flow[1, 0, 16:24, 40:56] = -4.0 * 900.0
+    valid = torch.ones(B, 1, 4 * H, 4 * W).cuda()
+    valid[:, :, :, 100:130] = 0.0
+
+    def run(fused):
+        f1 = b1.cuda().requires_grad_(True)
+        f2 = b2.cuda().requires_grad_(True)
+        blk = tcs.DifferentiableCorrBlock1D(f1, f2, precision="fp32")
+        cv = blk.get_cost_volume()
+        loss, metrics = (tcs.init_loss if fused else ref_init_loss)(cv if fused else cv.materialize(), flow, valid, k=k,
+                                                                   scale=0.25, threshold=0.5)
+        loss.backward()
+        return f1.grad, f2.grad, metrics
+
+    r1, r2, rm = run(False)
+    t1, t2, tm = run(True)
+    for name in ("init_loss", "init_gt_loss", "init_nm_loss", "forward_mask_rate"):
+        assert abs(tm[name] - rm[name]) <= 2e-6, (name, tm[name], rm[name])
+    assert rm["init_nm_loss"] > 1e-3 and rm["init_gt_loss"] < 0.9, "vacuous case"
+    scale = float(r1.abs().max())
+    assert_close(host(t1), host(r1), rtol=1e-4, atol=2e-6 * scale, what="d init_loss / d fmap1")
+    assert_close(host(t2), host(r2), rtol=1e-4, atol=2e-6 * scale, what="d init_loss / d fmap2")
+    # the reference's own function also accepts the deferred volume (it materialises on first use)
+    f1 = b1.cuda().requires_grad_(True)
+    blk = tcs.DifferentiableCorrBlock1D(f1, b2.cuda(), precision="fp32")
+    loss, _ = ref_init_loss(blk.get_cost_volume(), flow, valid, k=k, scale=0.25, threshold=0.5)
+    assert abs(float(loss) - rm["init_loss"]) <= 1e-6
+
+
 def test_training_step_through_the_real_model(ref, tcs):
     """install(training=True): TCStereo.forward in training mode (test_mode=False) with the differentiable correlation block;
     the gradients that reach the feature head (conv2) and the context encoder agree with the reference's."""

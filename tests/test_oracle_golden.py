@@ -133,3 +133,23 @@ def test_stencil_oracles_match_reference_bit_for_bit():
     assert_exact(matrix, g["matrix"], what="propagate_disparity matrix")
     up = orc.convex_upsample(-g["disp"], g["up_mask"], 4, True)                  # tc_stereo.py:75-88 (exp: not bit-exact)
     assert_close(up, g["up"], rtol=1e-5, atol=1e-5, what="upsample_flow")
+
+
+def test_init_loss_oracle_matches_the_reference_function():
+    """train_stereo.py:138-182 executed by the reference itself (make_golden_init_loss.py) against the restatement: the loss
+    terms, the metric, and d loss / d cost_volume on w2 <= w1 — outside that triangle the volume is exactly 0 (corr.py:28-31),
+    torch.topk breaks the ties among those zeros in an unspecified order, and no gradient reaches the features from there."""
+    g = load_golden("init_loss_small")
+    o = orc.init_loss(g["cost_volume"], g["flow_gt"], g["valid"], k=int(g["k"]), scale=0.25, threshold=float(g["threshold"]),
+                      valid_interp=g["valid_interp"])
+    for name in ("loss", "gt_loss", "nm_loss"):
+        assert abs(float(o[name]) - float(g[name])) <= 1e-6, name
+    assert abs(float(o["forward_mask_rate"]) - float(g["forward_mask_rate"])) <= 1e-7
+    assert 0.3 < o["mask"].mean() < 0.9, "the case must have masked AND unmasked pixels"
+    B, D, H, W = g["cost_volume"].shape
+    tri = np.arange(D).reshape(1, D, 1, 1) <= np.arange(W).reshape(1, 1, 1, W)
+    assert_close(o["grad_cost_volume"] * tri, g["grad_cost_volume"] * tri, rtol=1e-6, atol=1e-9, what="d loss / d cost_volume")
+    assert ((g["grad_cost_volume"] * tri) != 0).sum() > 500
+    # without torch's interpolation of `valid` the restatement differs only where `valid == 1` hangs on a last bit
+    own = orc.init_loss(g["cost_volume"], g["flow_gt"], g["valid"], k=int(g["k"]), scale=0.25, threshold=float(g["threshold"]))
+    assert (own["mask"] != o["mask"]).sum() <= 4
