@@ -25,6 +25,34 @@ import torch  # noqa: E402
 from oracle import ref_model  # noqa: E402
 
 
+def cpu_reference(ref, args):
+    """The reference's own TCStereo.forward on the host (all threads); its cupy splat kernel cannot run there and is replaced by
+    oracle/torch_port.splat (index_add_).  One warm-up and two timed calls per kind of frame: a call takes tens of seconds."""
+    import time
+    model = ref_model.make_model("cpu", mixed_precision=False)
+    imgs, K, poses, base = ref_model.synthetic_sequence(2, args.height, args.width, device="cpu")
+    undo = ref_model.use_cpu_splat(ref, threaded=True)
+    res = {"threads": torch.get_num_threads(), "cores": os.cpu_count()}
+    try:
+        with torch.no_grad():
+            o0 = model(imgs[0][0], imgs[0][1], iters=2, test_mode=True)
+            params = {"K": K, "T": poses[1], "previous_T": poses[0], "last_disp": o0["flow_q"], "last_net_list": o0["net_list"],
+                      "fmap1": o0["fmap1"], "baseline": base}
+            for name, fn in (("first_frame_ms", lambda: model(imgs[0][0], imgs[0][1], iters=args.iters, test_mode=True)),
+                             ("temporal_frame_ms", lambda: model(imgs[1][0], imgs[1][1], iters=args.iters, test_mode=True, params=dict(params)))):
+                fn()
+                ts = []
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    fn()
+                    ts.append(1e3 * (time.perf_counter() - t0))
+                res[name] = min(ts)
+    finally:
+        if callable(undo):
+            undo()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--height", type=int, default=544)
@@ -32,6 +60,7 @@ def main():
     ap.add_argument("--iters", type=int, default=32)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--mixed-precision", action="store_true", help="the shipped scripts' --mixed_precision: learned blocks under fp16 autocast")
+    ap.add_argument("--cpu-reference", action="store_true", help="also time the reference's TCStereo.forward on the host cores (SURVEY.md 8d(i))")
     args = ap.parse_args()
     import tcs_b200
     ref = ref_model.load()
@@ -89,6 +118,9 @@ def main():
             if strip:
                 tcs_b200.restore_asserts()
         print(name, out[name], flush=True)
+    if args.cpu_reference:
+        out["reference on the host cores"] = cpu_reference(ref, args)
+        print("reference on the host cores", out["reference on the host cores"], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "real_model_timing%s.json" % ("_amp" if args.mixed_precision else "")), "w"), indent=1)
 
