@@ -125,6 +125,18 @@ int tcs_corr_lookup_encode(const float* lvl0, const float* lvl1, const float* lv
                            float* out, int B, int H, int W1, int W2, int num_levels, int radius, int Cout, int relu,
                            int W2_pitch, void* stream);
 
+/* The same on the tensor cores, for the model's own shape (Cout = 64) and row-aligned levels (row pitch % 16 == 0): the 36 -> 64
+ * product of 128 pixels is one 128 x 64 x 48 tcgen05 GEMM in fp16 hi/lo split (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM),
+ * the taps written as the A operand by the threads that sampled them.  `packed` (tcs_corr_encode_packed_bytes() bytes, 16-byte
+ * aligned) is written once per weight by tcs_corr_encode_pack_weights(weight [64,36] fp32, bias [64] or NULL): the weights scaled
+ * by a power of two, split and laid out as the K-major SWIZZLE_64B B operand, then the bias and the un-scaling factor.
+ * ref: core/update.py:97,104 on core/corr.py:33-52, as tcs_corr_lookup_encode. */
+int tcs_corr_encode_packed_bytes(void);
+int tcs_corr_encode_pack_weights(const float* weight, const float* bias, void* packed, void* stream);
+int tcs_corr_lookup_encode_tc(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                              const float* coords, long long coords_bstride, const void* packed, float* out,
+                              int B, int H, int W1, int W2, int relu, int W2_pitch, void* stream);
+
 /* ---- (3) alternate (on-the-fly) lookup ---------------------------------------------------------- */
 
 /* Average-pool the fp32 normalised right features along W (channels last): out[b,h,j,:] =

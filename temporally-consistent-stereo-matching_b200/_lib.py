@@ -32,6 +32,9 @@ SIGNATURES = {
     "tcs_corr_build_fp32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_lookup": (_i, [_p, _p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_lookup_encode": (_i, [_p, _p, _p, _p, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "tcs_corr_encode_packed_bytes": (_i, []),
+    "tcs_corr_encode_pack_weights": (_i, [_p, _p, _p, _p]),
+    "tcs_corr_lookup_encode_tc": (_i, [_p, _p, _p, _p, _p, _ll, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_corr_lookup_backward": (_i, [_p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tcs_init_loss_forward": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "tcs_init_loss_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),

@@ -155,6 +155,26 @@ def _coords_plane(coords, B, H, W1):
     return c, c.data_ptr(), (c.stride(0) if B > 1 else H * W1)
 
 
+_packed_cache = {}
+# Below this many pixels per call (3 frames of 136x240) the tensor-core form's per-CTA set-up (TMEM allocation, barrier, 9 KB of
+# weights) costs more than its GEMM saves: measured 28 vs 24 us at 1 x 136x240, 48 vs 66 us at 8 x 136x240 (tools/time_encode.py).
+_ENCODE_TC_MIN_PIXELS = 3 * 136 * 240
+
+
+def _packed_encoder_weights(weight, bias, w2d, b1d):
+    """The B operand of tcs_corr_lookup_encode_tc for this (weight, bias): packed on the device by one small kernel, cached until
+    either tensor is modified in place (version counter) or replaced (storage pointer)."""
+    key = (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version), weight.device.index)
+    hit = _packed_cache.get(key)
+    if hit is None:
+        if len(_packed_cache) > 16:
+            _packed_cache.clear()
+        packed = torch.empty(int(_lib.load().tcs_corr_encode_packed_bytes()), dtype=torch.uint8, device=weight.device)
+        _lib.call("tcs_corr_encode_pack_weights", w2d.data_ptr(), b1d.data_ptr() if b1d is not None else None, packed.data_ptr(), _stream())
+        hit = _packed_cache[key] = (packed, weight, bias)          # the tensors are kept alive: their pointers stay theirs
+    return hit[0]
+
+
 class LazyLookup(LazyTensorOps):
     """corr_fn(coords) not yet evaluated.  BasicMotionEncoder's patched forward calls .encode(convc1) and never
     materialises the 36 tap planes; every other use (torch functions, the reference's isnan asserts) goes through
@@ -322,8 +342,15 @@ class CorrBlock1D:
         out = torch.empty((self.B, cout, self.H, self.W1), dtype=torch.float32, device=self.device)
         ptrs = [self._levels[l].data_ptr() for l in range(4)]
         with torch.cuda.device(self.device):
-            _lib.call("tcs_corr_lookup_encode", *ptrs, cptr, cstride, w.data_ptr(), bb.data_ptr() if bb is not None else None,
-                      out.data_ptr(), self.B, self.H, self.W1, self.W2, 4, 4, cout, 1 if relu else 0, self._pitch_arg(), _stream())
+            tc = os.environ.get("TCS_B200_ENCODE_TC", "auto")          # "0" never, "1" whenever possible, default: when it pays
+            if cout == 64 and self.W2p % 16 == 0 and tc != "0" and (tc == "1" or self.B * self.H * self.W1 >= _ENCODE_TC_MIN_PIXELS):
+                # tensor-core form: the weights split / swizzled once per (weight, bias) version
+                packed = _packed_encoder_weights(weight, bias, w, bb)
+                _lib.call("tcs_corr_lookup_encode_tc", *ptrs, cptr, cstride, packed.data_ptr(), out.data_ptr(),
+                          self.B, self.H, self.W1, self.W2, 1 if relu else 0, self._pitch_arg(), _stream())
+            else:
+                _lib.call("tcs_corr_lookup_encode", *ptrs, cptr, cstride, w.data_ptr(), bb.data_ptr() if bb is not None else None,
+                          out.data_ptr(), self.B, self.H, self.W1, self.W2, 4, 4, cout, 1 if relu else 0, self._pitch_arg(), _stream())
         return out
 
     def lazy(self, coords):

@@ -8,6 +8,7 @@
 // rounding: x = k + coords/2^l ; xg = 2x/(W-1) - 1 ; ix = ((xg+1)/2)*(W-1) ; x0 = floor(ix) ;
 // out = v[x0]*(x0+1-ix) + v[x0+1]*(ix-x0), out-of-range taps contributing 0 (zeros padding).
 #include "tcs_common.cuh"
+#include "sm100_ptx.cuh"
 #include <cstdlib>
 
 namespace tcs {
@@ -523,6 +524,197 @@ corr_lookup_encode_kernel(const LevelPtrs lv, const float* __restrict__ coords, 
     }
 }
 
+// ---- the same on the tensor cores (Cout = 64, row-aligned levels) ------------------------------------------------------------------
+// The 36 -> 64 product of 128 pixels is a small GEMM.  The CTA's 128 threads (thread = pixel) split taps 0..31 into fp16 hi + lo
+// (x 2^8, as the build does) and write them as the A operand, one K-major SWIZZLE_64B block [128 x 32]; the B operand is the
+// weight matrix [64 x 32], split and swizzled ONCE by encode_pack_weights_kernel (scaled by a power of two that puts its largest
+// entry in [2^9, 2^10)); one thread issues hi.hi + hi.lo + lo.hi as 6 tcgen05.mma 128 x 64 x 16 into 64 TMEM columns; every warp
+// reads its 32 lanes back (thread = its own pixel again), un-scales, adds the bias and the last four taps' share (level 3's taps
+// 5..8: 4 fp32 FMAs per output against weights broadcast from shared memory - a second, mostly empty K block would cost 12 KB of
+// shared memory per CTA and with it a third of the resident warps the lookup part lives on), applies ReLU and stores 64
+// coalesced planes.  CTAs are persistent (TMEM, barrier and weights set up once).
+namespace enc_tc {
+constexpr int kN = 64;                      // output channels
+constexpr int kRows = kLookThreads;         // pixels per tile = UMMA M
+static_assert(kRows == 128, "one UMMA M tile per CTA");
+constexpr int kK = 32;                      // taps on the tensor cores
+constexpr int kTail = kEncTaps - kK;        // 4 taps on the CUDA cores
+constexpr int kATile = kRows * 64;          // 8 KB (32 fp16 = 64 B per row)
+constexpr int kBTile = kN * 64;             // 4 KB
+constexpr int kPackWeights = 2 * kBTile;    // B_hi, B_lo
+constexpr int kPackTail = kN * kTail * 4;   // fp32 weights of the last four taps, [64][4]
+constexpr int kPackBytes = kPackWeights + kPackTail + kN * 4 + 16;   // + bias[64] + {2^-(8+s), pad}
+constexpr int kSmemBytes = 1024 + 2 * kATile + kPackBytes + 16;
+constexpr int kTmemCols = 64;
+
+// byte offset of fp16 element (row r, k < 32) inside a K-major SWIZZLE_64B operand block
+__host__ __device__ constexpr uint32_t sw64_offset(int r, int k) {
+    return (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + (((k >> 3) ^ ((r >> 1) & 3)) << 4) + (k & 7) * 2);
+}
+}  // namespace enc_tc
+
+// packed: [B_hi | B_lo | tail weights | bias | 2^-(8+s)]: see enc_tc.  One block.
+__global__ void __launch_bounds__(256)
+encode_pack_weights_kernel(const float* __restrict__ weight, const float* __restrict__ bias, unsigned char* __restrict__ packed) {
+    using namespace enc_tc;
+    __shared__ float red[256];
+    float m = 0.0f;
+    for (int i = threadIdx.x; i < kN * kEncTaps; i += 256) m = fmaxf(m, fabsf(__ldg(weight + i)));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    m = red[0];
+    const int s = (m > 0.0f && isfinite(m)) ? 9 - ilogbf(m) : 0;       // max |w| * 2^s in [2^9, 2^10)
+    const float scale = ldexpf(1.0f, s);
+    for (int e = threadIdx.x; e < kN * kK; e += 256) {
+        const int n = e / kK, k = e % kK;
+        const float v = __ldg(weight + n * kEncTaps + k) * scale;
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn(v - __half2float(h));
+        const uint32_t off = sw64_offset(n, k);
+        *reinterpret_cast<__half*>(packed + off) = h;
+        *reinterpret_cast<__half*>(packed + kBTile + off) = l;
+    }
+    float* tail = reinterpret_cast<float*>(packed + kPackWeights);
+    for (int i = threadIdx.x; i < kN * kTail; i += 256) tail[i] = __ldg(weight + (i / kTail) * kEncTaps + kK + (i % kTail));
+    float* bs = tail + kN * kTail;
+    for (int i = threadIdx.x; i < kN; i += 256) bs[i] = bias != nullptr ? __ldg(bias + i) : 0.0f;
+    if (threadIdx.x == 0) { bs[kN] = ldexpf(1.0f, -(8 + s)); bs[kN + 1] = 0.0f; bs[kN + 2] = 0.0f; bs[kN + 3] = 0.0f; }
+}
+
+#ifndef TCS_ENCODE_TC_MINBLOCKS
+#define TCS_ENCODE_TC_MINBLOCKS 5              // 95 registers, no spills (6: 80 registers, 60 bytes spilled)
+#endif
+template <int kMode>   // 1: W2 pitch % 16 == 0; 2: + level 0 32-byte aligned
+__global__ void __launch_bounds__(kLookThreads, TCS_ENCODE_TC_MINBLOCKS)
+corr_lookup_encode_tc_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
+                             const unsigned char* __restrict__ packed, float* __restrict__ out, int HW, int W2, int W2p, int relu,
+                             int tiles_per_sample, int num_tiles) {
+    using namespace enc_tc;
+    extern __shared__ uint8_t enc_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(enc_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + kATile;
+    uint8_t* pk = smem + 2 * kATile;                                   // the packed weights, copied as they are
+    const uint32_t b_hi = smem_u32(pk), b_lo = b_hi + kBTile;
+    const float* s_tail = reinterpret_cast<const float*>(pk + kPackWeights);
+    const float* s_bias = s_tail + kN * kTail;
+    uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(pk + kPackBytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + 1);
+    const uint32_t bar = smem_u32(bar_ptr);
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (warp == 0) {
+        if (tid == 0) { ptx::mbar_init(bar, 1); ptx::fence_barrier_init(); }
+        __syncwarp();
+        ptx::tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    for (int i = tid; i < kPackBytes / 16; i += kLookThreads)
+        reinterpret_cast<uint4*>(pk)[i] = __ldg(reinterpret_cast<const uint4*>(packed) + i);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const float inv = s_bias[kN];
+    const long long npix = (long long)(num_tiles / tiles_per_sample) * HW;
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // ---- the lookup: this thread's 36 taps (a pixel past the end repeats the last one and is not stored)
+        const int b = tile / tiles_per_sample;
+        const int hw_raw = (tile - b * tiles_per_sample) * kLookThreads + tid;
+        const int hw = min(hw_raw, HW - 1);
+        const long long p = (long long)b * HW + hw;
+        const float c0 = sane_coord(__ldg(coords + b * coords_bstride + hw));
+        float tp[kEncTaps];
+        {
+            Span s1;
+            if (kMode == 2) {
+                SpanOct s0;
+                span_load_oct(s0, lv.p[0], p, c0, 0, W2p);
+                span_load(s1, lv.p[2], p, npix, c0, 2, W2p >> 2, true);
+                span_taps_oct<true>(s0, nullptr, 0, HW, b, 0, W2, tp);
+            } else {
+                Span s0;
+                span_load(s0, lv.p[0], p, npix, c0, 0, W2p, true);
+                span_load(s1, lv.p[2], p, npix, c0, 2, W2p >> 2, true);
+                span_taps_reg<true, true>(s0, nullptr, 0, HW, 4, b, 0, W2, tp);
+            }
+            span_taps_reg<true, true>(s1, nullptr, 0, HW, 4, b, 2, W2 >> 2, tp + 18);
+        }
+        // ---- A operand: row = tid, four 16-byte chunks of 8 taps
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float x0 = tp[8 * j + 2 * q] * 256.0f, x1 = tp[8 * j + 2 * q + 1] * 256.0f;
+                const __half2 h = __floats2half2_rn(x0, x1);
+                const float2 back = __half22float2(h);
+                const __half2 l = __floats2half2_rn(x0 - back.x, x1 - back.y);
+                hi[q] = *reinterpret_cast<const uint32_t*>(&h);
+                lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            const uint32_t off = sw64_offset(tid, 8 * j);
+            sts_v4_u32(a_hi + off, hi[0], hi[1], hi[2], hi[3]);
+            sts_v4_u32(a_lo + off, lo[0], lo[1], lo[2], lo[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        ptx::tc_fence_before_sync();
+        __syncthreads();                                               // (also: every warp has read the previous tile's accumulator)
+        if (tid == 0) {
+            ptx::tc_fence_after_sync();
+            constexpr uint32_t idesc = ptx::make_idesc_f16(0u, kRows, kN);
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {                     // hi.hi, hi.lo, lo.hi: the build's order
+                const uint64_t da = ptx::make_kmajor_sw64_desc(pass == 2 ? a_lo : a_hi);
+                const uint64_t db = ptx::make_kmajor_sw64_desc(pass == 1 ? b_lo : b_hi);
+#pragma unroll
+                for (int ks = 0; ks < kK / 16; ++ks) {
+                    ptx::umma_f16(tmem_base, da + 2 * ks, db + 2 * ks, idesc, acc);
+                    acc = 1;
+                }
+            }
+            ptx::umma_commit(bar);
+        }
+        ptx::mbar_wait(bar, phase);
+        phase ^= 1;
+        ptx::tc_fence_after_sync();
+        float* o = out + (long long)b * kN * HW + hw;
+        const float t0 = tp[kK], t1 = tp[kK + 1], t2 = tp[kK + 2], t3 = tp[kK + 3];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float v[32];
+            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + half * 32, v);
+            if (hw_raw < HW) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int oc = half * 32 + i;
+                    const float4 wt = *reinterpret_cast<const float4*>(s_tail + oc * kTail);     // broadcast
+                    float r = fmaf(v[i], inv, s_bias[oc]);
+                    r = fmaf(wt.x, t0, r);
+                    r = fmaf(wt.y, t1, r);
+                    r = fmaf(wt.z, t2, r);
+                    r = fmaf(wt.w, t3, r);
+                    stg_stream_f1(o + (long long)oc * HW, relu ? fmaxf(r, 0.0f) : r);
+                }
+            }
+        }
+        ptx::tc_fence_before_sync();                                   // the accumulator reads above precede the next tile's MMAs
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
 // ---- generic lookup (any radius <= 8): one thread per (pixel, level), scalar loads ---------------------
 __global__ void __launch_bounds__(256)
 corr_lookup_generic_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
@@ -904,6 +1096,53 @@ extern "C" int tcs_corr_lookup_encode(const float* lvl0, const float* lvl1, cons
     else
         corr_lookup_encode_kernel<0><<<grid, kLookThreads, 0, s>>>(lp, coords, coords_bstride, weight, bias, out, H * W1, W2, W2p, Cout, relu);
     TCS_CHECK_LAUNCH("tcs_corr_lookup_encode");
+    return 0;
+}
+
+extern "C" int tcs_corr_encode_packed_bytes(void) { return tcs::enc_tc::kPackBytes; }
+
+extern "C" int tcs_corr_encode_pack_weights(const float* weight, const float* bias, void* packed, void* stream) {
+    using namespace tcs;
+    TCS_REQUIRE(weight != nullptr && packed != nullptr && aligned16(packed), TCS_E_BADARG, "tcs_corr_encode_pack_weights: null or unaligned pointer");
+    encode_pack_weights_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(weight, bias, static_cast<unsigned char*>(packed));
+    TCS_CHECK_LAUNCH("tcs_corr_encode_pack_weights");
+    return 0;
+}
+
+extern "C" int tcs_corr_lookup_encode_tc(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                         const float* coords, long long coords_bstride, const void* packed, float* out,
+                                         int B, int H, int W1, int W2, int relu, int W2_pitch, void* stream) {
+    using namespace tcs;
+    const float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
+    int rc = check_lookup_args("tcs_corr_lookup_encode_tc", lv, coords, out, B, H, W1, W2, 4, 4);
+    if (rc != 0) return rc;
+    TCS_REQUIRE(packed != nullptr && aligned16(packed), TCS_E_BADARG, "tcs_corr_lookup_encode_tc: packed weights null or unaligned");
+    const int W2p = W2_pitch > 0 ? W2_pitch : W2;
+    TCS_REQUIRE(W2p % 16 == 0 && (W2p == W2 || (W2p > W2 && W2 % 8 == 0)), TCS_E_SHAPE,
+                "tcs_corr_lookup_encode_tc: needs a row pitch (%d) that is a multiple of 16 (W2=%d); use tcs_corr_lookup_encode", W2p, W2);
+    TCS_REQUIRE(B <= 65535, TCS_E_SHAPE, "tcs_corr_lookup_encode_tc: B must be <= 65535");
+    LevelPtrs lp;
+    for (int l = 0; l < 4; ++l) lp.p[l] = lv[l];
+    TCS_ONCE_PER_DEVICE(
+        TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_tc::kSmemBytes));
+        TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_tc::kSmemBytes));
+    );
+    const int tiles_per_sample = ceil_div(H * W1, kLookThreads);
+    const long long num_tiles = (long long)tiles_per_sample * B;
+    TCS_REQUIRE(num_tiles < 0x7fffffffLL, TCS_E_SHAPE, "tcs_corr_lookup_encode_tc: too many pixels");
+    int ctas_per_sm = TCS_ENCODE_TC_MINBLOCKS;                         // 96 registers x 128 threads; 26 KB of shared memory each
+    { const char* e = getenv("TCS_ENCODE_TC_CTAS"); if (e != nullptr && atoi(e) > 0) ctas_per_sm = atoi(e); }
+    const long long resident = (long long)ctas_per_sm * num_sms();
+    const unsigned grid = (unsigned)(num_tiles < resident ? num_tiles : resident);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned char* pk = static_cast<const unsigned char*>(packed);
+    if ((reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
+        corr_lookup_encode_tc_kernel<2><<<grid, kLookThreads, enc_tc::kSmemBytes, s>>>(lp, coords, coords_bstride, pk, out, H * W1, W2, W2p, relu,
+                                                                                        tiles_per_sample, (int)num_tiles);
+    else
+        corr_lookup_encode_tc_kernel<1><<<grid, kLookThreads, enc_tc::kSmemBytes, s>>>(lp, coords, coords_bstride, pk, out, H * W1, W2, W2p, relu,
+                                                                                        tiles_per_sample, (int)num_tiles);
+    TCS_CHECK_LAUNCH("tcs_corr_lookup_encode_tc");
     return 0;
 }
 

@@ -292,6 +292,42 @@ def test_lookup_encoded_golden(tcs, case):
     assert_close(host(lazy.materialize()), g["lookup"], what="lazy lookup materialised")
 
 
+@pytest.mark.parametrize("wscale", [0.3, 3.0e3, 1.0e-4, 0.0])
+@pytest.mark.parametrize("B,H,W", [(1, 136, 240), (2, 5, 248), (1, 3, 48)])
+def test_lookup_encoded_tensor_core_against_cuda_core_and_oracle(tcs, monkeypatch, B, H, W, wscale):
+    """tcs_corr_lookup_encode_tc (Cout = 64, row pitch % 16 == 0: one tcgen05 GEMM per 128 pixels, fp16 hi/lo split of taps and
+    weights) against the CUDA-core kernel and the oracle, for weights of any magnitude (the pack kernel scales by a power of two)
+    and a ragged last tile (H * W not a multiple of 128)."""
+    f1, f2 = make_fmaps(B, 128, H, W, 21 + W)
+    blk = tcs.CorrBlock1D(f1.cuda(), f2.cuda())                  # (the two-step build pitches 248 -> 256)
+    assert blk.W2p % 16 == 0
+    coords = make_coords(B, H, W, 6).cuda()
+    gen = torch.Generator().manual_seed(10)
+    w = (torch.randn(64, 36, generator=gen) * wscale).cuda()
+    bias = (torch.randn(64, generator=gen) * max(wscale, 1e-3)).cuda()
+    monkeypatch.setenv("TCS_B200_ENCODE_TC", "1")             # small calls take the CUDA-core kernel by default
+    tc = blk.lookup_encoded(coords, w, bias)
+    monkeypatch.setenv("TCS_B200_ENCODE_TC", "0")
+    cc = blk.lookup_encoded(coords, w, bias)
+    monkeypatch.setenv("TCS_B200_ENCODE_TC", "1")
+    assert not torch.equal(tc, cc) or wscale == 0.0, "the two forms round differently: identical bits mean the switch did nothing"
+    ref = orc.corr_lookup_encoded([host(x) for x in blk._levels], host(coords), host(w), host(bias), True)
+    scale = max(wscale, 1e-30)
+    assert_close(host(cc), ref, rtol=1e-5, atol=2e-6 * max(scale / 0.3, 1e-3), what="CUDA-core fused lookup + 1x1")
+    assert_close(host(tc), ref, rtol=1e-5, atol=2e-6 * max(scale / 0.3, 1e-3), what="tensor-core fused lookup + 1x1")
+    if wscale == 0.0:
+        assert torch.equal(tc, torch.relu(bias).view(1, 64, 1, 1).expand_as(tc))
+    # no ReLU, no bias
+    assert_close(host(blk.lookup_encoded(coords, w, None, relu=False)),
+                 orc.corr_lookup_encoded([host(x) for x in blk._levels], host(coords), host(w), None, False),
+                 rtol=1e-5, atol=2e-6 * max(scale / 0.3, 1e-3), what="tensor-core, no bias, no relu")
+    # the packed weights follow an in-place update of the parameter
+    w.mul_(2.0)
+    assert_close(host(blk.lookup_encoded(coords, w, None, relu=False)),
+                 2.0 * orc.corr_lookup_encoded([host(x) for x in blk._levels], host(coords), host(w) / 2.0, None, False),
+                 rtol=1e-5, atol=4e-6 * max(scale / 0.3, 1e-3), what="after an in-place weight update")
+
+
 @pytest.mark.parametrize("B,H,W,cout,relu", [(1, 136, 240, 64, True), (2, 30, 160, 64, False), (1, 9, 67, 8, True)])
 def test_lookup_encoded_full_size(tcs, B, H, W, cout, relu):
     f1, f2 = make_fmaps(B, 128, H, W, 13 + W)
@@ -808,7 +844,9 @@ def test_pitched_levels_give_the_same_bits_as_dense_ones(tcs, monkeypatch, B, H,
         phys = torch.as_strided(lv, (B, H, W1, pitched.W2p >> l), lv.stride(), lv.storage_offset())
         assert float(phys[..., W2 >> l:].abs().max()) == 0.0, "level %d: the padding columns must be exact zeros" % l
     assert torch.equal(pitched(coords), dense(coords))
+    monkeypatch.setenv("TCS_B200_ENCODE_TC", "0")            # pitched rows also qualify for the tensor-core 1x1: same kernel for both here
     assert torch.equal(pitched.lookup_encoded(coords, w), dense.lookup_encoded(coords, w))
+    monkeypatch.delenv("TCS_B200_ENCODE_TC")
     for a, b in zip(pitched.argmax_disp(), dense.argmax_disp()):
         assert torch.equal(a, b)
     assert torch.equal(pitched.get_cost_volume(), dense.get_cost_volume())
