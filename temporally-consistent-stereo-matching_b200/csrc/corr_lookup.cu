@@ -396,9 +396,11 @@ __device__ __forceinline__ void span_taps_oct(const SpanOct& sp, float* __restri
 
 // One thread per (pixel, level pair), blockIdx.y = pair: 50 registers instead of 80, so 40 warps per SM hide the
 // latency of the scattered loads instead of 24 (20.4 -> 19.5 us; the coordinate is simply read twice).
-// Block size 64 / 96 / 128 are equivalent, 256 is 3 % slower.
+// Block size 64 / 96 / 128 are equivalent, 256 is 3 % slower.  With the regular path and the packed taps the kernel would take
+// 72 registers; capped at 64 (8 CTAs per SM: 0.667 vs 0.676 ms per 32 calls; 9 -> 56 registers 0.675; 10 -> 48 registers and
+// 32 bytes spilled 0.717; tools/sweep_lookup.sh).
 #ifndef TCS_LOOKUP_MINBLOCKS
-#define TCS_LOOKUP_MINBLOCKS 1
+#define TCS_LOOKUP_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(kLookThreads, TCS_LOOKUP_MINBLOCKS)
 corr_lookup_r4x4o_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,

@@ -92,8 +92,8 @@ __device__ __forceinline__ float div_by_const(float x, float c, float rc) {
 struct f32x2 { uint64_t v; };
 __device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ f32x2 pk2(float a) { return pk2(a, a); }
-__device__ __forceinline__ float lo2(f32x2 x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); return a; }
-__device__ __forceinline__ float hi2(f32x2 x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); return b; }
+__device__ __forceinline__ float lo2(f32x2 x) { return __uint_as_float((uint32_t)(x.v & 0xffffffffull)); }   // register aliasing, no instruction
+__device__ __forceinline__ float hi2(f32x2 x) { return __uint_as_float((uint32_t)(x.v >> 32)); }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
