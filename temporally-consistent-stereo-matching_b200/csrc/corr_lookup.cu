@@ -402,6 +402,7 @@ __device__ __forceinline__ void span_taps_oct(const SpanOct& sp, float* __restri
 #ifndef TCS_LOOKUP_MINBLOCKS
 #define TCS_LOOKUP_MINBLOCKS 8
 #endif
+
 __global__ void __launch_bounds__(kLookThreads, TCS_LOOKUP_MINBLOCKS)
 corr_lookup_r4x4o_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
                          float* __restrict__ out, int HW, int W2, int W2p) {   // W2p: row pitch of level 0 (>= W2, zeros beyond W2)
