@@ -163,15 +163,23 @@ _ENCODE_TC_MIN_PIXELS = 3 * 136 * 240
 
 def _packed_encoder_weights(weight, bias, w2d, b1d):
     """The B operand of tcs_corr_lookup_encode_tc for this (weight, bias): packed on the device by one small kernel, cached until
-    either tensor is modified in place (version counter) or replaced (storage pointer)."""
+    either tensor is modified in place (version counter) or replaced (storage pointer).  A later call on ANOTHER stream waits for
+    the packing kernel's event first (the cache is process-wide, the packing ran on whichever stream missed)."""
     key = (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version), weight.device.index)
     hit = _packed_cache.get(key)
+    stream = torch.cuda.current_stream(weight.device)
     if hit is None:
         if len(_packed_cache) > 16:
             _packed_cache.clear()
         packed = torch.empty(int(_lib.load().tcs_corr_encode_packed_bytes()), dtype=torch.uint8, device=weight.device)
         _lib.call("tcs_corr_encode_pack_weights", w2d.data_ptr(), b1d.data_ptr() if b1d is not None else None, packed.data_ptr(), _stream())
-        hit = _packed_cache[key] = (packed, weight, bias)          # the tensors are kept alive: their pointers stay theirs
+        if torch.cuda.is_current_stream_capturing():
+            return packed                  # graph-pool memory: packed again by every replay, never handed to an eager caller
+        done = torch.cuda.Event()
+        done.record(stream)
+        hit = _packed_cache[key] = (packed, done, stream, weight, bias)   # the tensors are kept alive: their pointers stay theirs
+    elif hit[2] != stream:
+        stream.wait_event(hit[1])
     return hit[0]
 
 
