@@ -528,32 +528,40 @@ corr_lookup_encode_kernel(const LevelPtrs lv, const float* __restrict__ coords, 
 }
 
 // ---- the same on the tensor cores (Cout = 64, row-aligned levels) ------------------------------------------------------------------
-// The 36 -> 64 product of 128 pixels is a small GEMM.  The CTA's 128 threads (thread = pixel) split taps 0..31 into fp16 hi + lo
-// (x 2^8, as the build does) and write them as the A operand, one K-major SWIZZLE_64B block [128 x 32]; the B operand is the
-// weight matrix [64 x 32], split and swizzled ONCE by encode_pack_weights_kernel (scaled by a power of two that puts its largest
-// entry in [2^9, 2^10)); one thread issues hi.hi + hi.lo + lo.hi as 6 tcgen05.mma 128 x 64 x 16 into 64 TMEM columns; every warp
-// reads its 32 lanes back (thread = its own pixel again), un-scales, adds the bias and the last four taps' share (level 3's taps
-// 5..8: 4 fp32 FMAs per output against weights broadcast from shared memory - a second, mostly empty K block would cost 12 KB of
-// shared memory per CTA and with it a third of the resident warps the lookup part lives on), applies ReLU and stores 64
-// coalesced planes.  CTAs are persistent (TMEM, barrier and weights set up once).
+// The 36 -> 64 product of 128 pixels is a small GEMM.  A tile = 128 pixels, a CTA = 256 threads: TWO threads per pixel, one per
+// level pair, exactly as in the plain lookup (the pair's 18 taps in one thread keep it at the lookup's register count and hence
+// at its number of resident warps, which is what the scattered window loads live on: with all 36 taps in one thread the kernel
+// needed 95 registers and ran at 46 us against the lookup's 21, profiles/r02_encode_tc.md).  Each thread splits its first 16 taps
+// into fp16 hi + lo (x 2^8, as the build does) and writes them as two whole 16-byte chunks of its pixel's row of the A operand
+// (K-major SWIZZLE_64B, [128 x 32]: K index k < 16 = tap k of levels 0-1, 16 <= k < 32 = tap k - 16 of levels 2-3); its last two
+// taps go to a small shared table.  The B operand is the weight matrix in the same K order, split and swizzled ONCE by
+// encode_pack_weights_kernel (scaled by a power of two that puts its largest entry in [2^9, 2^10)).  One thread issues
+// hi.hi + hi.lo + lo.hi as 6 tcgen05.mma 128 x 64 x 16 into 64 TMEM columns; then all eight warps read the accumulator back
+// (warp w: lanes 32 (w % 4).., columns 32 (w / 4)..: thread = its pixel again, half of the outputs), un-scale, add the bias and
+// the four left-over taps' share (4 fp32 FMAs per output, weights broadcast from shared memory), apply ReLU and store 32
+// coalesced planes each.  CTAs are persistent (TMEM, barrier and weights set up once).
 namespace enc_tc {
 constexpr int kN = 64;                      // output channels
-constexpr int kRows = kLookThreads;         // pixels per tile = UMMA M
-static_assert(kRows == 128, "one UMMA M tile per CTA");
-constexpr int kK = 32;                      // taps on the tensor cores
-constexpr int kTail = kEncTaps - kK;        // 4 taps on the CUDA cores
+constexpr int kRows = 128;                  // pixels per tile = UMMA M
+constexpr int kThreads = 2 * kRows;         // two threads per pixel
+constexpr int kK = 32;                      // taps on the tensor cores: 16 of each level pair
+constexpr int kTail = kEncTaps - kK;        // 4 taps on the CUDA cores: taps 16, 17 of each level pair
 constexpr int kATile = kRows * 64;          // 8 KB (32 fp16 = 64 B per row)
 constexpr int kBTile = kN * 64;             // 4 KB
 constexpr int kPackWeights = 2 * kBTile;    // B_hi, B_lo
-constexpr int kPackTail = kN * kTail * 4;   // fp32 weights of the last four taps, [64][4]
+constexpr int kPackTail = kN * kTail * 4;   // fp32 weights of the four left-over taps, [64][4]
 constexpr int kPackBytes = kPackWeights + kPackTail + kN * 4 + 16;   // + bias[64] + {2^-(8+s), pad}
-constexpr int kSmemBytes = 1024 + 2 * kATile + kPackBytes + 16;
+constexpr int kTailBytes = 2 * kRows * kTail * 4;                    // left-over taps [tile parity][128][4] fp32
+constexpr int kSmemBytes = 1024 + 2 * kATile + kPackBytes + 16 + kTailBytes;
 constexpr int kTmemCols = 64;
 
 // byte offset of fp16 element (row r, k < 32) inside a K-major SWIZZLE_64B operand block
 __host__ __device__ constexpr uint32_t sw64_offset(int r, int k) {
     return (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + (((k >> 3) ^ ((r >> 1) & 3)) << 4) + (k & 7) * 2);
 }
+// lookup output channel (level * 9 + tap) behind GEMM K index k / behind left-over tap q
+__host__ __device__ constexpr int tap_of_k(int k) { return k < 16 ? k : 18 + (k - 16); }
+__host__ __device__ constexpr int tap_of_tail(int q) { return q < 2 ? 16 + q : 34 + (q - 2); }
 }  // namespace enc_tc
 
 // packed: [B_hi | B_lo | tail weights | bias | 2^-(8+s)]: see enc_tc.  One block.
@@ -574,7 +582,7 @@ encode_pack_weights_kernel(const float* __restrict__ weight, const float* __rest
     const float scale = ldexpf(1.0f, s);
     for (int e = threadIdx.x; e < kN * kK; e += 256) {
         const int n = e / kK, k = e % kK;
-        const float v = __ldg(weight + n * kEncTaps + k) * scale;
+        const float v = __ldg(weight + n * kEncTaps + tap_of_k(k)) * scale;
         const __half h = __float2half_rn(v);
         const __half l = __float2half_rn(v - __half2float(h));
         const uint32_t off = sw64_offset(n, k);
@@ -582,17 +590,17 @@ encode_pack_weights_kernel(const float* __restrict__ weight, const float* __rest
         *reinterpret_cast<__half*>(packed + kBTile + off) = l;
     }
     float* tail = reinterpret_cast<float*>(packed + kPackWeights);
-    for (int i = threadIdx.x; i < kN * kTail; i += 256) tail[i] = __ldg(weight + (i / kTail) * kEncTaps + kK + (i % kTail));
+    for (int i = threadIdx.x; i < kN * kTail; i += 256) tail[i] = __ldg(weight + (i / kTail) * kEncTaps + tap_of_tail(i % kTail));
     float* bs = tail + kN * kTail;
     for (int i = threadIdx.x; i < kN; i += 256) bs[i] = bias != nullptr ? __ldg(bias + i) : 0.0f;
     if (threadIdx.x == 0) { bs[kN] = ldexpf(1.0f, -(8 + s)); bs[kN + 1] = 0.0f; bs[kN + 2] = 0.0f; bs[kN + 3] = 0.0f; }
 }
 
 #ifndef TCS_ENCODE_TC_MINBLOCKS
-#define TCS_ENCODE_TC_MINBLOCKS 5              // 95 registers, no spills (6: 80 registers, 60 bytes spilled)
+#define TCS_ENCODE_TC_MINBLOCKS 4              // 256 threads x 64 registers
 #endif
 template <int kMode>   // 1: W2 pitch % 16 == 0; 2: + level 0 32-byte aligned
-__global__ void __launch_bounds__(kLookThreads, TCS_ENCODE_TC_MINBLOCKS)
+__global__ void __launch_bounds__(enc_tc::kThreads, TCS_ENCODE_TC_MINBLOCKS)
 corr_lookup_encode_tc_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
                              const unsigned char* __restrict__ packed, float* __restrict__ out, int HW, int W2, int W2p, int relu,
                              int tiles_per_sample, int num_tiles) {
@@ -606,8 +614,10 @@ corr_lookup_encode_tc_kernel(const LevelPtrs lv, const float* __restrict__ coord
     const float* s_bias = s_tail + kN * kTail;
     uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(pk + kPackBytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + 1);
+    float* left = reinterpret_cast<float*>(pk + kPackBytes + 16);      // [2][128][4]
     const uint32_t bar = smem_u32(bar_ptr);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int px = tid & (kRows - 1), pair = tid >> 7;                 // warps 0-3: levels 0-1, warps 4-7: levels 2-3
 
     if (warp == 0) {
         if (tid == 0) { ptx::mbar_init(bar, 1); ptx::fence_barrier_init(); }
@@ -615,7 +625,7 @@ corr_lookup_encode_tc_kernel(const LevelPtrs lv, const float* __restrict__ coord
         ptx::tmem_alloc(smem_u32(tmem_slot), kTmemCols);
         ptx::tmem_relinquish();
     }
-    for (int i = tid; i < kPackBytes / 16; i += kLookThreads)
+    for (int i = tid; i < kPackBytes / 16; i += kThreads)
         reinterpret_cast<uint4*>(pk)[i] = __ldg(reinterpret_cast<const uint4*>(packed) + i);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     ptx::tc_fence_before_sync();
@@ -627,31 +637,31 @@ corr_lookup_encode_tc_kernel(const LevelPtrs lv, const float* __restrict__ coord
     uint32_t phase = 0;
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        // ---- the lookup: this thread's 36 taps (a pixel past the end repeats the last one and is not stored)
+        // ---- the lookup: this thread's 18 taps (a pixel past the end repeats the last one and is not stored)
         const int b = tile / tiles_per_sample;
-        const int hw_raw = (tile - b * tiles_per_sample) * kLookThreads + tid;
+        const int hw_raw = (tile - b * tiles_per_sample) * kRows + px;
         const int hw = min(hw_raw, HW - 1);
         const long long p = (long long)b * HW + hw;
         const float c0 = sane_coord(__ldg(coords + b * coords_bstride + hw));
-        float tp[kEncTaps];
-        {
-            Span s1;
+        float tp[18];
+        if (pair == 0) {                                               // warp-uniform
             if (kMode == 2) {
                 SpanOct s0;
                 span_load_oct(s0, lv.p[0], p, c0, 0, W2p);
-                span_load(s1, lv.p[2], p, npix, c0, 2, W2p >> 2, true);
                 span_taps_oct<true>(s0, nullptr, 0, HW, b, 0, W2, tp);
             } else {
                 Span s0;
                 span_load(s0, lv.p[0], p, npix, c0, 0, W2p, true);
-                span_load(s1, lv.p[2], p, npix, c0, 2, W2p >> 2, true);
                 span_taps_reg<true, true>(s0, nullptr, 0, HW, 4, b, 0, W2, tp);
             }
-            span_taps_reg<true, true>(s1, nullptr, 0, HW, 4, b, 2, W2 >> 2, tp + 18);
+        } else {
+            Span s1;
+            span_load(s1, lv.p[2], p, npix, c0, 2, W2p >> 2, true);
+            span_taps_reg<true, true>(s1, nullptr, 0, HW, 4, b, 2, W2 >> 2, tp);
         }
-        // ---- A operand: row = tid, four 16-byte chunks of 8 taps
+        // ---- A operand: row = pixel, this thread's two 16-byte chunks (K = 16 pair .. 16 pair + 15); left-over taps to the table
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -662,10 +672,13 @@ corr_lookup_encode_tc_kernel(const LevelPtrs lv, const float* __restrict__ coord
                 hi[q] = *reinterpret_cast<const uint32_t*>(&h);
                 lo[q] = *reinterpret_cast<const uint32_t*>(&l);
             }
-            const uint32_t off = sw64_offset(tid, 8 * j);
+            const uint32_t off = sw64_offset(px, 16 * pair + 8 * j);
             sts_v4_u32(a_hi + off, hi[0], hi[1], hi[2], hi[3]);
             sts_v4_u32(a_lo + off, lo[0], lo[1], lo[2], lo[3]);
         }
+        float* mine = left + ((phase * kRows + px) * kTail + 2 * pair);
+        mine[0] = tp[16];
+        mine[1] = tp[17];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
         ptx::tc_fence_before_sync();
         __syncthreads();                                               // (also: every warp has read the previous tile's accumulator)
@@ -686,26 +699,24 @@ corr_lookup_encode_tc_kernel(const LevelPtrs lv, const float* __restrict__ coord
             ptx::umma_commit(bar);
         }
         ptx::mbar_wait(bar, phase);
-        phase ^= 1;
         ptx::tc_fence_after_sync();
-        float* o = out + (long long)b * kN * HW + hw;
-        const float t0 = tp[kK], t1 = tp[kK + 1], t2 = tp[kK + 2], t3 = tp[kK + 3];
+        // ---- epilogue: this thread's pixel, outputs 32 pair .. 32 pair + 31 (the warp's TMEM lane quarter is warp % 4 = px / 32)
+        const float4 t4 = *reinterpret_cast<const float4*>(left + (phase * kRows + px) * kTail);
+        phase ^= 1;
+        float* o = out + ((long long)b * kN + 32 * pair) * HW + hw;
+        float v[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 32 * pair, v);
+        if (hw_raw < HW) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float v[32];
-            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + half * 32, v);
-            if (hw_raw < HW) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int oc = half * 32 + i;
-                    const float4 wt = *reinterpret_cast<const float4*>(s_tail + oc * kTail);     // broadcast
-                    float r = fmaf(v[i], inv, s_bias[oc]);
-                    r = fmaf(wt.x, t0, r);
-                    r = fmaf(wt.y, t1, r);
-                    r = fmaf(wt.z, t2, r);
-                    r = fmaf(wt.w, t3, r);
-                    stg_stream_f1(o + (long long)oc * HW, relu ? fmaxf(r, 0.0f) : r);
-                }
+            for (int i = 0; i < 32; ++i) {
+                const int oc = 32 * pair + i;
+                const float4 wt = *reinterpret_cast<const float4*>(s_tail + oc * kTail);         // broadcast
+                float r = fmaf(v[i], inv, s_bias[oc]);
+                r = fmaf(wt.x, t4.x, r);
+                r = fmaf(wt.y, t4.y, r);
+                r = fmaf(wt.z, t4.z, r);
+                r = fmaf(wt.w, t4.w, r);
+                stg_stream_f1(o + (long long)i * HW, relu ? fmaxf(r, 0.0f) : r);
             }
         }
         ptx::tc_fence_before_sync();                                   // the accumulator reads above precede the next tile's MMAs
@@ -1130,20 +1141,20 @@ extern "C" int tcs_corr_lookup_encode_tc(const float* lvl0, const float* lvl1, c
         TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_tc::kSmemBytes));
         TCS_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_encode_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_tc::kSmemBytes));
     );
-    const int tiles_per_sample = ceil_div(H * W1, kLookThreads);
+    const int tiles_per_sample = ceil_div(H * W1, enc_tc::kRows);
     const long long num_tiles = (long long)tiles_per_sample * B;
     TCS_REQUIRE(num_tiles < 0x7fffffffLL, TCS_E_SHAPE, "tcs_corr_lookup_encode_tc: too many pixels");
-    int ctas_per_sm = TCS_ENCODE_TC_MINBLOCKS;                         // 96 registers x 128 threads; 26 KB of shared memory each
+    int ctas_per_sm = TCS_ENCODE_TC_MINBLOCKS;                         // 64 registers x 256 threads; 29 KB of shared memory each
     { const char* e = getenv("TCS_ENCODE_TC_CTAS"); if (e != nullptr && atoi(e) > 0) ctas_per_sm = atoi(e); }
     const long long resident = (long long)ctas_per_sm * num_sms();
     const unsigned grid = (unsigned)(num_tiles < resident ? num_tiles : resident);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const unsigned char* pk = static_cast<const unsigned char*>(packed);
     if ((reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
-        corr_lookup_encode_tc_kernel<2><<<grid, kLookThreads, enc_tc::kSmemBytes, s>>>(lp, coords, coords_bstride, pk, out, H * W1, W2, W2p, relu,
+        corr_lookup_encode_tc_kernel<2><<<grid, enc_tc::kThreads, enc_tc::kSmemBytes, s>>>(lp, coords, coords_bstride, pk, out, H * W1, W2, W2p, relu,
                                                                                         tiles_per_sample, (int)num_tiles);
     else
-        corr_lookup_encode_tc_kernel<1><<<grid, kLookThreads, enc_tc::kSmemBytes, s>>>(lp, coords, coords_bstride, pk, out, H * W1, W2, W2p, relu,
+        corr_lookup_encode_tc_kernel<1><<<grid, enc_tc::kThreads, enc_tc::kSmemBytes, s>>>(lp, coords, coords_bstride, pk, out, H * W1, W2, W2p, relu,
                                                                                         tiles_per_sample, (int)num_tiles);
     TCS_CHECK_LAUNCH("tcs_corr_lookup_encode_tc");
     return 0;
