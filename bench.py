@@ -579,11 +579,16 @@ def run_b200(args):
                     "operand_stream_gbs": operand_bytes / (lookup_ms * 1e-3) / 1e9,
                     "note": "each call re-streams the 16-bit operands from HBM (operand_stream_gbs) and rebuilds every tile's band in TMEM"}
     build_flops = 2.0 * npix * W * C
-    build_bytes = 2 * npix * C * 4 + npix * W * 4 * (1 + 0.5 + 0.25 + 0.125)
+    # levels 1 and 3 are not stored any more (every radius-4 lookup kernel re-pools them from levels 0 and 2): the bytes the build
+    # has to move are the two fp32 maps in and levels 0 and 2 out.  SURVEY.md 8d's figure (all four levels) is kept beside it.
+    lazy_odd = args.mode == "pyramid" and os.environ.get("TCS_B200_LAZY_ODD_LEVELS", "1") != "0" and args.precision != "fp32"
+    build_bytes_all_levels = 2 * npix * C * 4 + npix * W * 4 * (1 + 0.5 + 0.25 + 0.125)
+    build_bytes = 2 * npix * C * 4 + npix * W * 4 * ((1 + 0.25) if lazy_odd else (1 + 0.5 + 0.25 + 0.125))
     warp_bytes = npix * (4 + 1024 + 1024 + 4 + 4 + 4 + 1344)   # disp + prev fmap + cur fmap in; disp', mask, cost out; hidden gather
     phases_out = {
         "build_ms": phase_ms[0], "warp_ms": phase_ms[1], "lookups_ms": phase_ms[2],
-        "build": {"note": ("fused normalise + split + tcgen05 build" if fused_build else "2 pre-passes + tcgen05 build") + ", fp32 fmaps in, fp32 levels out", "algorithmic_bytes": build_bytes,
+        "build": {"note": ("fused normalise + split + tcgen05 build" if fused_build else "2 pre-passes + tcgen05 build") + ", fp32 fmaps in, fp32 levels out" + (" (levels 0 and 2 stored; 1 and 3 re-pooled by the lookup)" if lazy_odd else ""),
+                  "algorithmic_bytes": build_bytes, "algorithmic_bytes_all_four_levels": build_bytes_all_levels,
                   "hbm_gbs": build_bytes / (phase_ms[0] * 1e-3) / 1e9, "hbm_frac": build_bytes / (phase_ms[0] * 1e-3) / 1e9 / pk["hbm_gbs"],
                   "tflops": build_flops / (phase_ms[0] * 1e-3) / 1e12, "tensor_frac": build_flops / (phase_ms[0] * 1e-3) / 1e12 / pk["bf16_tflops"]},
         "warp": {"algorithmic_bytes": warp_bytes, "hbm_gbs": warp_bytes / (phase_ms[1] * 1e-3) / 1e9,

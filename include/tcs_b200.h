@@ -73,7 +73,10 @@ int tcs_corr_prepass_kblocked(const float* fmap, void* hi, void* lo,
  * widths, exactly as avg_pool2d does.
  *   a_hi,a_lo  [B,H,W1,C] operands of the left image  (lo nullable unless prec is *X3)
  *   b_hi,b_lo  [B,H,W2,C] operands of the right image
- *   lvl[l]     [B,H,W1,W2>>l] fp32 (out), l < num_levels <= 4; every level pointer 16-byte aligned
+ *   lvl[l]     [B,H,W1,W2>>l] fp32 (out), l < num_levels <= 4; every level pointer 16-byte aligned.  lvl1 and / or lvl3 may be
+ *              NULL: that level is then not stored (it is still the input of the next one).  tcs_corr_lookup at radius 4 with
+ *              4 levels, tcs_corr_lookup_encode[_tc], tcs_corr_argmax and tcs_corr_cost_volume read levels 0 and 2 only — they
+ *              re-pool the odd levels as (a + b) * 0.5, the expression used here — so a third of the pyramid need not exist
  *   W2_pitch   0 (dense rows) or the row pitch of level 0 in floats (level l: W2_pitch >> l), a multiple of 16 above W2
  *              with W2 % 8 == 0: the columns past W2 of every level are written as exact zeros, which puts widths like the
  *              KITTI shape's 312 on tcs_corr_lookup's predicate-free path (rows that start on 16-byte boundaries)

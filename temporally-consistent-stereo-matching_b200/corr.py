@@ -79,6 +79,46 @@ def level_pitch(W2, num_levels=4, radius=4):
     return W2
 
 
+def _pool_level_into(src, dst):
+    """dst = avg_pool2d(src, [1,2]) (ref: corr.py:21-23) on the PHYSICAL rows of two level views (their pitch may exceed their
+    width: the padding columns are zeros and pool to zeros): (even + odd) * 0.5, the expression the build epilogue uses, so the
+    bits are the ones the build would have stored."""
+    B, H, W1, _ = src.shape
+    ps = torch.as_strided(src, (B, H, W1, src.stride(2)), src.stride(), src.storage_offset())
+    pd = torch.as_strided(dst, (B, H, W1, dst.stride(2)), dst.stride(), dst.storage_offset())
+    n = min(pd.shape[3], ps.shape[3] // 2)
+    pd[..., :n] = (ps[..., 0:2 * n:2] + ps[..., 1:2 * n:2]) * 0.5
+    if n < pd.shape[3]:
+        pd[..., n:] = 0
+
+
+class _Levels(list):
+    """The levels of a pyramid, [B,H,W1,W2>>l] each.  `pending`: the build did not store levels 1 and 3 — the row-aligned
+    lookup kernels re-pool them from levels 0 and 2 on the fly (csrc/corr_lookup.cu), so a third of the pyramid's bytes never
+    has to be written.  Anything that does touch an odd level (an index, a slice, an iteration: corr_pyramid, the tests) gets
+    it pooled from the level below first; raw(l) is for the kernels' pointer arguments."""
+    pending = False
+
+    def raw(self, l):
+        return list.__getitem__(self, l)
+
+    def fill(self):
+        if self.pending:
+            self.pending = False
+            with torch.no_grad():
+                for l in range(1, len(self), 2):
+                    _pool_level_into(list.__getitem__(self, l - 1), list.__getitem__(self, l))
+
+    def __getitem__(self, i):
+        if self.pending and not (isinstance(i, int) and (i % len(self)) % 2 == 0):
+            self.fill()
+        return list.__getitem__(self, i)
+
+    def __iter__(self):
+        self.fill()
+        return list.__iter__(self)
+
+
 def alloc_pyramid(B, H, W1, W2, num_levels, device, pitch=None, zero=False):
     """One flat fp32 buffer holding every level [B,H,W1,W2>>l], each 128-byte aligned (the lookup's 32-byte
     loads need 32) and padded so the lookup may read up to the next 16-byte boundary past a level's end.
@@ -99,9 +139,11 @@ FUSED_MAX_W2 = 240
 FUSED_MAX_W1 = 256
 
 
-def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3", fused=None, pitch=None):
+def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3", fused=None, pitch=None, odd_levels=True):
     """All pyramid levels of the 1-D all-pairs cosine correlation (ref: corr.py:54-62 + :15-23).
 
+    odd_levels=False (4 levels, tensor-core build): levels 1 and 3 are left unwritten (`levels.pending`) for a consumer that
+    re-pools them from levels 0 and 2 - every radius-4 lookup kernel does; see _Levels.
     precision: 'bf16' | 'bf16x3' | 'fp16' | 'fp16x3' (tcgen05 tensor cores) or 'fp32' (CUDA cores).
     fused: None = the single fused kernel (normalise + split + UMMA + pyramid, no operand round trip through HBM)
     whenever the shape allows it (W2 <= 240, W1 <= 256, both multiples of 4), else the pre-pass + build pair;
@@ -122,7 +164,10 @@ def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3", fused=None, pi
     if fused or precision == "fp32":
         pitch = None                                # only the pre-pass + tcgen05 build writes pitched rows
     flat, levels = alloc_pyramid(B, H, W1, W2, num_levels, fmap1.device, pitch=pitch)
-    ptrs = [levels[l].data_ptr() if l < num_levels else None for l in range(4)]
+    levels = _Levels(levels)
+    skip_odd = (not odd_levels) and num_levels == 4 and precision != "fp32"
+    ptrs = [levels.raw(l).data_ptr() if (l < num_levels and not (skip_odd and l % 2 == 1)) else None for l in range(4)]
+    levels.pending = skip_odd
     with torch.cuda.device(fmap1.device):
         if precision == "fp32":
             _, _, a32 = normalized_operands(fmap1, want_hi=False, want_n32=True)
@@ -240,8 +285,10 @@ class CorrBlock1D:
         self._cost_volume = None
         self.W2p = self.W2
         if self.mode == "pyramid":
+            # 4 levels at radius 4 always take the lookup kernels that read only levels 0 and 2 (corr_lookup_r4x4*_kernel)
+            lazy_odd = num_levels == 4 and radius == 4 and os.environ.get("TCS_B200_LAZY_ODD_LEVELS", "1") != "0"
             self._flat, self._levels = build_pyramid(fmap1, fmap2, num_levels, self.precision,
-                                                     pitch=level_pitch(self.W2, num_levels, radius))
+                                                     pitch=level_pitch(self.W2, num_levels, radius), odd_levels=not lazy_odd)
             self.W2p = self._levels[0].stride(2)            # the row pitch the build really used (== W2 when dense)
             self._fmaps = None
         else:
@@ -306,6 +353,11 @@ class CorrBlock1D:
         _, levels = build_pyramid(self._fmaps[0], self._fmaps[1], 1, self.precision)
         return levels[0]
 
+    def _level_ptr(self, l):
+        """Level l's address for a kernel argument (an unwritten odd level stays unwritten: see _Levels)."""
+        lv = self._levels
+        return (lv.raw(l) if isinstance(lv, _Levels) else lv[l]).data_ptr()
+
     def _pitch_arg(self):
         """The row pitch for the C-ABI (0 = dense), read off the level-0 view so that a replaced level is seen."""
         p = self._levels[0].stride(2)
@@ -319,7 +371,7 @@ class CorrBlock1D:
                           dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             if self.mode == "pyramid":
-                ptrs = [self._levels[l].data_ptr() if l < self.num_levels else None for l in range(4)]
+                ptrs = [self._level_ptr(l) if l < self.num_levels else None for l in range(4)]
                 _lib.call("tcs_corr_lookup", *ptrs, cptr, cstride, out.data_ptr(),
                           self.B, self.H, self.W1, self.W2, self.num_levels, self.radius, self._pitch_arg(), _stream())
             elif self._alt_tc:
@@ -348,7 +400,7 @@ class CorrBlock1D:
         bb = bias.detach().float().contiguous() if bias is not None else None
         cout = w.shape[0]
         out = torch.empty((self.B, cout, self.H, self.W1), dtype=torch.float32, device=self.device)
-        ptrs = [self._levels[l].data_ptr() for l in range(4)]
+        ptrs = [self._level_ptr(l) for l in range(4)]
         with torch.cuda.device(self.device):
             tc = os.environ.get("TCS_B200_ENCODE_TC", "auto")          # "0" never, "1" whenever possible, default: when it pays
             if cout == 64 and self.W2p % 16 == 0 and tc != "0" and (tc == "1" or self.B * self.H * self.W1 >= _ENCODE_TC_MIN_PIXELS):

@@ -223,7 +223,8 @@ extern "C" int tcs_corr_build(const void* a_hi, const void* a_lo, const void* b_
     TCS_REQUIRE(num_levels >= 1 && num_levels <= TCS_MAX_LEVELS, TCS_E_SHAPE, "tcs_corr_build: num_levels=%d not in [1,4]", num_levels);
     float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
     for (int l = 0; l < num_levels; ++l)
-        TCS_REQUIRE(lv[l] != nullptr && aligned16(lv[l]), TCS_E_ALIGN, "tcs_corr_build: level %d pointer null or not 16-byte aligned", l);
+        TCS_REQUIRE((lv[l] != nullptr || (l & 1)) && aligned16(lv[l]), TCS_E_ALIGN,
+                    "tcs_corr_build: level %d pointer null or not 16-byte aligned (only the odd levels may be omitted)", l);
     TCS_REQUIRE(B > 0 && H > 0 && W1 > 0 && W2 >= 8 && C > 0, TCS_E_BADARG, "tcs_corr_build: bad sizes");
     TCS_REQUIRE((W2 >> (num_levels - 1)) >= 1, TCS_E_SHAPE, "tcs_corr_build: W2 too small for %d levels", num_levels);
     TCS_REQUIRE(C % kBlockK == 0, TCS_E_SHAPE, "tcs_corr_build: C=%d must be a multiple of 64", C);

@@ -220,7 +220,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpilogueArgs& p, const C
                 const int lim2 = min(n_end >> 2, W2_2);
                 store4(r2, (cg >> 2), lim2, vec2, make_float4(l2[0], l2[1], l2[2], l2[3]));
                 store4(r2, (cg >> 2) + 4, lim2, vec2, make_float4(l2[4], l2[5], l2[6], l2[7]));
-                if (p.num_levels > 3) {
+                if (p.num_levels > 3 && p.lvl[3] != nullptr) {
                     float* r3 = p.lvl[3] + (rbase + row) * W2_3;
                     const int lim3 = min(n_end >> 3, W2_3);
                     store4(r3, (cg >> 3), lim3, vec3,
@@ -551,7 +551,8 @@ extern "C" int tcs_corr_build_fused(const float* fmap1, const float* fmap2,
     TCS_REQUIRE(num_levels >= 1 && num_levels <= TCS_MAX_LEVELS, TCS_E_SHAPE, "tcs_corr_build_fused: num_levels=%d not in [1,4]", num_levels);
     float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
     for (int l = 0; l < num_levels; ++l)
-        TCS_REQUIRE(lv[l] != nullptr && aligned16(lv[l]), TCS_E_ALIGN, "tcs_corr_build_fused: level %d pointer null or not 16-byte aligned", l);
+        TCS_REQUIRE((lv[l] != nullptr || (l & 1)) && aligned16(lv[l]), TCS_E_ALIGN,
+                    "tcs_corr_build_fused: level %d pointer null or not 16-byte aligned (only the odd levels may be omitted)", l);
     TCS_REQUIRE(B > 0 && H > 0 && W1 > 0 && C > 0, TCS_E_BADARG, "tcs_corr_build_fused: bad sizes");
     TCS_REQUIRE(W2 >= 8 && W2 <= kMaxN && W1 <= kMaxW1 && W1 % 4 == 0 && W2 % 4 == 0, TCS_E_SHAPE,
                 "tcs_corr_build_fused: needs 8 <= W2 <= %d, W1 <= %d, both multiples of 4 (got W1=%d W2=%d); use tcs_corr_prepass + tcs_corr_build",
@@ -581,7 +582,7 @@ extern "C" int tcs_corr_build_fused(const float* fmap1, const float* fmap2,
     // TMA stores need 16-byte row strides on both levels; otherwise the epilogue falls back to ordinary stores
     // (measured 373 us vs 354 us for the ordinary stores at 540p x 8: each warp has a single staging box, so the
     // bulk store serialises with the next chunk; opt in with TCS_FUSED_TMA_STORE=1)
-    { const char* e = getenv("TCS_FUSED_TMA_STORE"); p.tma_store = (kEpiStageBytes >= 6144) && (W2 % 8 == 0) && e != nullptr && atoi(e) != 0; }
+    { const char* e = getenv("TCS_FUSED_TMA_STORE"); p.tma_store = (kEpiStageBytes >= 6144) && (W2 % 8 == 0) && e != nullptr && atoi(e) != 0 && (num_levels < 2 || lv[1] != nullptr); }
     CUtensorMap tml0 = tma, tml1 = tma;
     if (p.tma_store) {
         if ((rc = make_level_map(&tml0, lv[0], B * H, W1, W2, 32, CU_TENSOR_MAP_SWIZZLE_128B)) != 0) return rc;

@@ -1,6 +1,8 @@
 // Epilogue shared by the correlation-build kernels: one finished 128 x N accumulator tile in TMEM ->
 // pyramid levels 0..3 in global memory.
 // ref: core/corr.py:15-23 (level l+1 = avg_pool2d(level l, [1,2]) == (even + odd) * 0.5, floor on odd widths).
+// A null pointer for level 1 or level 3 means "do not store it": the row-aligned lookup kernels re-pool the odd levels from
+// the even ones (corr_lookup.cu), so for them a third of the pyramid's bytes need never be written.
 #pragma once
 
 #include "tcs_common.cuh"
@@ -70,7 +72,8 @@ __device__ __forceinline__ void epilogue_tile(const EpilogueArgs& p, uint32_t ta
         float l1[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) l1[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
-        if (!kAliasedStage && p.num_levels > 1) {
+        const bool want1 = p.num_levels > 1 && p.lvl[1] != nullptr;
+        if (!kAliasedStage && want1) {
 #pragma unroll
             for (int s = 0; s < 4; ++s)
                 sts_v4_f32(stage1 + 16u * (lane * 4 + (s ^ ((lane >> 1) & 3))), make_float4(l1[4 * s], l1[4 * s + 1], l1[4 * s + 2], l1[4 * s + 3]));
@@ -88,14 +91,14 @@ __device__ __forceinline__ void epilogue_tile(const EpilogueArgs& p, uint32_t ta
                 }
             }
         }
-        if (kAliasedStage && p.num_levels > 1) {
+        if (kAliasedStage && want1) {
             __syncwarp();   // level-0 reads of the shared staging area are done; reuse it for level 1
 #pragma unroll
             for (int s = 0; s < 4; ++s)
                 sts_v4_f32(stage1 + 16u * (lane * 4 + (s ^ ((lane >> 1) & 3))), make_float4(l1[4 * s], l1[4 * s + 1], l1[4 * s + 2], l1[4 * s + 3]));
             __syncwarp();
         }
-        if (p.num_levels > 1) {
+        if (want1) {
             const int s = lane & 3;
             const int lim = min(n_end >> 1, W2_1);
 #pragma unroll
@@ -120,7 +123,7 @@ __device__ __forceinline__ void epilogue_tile(const EpilogueArgs& p, uint32_t ta
                 const int lim2 = min(n_end >> 2, W2_2);
                 store4(r2, (cg >> 2), lim2, vec2, make_float4(l2[0], l2[1], l2[2], l2[3]));
                 store4(r2, (cg >> 2) + 4, lim2, vec2, make_float4(l2[4], l2[5], l2[6], l2[7]));
-                if (p.num_levels > 3) {
+                if (p.num_levels > 3 && p.lvl[3] != nullptr) {
                     float* r3 = p.lvl[3] + (rbase + row) * W2_3;
                     const int lim3 = min(n_end >> 3, W2_3);
                     store4(r3, (cg >> 3), lim3, vec3,
