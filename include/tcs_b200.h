@@ -108,7 +108,9 @@ int tcs_corr_build_fp32(const float* a_n32, const float* b_n32,
  * F.grid_sample, align_corners=True, zeros padding), including grid_sample's normalise /
  * un-normalise fp32 round trip.
  *   lvl[l]  as written by tcs_corr_build; each level must be readable up to the next 16-byte
- *           boundary past its end (the Python wrapper pads)
+ *           boundary past its end (the Python wrapper pads).  With num_levels == 4 and radius == 4 only levels 0 and 2 are
+ *           read (1 and 3 are re-pooled from them on the fly, bit for bit): lvl1 and lvl3 may then be NULL — here, in
+ *           tcs_corr_lookup_encode and in tcs_corr_lookup_encode_tc
  *   coords  fp32, x coordinate of pixel (b,h,w1) at  coords[b*coords_bstride + h*W1 + w1]
  *           (coords_bstride lets the caller pass channel 0 of a [B,2,H,W1] tensor)
  *   out     [B, num_levels*(2r+1), H, W1] fp32

@@ -107,7 +107,12 @@ class _Levels(list):
             self.pending = False
             with torch.no_grad():
                 for l in range(1, len(self), 2):
-                    _pool_level_into(list.__getitem__(self, l - 1), list.__getitem__(self, l))
+                    src = list.__getitem__(self, l - 1)
+                    if list.__getitem__(self, l) is None:          # same pitch rule as alloc_pyramid: level l rows are pitch >> l wide
+                        B, H, W1, Ws = src.shape
+                        phys = torch.empty((B, H, W1, src.stride(2) >> 1), dtype=torch.float32, device=src.device)
+                        list.__setitem__(self, l, phys[..., :Ws >> 1])
+                    _pool_level_into(src, list.__getitem__(self, l))
 
     def __getitem__(self, i):
         if self.pending and not (isinstance(i, int) and (i % len(self)) % 2 == 0):
@@ -119,19 +124,22 @@ class _Levels(list):
         return list.__iter__(self)
 
 
-def alloc_pyramid(B, H, W1, W2, num_levels, device, pitch=None, zero=False):
+def alloc_pyramid(B, H, W1, W2, num_levels, device, pitch=None, zero=False, skip_odd=False):
     """One flat fp32 buffer holding every level [B,H,W1,W2>>l], each 128-byte aligned (the lookup's 32-byte
     loads need 32) and padded so the lookup may read up to the next 16-byte boundary past a level's end.
     pitch: row pitch of level 0 (level l: pitch >> l); the returned levels are then views of the first W2>>l columns of each
-    row, and whoever fills them must leave zeros in the rest (tcs_corr_build does; zero=True for copies)."""
+    row, and whoever fills them must leave zeros in the rest (tcs_corr_build does; zero=True for copies).
+    skip_odd: levels 1 and 3 get no storage (None in the returned list; _Levels.fill allocates them if ever asked for)."""
     P = pitch or W2
     sizes = [B * H * W1 * (P >> l) for l in range(num_levels)]
     offs, total = [], 0
-    for s in sizes:
+    for l, s in enumerate(sizes):
         offs.append(total)
-        total += (_pad16(s) + 4 + 31) & ~31
+        if not (skip_odd and l % 2 == 1):
+            total += (_pad16(s) + 4 + 31) & ~31
     flat = (torch.zeros if (zero and P != W2) else torch.empty)(total, dtype=torch.float32, device=device)
-    levels = [flat[o:o + s].view(B, H, W1, P >> l)[..., :W2 >> l] for l, (o, s) in enumerate(zip(offs, sizes))]
+    levels = [None if (skip_odd and l % 2 == 1) else flat[o:o + s].view(B, H, W1, P >> l)[..., :W2 >> l]
+              for l, (o, s) in enumerate(zip(offs, sizes))]
     return flat, levels
 
 
@@ -163,10 +171,10 @@ def build_pyramid(fmap1, fmap2, num_levels=4, precision="bf16x3", fused=None, pi
         fused = fits and precision != "fp32" and os.environ.get("TCS_B200_FUSED_BUILD", "1") != "0"
     if fused or precision == "fp32":
         pitch = None                                # only the pre-pass + tcgen05 build writes pitched rows
-    flat, levels = alloc_pyramid(B, H, W1, W2, num_levels, fmap1.device, pitch=pitch)
-    levels = _Levels(levels)
     skip_odd = (not odd_levels) and num_levels == 4 and precision != "fp32"
-    ptrs = [levels.raw(l).data_ptr() if (l < num_levels and not (skip_odd and l % 2 == 1)) else None for l in range(4)]
+    flat, levels = alloc_pyramid(B, H, W1, W2, num_levels, fmap1.device, pitch=pitch, skip_odd=skip_odd)
+    levels = _Levels(levels)
+    ptrs = [levels.raw(l).data_ptr() if (l < num_levels and levels.raw(l) is not None) else None for l in range(4)]
     levels.pending = skip_odd
     with torch.cuda.device(fmap1.device):
         if precision == "fp32":
@@ -356,7 +364,8 @@ class CorrBlock1D:
     def _level_ptr(self, l):
         """Level l's address for a kernel argument (an unwritten odd level stays unwritten: see _Levels)."""
         lv = self._levels
-        return (lv.raw(l) if isinstance(lv, _Levels) else lv[l]).data_ptr()
+        t = lv.raw(l) if isinstance(lv, _Levels) else lv[l]
+        return None if t is None else t.data_ptr()
 
     def _pitch_arg(self):
         """The row pitch for the C-ABI (0 = dense), read off the level-0 view so that a replaced level is seen."""

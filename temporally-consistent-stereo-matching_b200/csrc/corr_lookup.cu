@@ -1018,15 +1018,19 @@ corr_cost_volume_kernel(const float* __restrict__ lvl0, float* __restrict__ out,
 
 // ================================================ C ABI ==================================================
 
+// odd_optional: the caller's kernels read only levels 0 and 2 when num_levels == 4 and radius == 4 (they re-pool 1 and 3), so
+// those two pointers may be NULL (a pyramid built without them, see tcs_corr_build).
 static int check_lookup_args(const char* fn, const float* const* lv, const float* coords, const float* out,
-                             int B, int H, int W1, int W2, int num_levels, int radius) {
+                             int B, int H, int W1, int W2, int num_levels, int radius, bool odd_optional = false) {
     using namespace tcs;
     TCS_REQUIRE(coords != nullptr && out != nullptr, TCS_E_BADARG, "%s: null coords/out", fn);
     TCS_REQUIRE(num_levels >= 1 && num_levels <= TCS_MAX_LEVELS, TCS_E_SHAPE, "%s: num_levels=%d not in [1,4]", fn, num_levels);
     TCS_REQUIRE(radius >= 0 && radius <= TCS_MAX_RADIUS, TCS_E_SHAPE, "%s: radius=%d not in [0,8]", fn, radius);
     TCS_REQUIRE(B > 0 && H > 0 && W1 > 0 && (W2 >> (num_levels - 1)) >= 2, TCS_E_SHAPE, "%s: bad sizes (coarsest level needs width >= 2)", fn);
+    const bool skip_odd = odd_optional && num_levels == 4 && radius == 4;
     for (int l = 0; l < num_levels; ++l)
-        TCS_REQUIRE(lv[l] != nullptr && aligned16(lv[l]), TCS_E_ALIGN, "%s: level %d pointer null or not 16-byte aligned", fn, l);
+        TCS_REQUIRE((lv[l] != nullptr || (skip_odd && (l & 1))) && aligned16(lv[l]), TCS_E_ALIGN,
+                    "%s: level %d pointer null or not 16-byte aligned", fn, l);
     return 0;
 }
 
@@ -1035,7 +1039,7 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
                                int B, int H, int W1, int W2, int num_levels, int radius, int W2_pitch, void* stream) {
     using namespace tcs;
     const float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
-    int rc = check_lookup_args("tcs_corr_lookup", lv, coords, out, B, H, W1, W2, num_levels, radius);
+    int rc = check_lookup_args("tcs_corr_lookup", lv, coords, out, B, H, W1, W2, num_levels, radius, true);
     if (rc != 0) return rc;
     const int W2p = W2_pitch > 0 ? W2_pitch : W2;
     TCS_REQUIRE(W2p == W2 || (num_levels == 4 && radius == 4 && W2p > W2 && W2p % 16 == 0 && W2 % 8 == 0), TCS_E_SHAPE,
@@ -1082,7 +1086,7 @@ extern "C" int tcs_corr_lookup_encode(const float* lvl0, const float* lvl1, cons
                                       int radius, int Cout, int relu, int W2_pitch, void* stream) {
     using namespace tcs;
     const float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
-    int rc = check_lookup_args("tcs_corr_lookup_encode", lv, coords, out, B, H, W1, W2, num_levels, radius);
+    int rc = check_lookup_args("tcs_corr_lookup_encode", lv, coords, out, B, H, W1, W2, num_levels, radius, true);
     if (rc != 0) return rc;
     const int W2p = W2_pitch > 0 ? W2_pitch : W2;
     TCS_REQUIRE(W2p == W2 || (W2p > W2 && W2p % 16 == 0 && W2 % 8 == 0), TCS_E_SHAPE,
@@ -1128,7 +1132,7 @@ extern "C" int tcs_corr_lookup_encode_tc(const float* lvl0, const float* lvl1, c
                                          int B, int H, int W1, int W2, int relu, int W2_pitch, void* stream) {
     using namespace tcs;
     const float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
-    int rc = check_lookup_args("tcs_corr_lookup_encode_tc", lv, coords, out, B, H, W1, W2, 4, 4);
+    int rc = check_lookup_args("tcs_corr_lookup_encode_tc", lv, coords, out, B, H, W1, W2, 4, 4, true);
     if (rc != 0) return rc;
     TCS_REQUIRE(packed != nullptr && aligned16(packed), TCS_E_BADARG, "tcs_corr_lookup_encode_tc: packed weights null or unaligned");
     const int W2p = W2_pitch > 0 ? W2_pitch : W2;

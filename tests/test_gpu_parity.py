@@ -925,3 +925,35 @@ def test_init_loss_kernel_matches_the_oracle_on_the_golden_case(tcs, precision):
 def test_init_loss_refuses_a_plain_tensor(tcs):
     with pytest.raises(TypeError):
         tcs.init_loss(torch.zeros(1, 8, 2, 8, device="cuda"), torch.zeros(1, 1, 8, 32, device="cuda"), torch.ones(1, 1, 8, 32, device="cuda"))
+
+
+@pytest.mark.parametrize("B,H,W1,W2", [(2, 9, 240, 240), (1, 5, 248, 248), (1, 4, 100, 78)])
+def test_odd_levels_are_not_stored_until_asked_for(tcs, monkeypatch, B, H, W1, W2):
+    """Every radius-4, 4-level lookup kernel reads levels 0 and 2 only (it re-pools 1 and 3), so the build leaves the odd levels
+    unwritten and unallocated; lookups, the fused 1x1, argmax and the cost volume do not need them, and whatever does ask for one
+    gets exactly what the build would have stored (dense, pitched and odd widths)."""
+    g = torch.Generator().manual_seed(W2)
+    f1, f2 = torch.randn(B, 128, H, W1, generator=g).cuda(), torch.randn(B, 128, H, W2, generator=g).cuda()
+    coords = make_coords(B, H, W1, 4).cuda()
+    w = torch.randn(64, 36, device="cuda") * 0.2
+    lazy = tcs.CorrBlock1D(f1, f2)
+    assert lazy._levels.pending and lazy._levels.raw(1) is None and lazy._levels.raw(3) is None
+    out, enc, amax = lazy(coords), lazy.lookup_encoded(coords, w), lazy.argmax_disp()
+    cv = lazy.get_cost_volume()
+    assert lazy._levels.pending, "a consumer that does not need the odd levels materialised them"
+    monkeypatch.setenv("TCS_B200_LAZY_ODD_LEVELS", "0")
+    full = tcs.CorrBlock1D(f1, f2)
+    assert not full._levels.pending
+    assert torch.equal(out, full(coords)) and torch.equal(enc, full.lookup_encoded(coords, w)) and torch.equal(cv, full.get_cost_volume())
+    for a, b in zip(amax, full.argmax_disp()):
+        assert torch.equal(a, b)
+    pyr = lazy.corr_pyramid                                            # the reference's attribute: asks for every level
+    assert not lazy._levels.pending
+    for l in range(4):
+        assert torch.equal(lazy._levels[l], full._levels[l]), "level %d" % l
+        assert lazy._levels[l].stride() == full._levels[l].stride()
+        assert pyr[l].shape == (B * H * W1, 1, 1, W2 >> l)
+    # the general-radius kernel reads every level: such a block stores them all
+    monkeypatch.delenv("TCS_B200_LAZY_ODD_LEVELS")
+    r3 = tcs.CorrBlock1D(f1, f2, radius=3)
+    assert not r3._levels.pending
