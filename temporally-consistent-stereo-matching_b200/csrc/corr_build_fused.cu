@@ -36,7 +36,7 @@ constexpr int kUmmaK = 16;
 constexpr int kMaxN = 240;                          // one N tile
 constexpr int kMaxW1 = 256;
 #ifndef TCS_FUSED_CTAS
-#define TCS_FUSED_CTAS 1                            // CTAs per SM: 2 = half-size CTAs whose norm and convert passes interleave on the SM
+#define TCS_FUSED_CTAS 2                            // CTAs per SM: 2 = half-size CTAs whose norm and convert passes interleave on the SM
 #endif
 constexpr int kCtasPerSm = TCS_FUSED_CTAS;
 constexpr int kStages = kCtasPerSm == 2 ? 1 : 2;    // operand tile stages
@@ -56,7 +56,7 @@ constexpr int kAccStages = kCtasPerSm == 2 ? 1 : 2;
 constexpr int kAccCols = 256;
 constexpr int kTmemCols = kAccStages * kAccCols;
 #ifndef TCS_FUSED_CONV_WARPS
-#define TCS_FUSED_CONV_WARPS (TCS_FUSED_CTAS == 2 ? 6 : 10)
+#define TCS_FUSED_CONV_WARPS (TCS_FUSED_CTAS == 2 ? 8 : 10)
 #endif
 constexpr int kConvWarps = TCS_FUSED_CONV_WARPS;
 constexpr int kConvThreads = kConvWarps * 32;       // 320
@@ -599,7 +599,7 @@ extern "C" int tcs_corr_build_fused(const float* fmap1, const float* fmap2,
     p.tile_mode = kCtasPerSm == 2 ? 1 : 0;
     { const char* e = getenv("TCS_FUSED_TILE_MODE"); if (e != nullptr) p.tile_mode = atoi(e) != 0; }
     p.stagger_ns = 0;
-    if (kCtasPerSm == 2 && grid > num_sms()) { const char* e = getenv("TCS_FUSED_STAGGER_NS"); p.stagger_ns = e != nullptr ? atoi(e) : 10000; }
+    if (kCtasPerSm == 2 && grid > num_sms()) { const char* e = getenv("TCS_FUSED_STAGGER_NS"); p.stagger_ns = e != nullptr ? atoi(e) : 5000; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (fp16) corr_build_fused_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(tma, tmb, tml0, tml1, p);
     else corr_build_fused_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(tma, tmb, tml0, tml1, p);
