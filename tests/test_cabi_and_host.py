@@ -265,3 +265,34 @@ def test_bench_reference_gpu_arm_degrades_without_a_gpu():
     assert r.returncode == 0, r.stderr
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert d["impl"] == "reference-gpu" and "unavailable" in d
+
+
+def test_unstored_odd_levels_materialise_as_the_pooled_level_below():
+    """corr._Levels (host logic, no GPU): levels 1 and 3 that the build did not store are allocated and pooled from the level
+    below on first touch - (even + odd) * 0.5 on the physical rows, i.e. F.avg_pool2d's values (ref: corr.py:21-23), pitch and zero
+    padding included; even levels never trigger it."""
+    import torch
+    import torch.nn.functional as F
+    from tcs_b200 import corr
+    g = torch.Generator().manual_seed(0)
+    for W2, P in ((40, 40), (24, 32), (77, 77)):                      # dense, pitched (zeros past W2), odd width
+        B, H, W1 = 2, 3, 5
+        phys0 = torch.zeros(B, H, W1, P)
+        phys0[..., :W2] = torch.randn(B, H, W1, W2, generator=g)
+        lv0 = phys0[..., :W2]
+        phys2 = torch.zeros(B, H, W1, P >> 2)
+        lv1_ref = F.avg_pool2d(lv0.reshape(-1, 1, 1, W2), [1, 2], stride=[1, 2]).reshape(B, H, W1, W2 >> 1)
+        lv2_ref = F.avg_pool2d(lv1_ref.reshape(-1, 1, 1, W2 >> 1), [1, 2], stride=[1, 2]).reshape(B, H, W1, W2 >> 2)
+        phys2[..., :W2 >> 2] = lv2_ref
+        levels = corr._Levels([lv0, None, phys2[..., :W2 >> 2], None])
+        levels.pending = True
+        assert levels[0] is lv0 and levels[2].shape[-1] == W2 >> 2 and levels[-2] is levels.raw(2)
+        assert levels.pending and levels.raw(1) is None, "an even level materialised the odd ones"
+        lv1 = levels[1]
+        assert not levels.pending and levels.raw(3) is not None
+        assert torch.equal(lv1, lv1_ref) and lv1.stride(2) == P >> 1
+        lv3_ref = F.avg_pool2d(lv2_ref.reshape(-1, 1, 1, W2 >> 2), [1, 2], stride=[1, 2]).reshape(B, H, W1, W2 >> 3)
+        assert torch.equal(levels[3], lv3_ref) and levels[3].stride(2) == P >> 3
+        full1 = torch.as_strided(lv1, (B, H, W1, P >> 1), lv1.stride(), lv1.storage_offset())
+        assert float(full1[..., W2 >> 1:].abs().sum()) == 0.0, "padding columns must stay zero"
+        assert [tuple(x.shape) for x in levels] == [(B, H, W1, W2 >> l) for l in range(4)]
