@@ -18,7 +18,11 @@
 //                 per pipeline stage; fence.proxy.async + mbarrier arrive hand the stage to the MMA thread.
 //   warps 12..15  epilogue, shared with corr_build.cu (corr_epilogue.cuh); optional TMA-store variant below.
 //
-// A tile is one (b,h) row x 128 w1 x all w2 (W2 <= 240 fits one UMMA N); a CTA walks whole rows so that the
+// The sizes above are those of ONE CTA per SM (TCS_FUSED_CTAS=1).  The default is TWO half-size CTAs per SM (one operand stage,
+// one accumulator stage, 2 + 2 staging slots, 8 converter warps, 448 threads, 114 KB each; work dealt tile by tile; the second
+// half of the grid starts 5 us late): while one CTA of the pair is in its DRAM-bound norm pass the other converts, multiplies and
+// stores.  0.255 against 0.277 ms at 540p x 8 and never slower on the shapes that take this kernel.
+// A tile is one (b,h) row x 128 w1 x all w2 (W2 <= 240 fits one UMMA N); a one-per-SM CTA walks whole rows so that the
 // norms are computed once per row.  x / ||x|| is evaluated as x * (1 / ||x||) here (one rounding more than
 // the pre-pass's exact division, far below the 16-bit split that follows).
 #include "tcs_common.cuh"
