@@ -402,11 +402,19 @@ __device__ __forceinline__ void span_taps_oct(const SpanOct& sp, float* __restri
 #ifndef TCS_LOOKUP_MINBLOCKS
 #define TCS_LOOKUP_MINBLOCKS 8
 #endif
+#ifndef TCS_LOOKUP_PDL
+#define TCS_LOOKUP_PDL 1
+#endif
 
 __global__ void __launch_bounds__(kLookThreads, TCS_LOOKUP_MINBLOCKS)
 corr_lookup_r4x4o_kernel(const LevelPtrs lv, const float* __restrict__ coords, long long coords_bstride,
                          float* __restrict__ out, int HW, int W2, int W2p) {   // W2p: row pitch of level 0 (>= W2, zeros beyond W2)
     const int b = blockIdx.z;
+#if TCS_LOOKUP_PDL
+    // Programmatic dependent launch: this grid's CTAs may be scheduled while the previous kernel of the stream drains; nothing is
+    // read before that kernel has completed and flushed (wait), and the NEXT kernel may start launching at once.
+    pdl_wait_then_release();
+#endif
     const int hw = blockIdx.x * blockDim.x + threadIdx.x;           // launched with kLookThreads, or 32 for a small frame
     if (hw >= HW) return;
     const long long npix = (long long)gridDim.z * HW;
@@ -1064,8 +1072,13 @@ extern "C" int tcs_corr_lookup(const float* lvl0, const float* lvl1, const float
         const long long ctas128 = (long long)grid.x * 2 * B;
         const int threads = (small_cta > 0 && ctas128 < 8LL * num_sms()) ? 32 : kLookThreads;
         const dim3 grid2((unsigned)ceil_div(H * W1, threads), 2, B);
-        if (num_levels == 4 && W2p % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0)
+        if (num_levels == 4 && W2p % 16 == 0 && (reinterpret_cast<uintptr_t>(lvl0) & 31) == 0) {
+#if TCS_LOOKUP_PDL
+            TCS_CHECK_CUDA(launch_pdl(corr_lookup_r4x4o_kernel, grid2, dim3(threads), 0, s, lp, coords, coords_bstride, out, H * W1, W2, W2p));
+#else
             corr_lookup_r4x4o_kernel<<<grid2, threads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, W2p);
+#endif
+        }
         else if (num_levels == 4 && W2p % 16 == 0)
             corr_lookup_r4x4_kernel<true><<<grid2, threads, 0, s>>>(lp, coords, coords_bstride, out, H * W1, W2, W2p);
         else if (num_levels == 4)     // any width: span in registers, no shared memory (+2 % in the step)

@@ -87,6 +87,33 @@ __device__ __forceinline__ float div_by_const(float x, float c, float rc) {
     return __fmaf_rn(r, rc, q0);
 }
 
+// Programmatic dependent launch.  A kernel launched with launch_pdl() may have its CTAs scheduled while the previous kernel of the
+// stream is still draining; pdl_wait_then_release() at its top blocks until that kernel has completed and its writes are visible
+// (so nothing changes semantically) and lets the NEXT programmatic launch begin.  In a kernel launched the ordinary way both
+// instructions are no-ops.  Worth 1-2 us per kernel boundary, i.e. something for chains of short kernels.
+__device__ __forceinline__ void pdl_wait_then_release() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... Exp, typename... Act>
+inline cudaError_t launch_pdl_if(bool pdl, void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Act&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;            // without the attribute this is an ordinary stream-ordered launch
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
+}
+template <typename... Exp, typename... Act>
+inline cudaError_t launch_pdl(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Act&&... args) {
+    return launch_pdl_if(true, kernel, grid, block, smem, s, static_cast<Act&&>(args)...);
+}
+
 // Packed pairs of fp32 (sm_100: FADD2 / FMUL2 / FFMA2 — one issue slot for two independent lanes).  Round-to-nearest, nothing
 // contracted: each lane's result is bit-identical to the scalar __fadd_rn / __fmul_rn / __fmaf_rn.
 struct f32x2 { uint64_t v; };
